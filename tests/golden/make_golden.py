@@ -218,6 +218,7 @@ def crafted_cases(rng):
     add_veh(s, 1, 100.0)
     s["head_lane"][4] = 4; s["head_j"][4] = 0
     tab = np.full((64, 12), 1e6)
+    tab[0:3] = np.array([[1.0], [2.0], [3.0]])      # ascending prefix: the table stays valid
     tab[3, 4] = 49.95   # spawns on lane 4 at this tick (tick 501 -> t=50.1)
     tab[3, 6] = 50.1000001
     tab[3, 7] = 50.0
