@@ -1,0 +1,168 @@
+/*
+ * pve_mcc.h -- C ABI of the B200-native batched PVE-MCC environment step.
+ *
+ * The reference (Mingtzge/PVE-MCC_for_unsignalized_intersection) has no plugin/FFI boundary:
+ * its de-facto interface is the Python object `TrafficInteraction` as consumed by main.py.
+ * Each entry point below names the reference member it replaces ("TIS" =
+ * traffic_interaction_scene.py, "MAIN" = main.py).  One handle = B independent 12-lane
+ * intersections resident on one GPU.  All `*_dev` pointers are device pointers (torch
+ * `data_ptr()`); `stream` is a `cudaStream_t` passed as `void*`.  No call synchronises the
+ * device unless it says so.  Every function returns 0 on success, a negative PVE_E* code
+ * otherwise; `pve_last_error()` returns the message.
+ *
+ * Vehicle slots are DENSE per intersection, ordered (lane ascending, j ascending) -- the order in
+ * which MAIN:398-406 iterates `env.veh_info` and therefore the order of the action vector.
+ */
+#ifndef PVE_MCC_H
+#define PVE_MCC_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PVE_NLANE 12
+#define PVE_OBS_H 7          /* ego row + 6 neighbour rows        TIS:1295 */
+#define PVE_OBS_W 28         /* (6 + 1) * 4 values per row        TIS:1295 */
+#define PVE_NNBR 6           /* closer_veh_num / o_agent_num      TIS:187, MAIN:90 */
+#define PVE_HDR_BYTES 144    /* packed per-intersection header, see pve_env_header */
+#define PVE_NEVER 2147483647 /* spawn tick of an exhausted arrival table */
+
+#define PVE_OK 0
+#define PVE_EINVAL -1
+#define PVE_ECUDA -2
+#define PVE_ENOMEM -3
+#define PVE_ESTATE -4
+
+/* status bits of one agent row */
+#define PVE_ST_DONE 1        /* veh["Done"] after scene_update            TIS:347, 351 */
+#define PVE_ST_REMOVED 2     /* scheduled in delete_veh                   TIS:348      */
+#define PVE_ST_FINISHED 4    /* crossed p < 0 this tick; jerk_sum valid   TIS:350-359  */
+
+/* vehicle flag bits inside pve meta.packed (bits 24..31) */
+#define PVE_F_CONTROL 1
+#define PVE_F_FINISH 2
+#define PVE_F_LOCK 4
+/* bits 3..4: lock_a + 1 */
+
+/*
+ * Construction parameters: replaces TrafficInteraction.__init__ (TIS:21-220, 12-lane branch
+ * TIS:146-186).  The geometry constants are supplied by the host so that they are computed
+ * with the reference's own expressions (see the Python `SceneConfig`); `pve_default_config`
+ * fills them with libm for C callers.
+ */
+typedef struct pve_config {
+    int32_t n_envs;        /* B: intersections on this GPU                                   */
+    int32_t veh_cap;       /* dense vehicle slots per intersection (<= 1024)                  */
+    int32_t agent_cap;     /* controlled vehicles per intersection (<= veh_cap)               */
+    int32_t threads;       /* CTA size: 0 = default, else 64 / 128 / 256                      */
+    int64_t out_cap;       /* rows of the per-agent output arrays the caller will provide     */
+    double dt, dt2;        /* deltaT and pow(deltaT, 2)                        TIS:21, 1529   */
+    double vm, vM, am, aM, v0;                                             /* TIS:21          */
+    double collision_thr;  /* args.collision_thr                               TIS:32         */
+    double lane_in;        /* lane_info[m][0] = dis_ctl - 6*lane_cw            TIS:149        */
+    double lane_len[3];    /* lane_info[m][1]                                  TIS:149-151    */
+    double remove_p;       /* -dis_ctl + int((12+1)/2)*lane_cw                 TIS:341-342    */
+    double lane_cw;
+    /* get_virtual_distance (TIS:733-803) as delta = (p1 - a1) + a2; member iff delta > 0;
+     * vd = b + delta.  First index: ego movement 0 = left, 1 = straight; second: k in lane2lane */
+    double vd_a1[2][4], vd_a2[2][4], vd_b[2][4];
+    double rot_cos[4], rot_sin[4];   /* cos/sin(3.141593/2 * approach)         TIS:1251, 1287 */
+} pve_config;
+
+/* Per-intersection header as stored on the device (little endian, 144 bytes). */
+typedef struct pve_env_header {
+    int32_t tick;                 /* scene updates done so far (TIS:223 as an integer)        */
+    int32_t id_seq;               /* TIS:212, 433 */
+    int32_t passed_veh;           /* TIS:197, 356 */
+    int32_t overflow;             /* arrivals dropped because a capacity was reached (sticky) */
+    int64_t passed_step_total;    /* TIS:198, 359 */
+    int32_t n_veh, n_ctrl;        /* vehicles / controlled vehicles now                       */
+    int32_t next_spawn[PVE_NLANE];/* spawn tick of row veh_rec[i] of lane i                   */
+    uint16_t veh_rec[PVE_NLANE];  /* TIS:207, 430 */
+    uint8_t lane_n[PVE_NLANE];    /* len(veh_info[i]) */
+    int8_t head_lane[PVE_NLANE];  /* virtual_lane_4[d][0][1], -1 if the list is empty TIS:1517 */
+    uint8_t head_j[PVE_NLANE];    /* virtual_lane_4[d][0][2] (index BEFORE last removal)      */
+    uint8_t pad_[4];
+} pve_env_header;
+
+/* Per-vehicle integer record: {uid, packed}; packed = step (bits 0..15, saturating) |
+ * collision (bits 16..23, saturating) | flags (bits 24..31). */
+typedef struct pve_veh_meta { int32_t uid; uint32_t packed; } pve_veh_meta;
+
+/* Raw state for teacher forcing / snapshots (replaces direct access to env.veh_info,
+ * SURVEY.md H7).  Pointers may be host or device memory. */
+typedef struct pve_state_view {
+    pve_env_header *hdr;          /* [B] */
+    double *p, *v, *a, *jerk_sum; /* [B][veh_cap]  TIS:403, 410, 411, 405 */
+    pve_veh_meta *meta;           /* [B][veh_cap]  */
+    float *row0;                  /* [B][veh_cap][28]  veh["state"][0] (TIS:288) */
+} pve_state_view;
+
+/*
+ * Outputs of one tick: replaces the 9-tuple of scene_update (TIS:376).  Rows of intersection b
+ * are agent_offset[b] .. agent_offset[b+1]-1, in the reference's order (lane asc, j asc).
+ *   actions  (TIS:290)  == obs[:, :, 2]              estm_collisions (TIS:338) == 0
+ *   jerks    (TIS:358)  == jerk_sum[status & FINISHED]
+ */
+typedef struct pve_outputs {
+    int32_t *agent_offset;  /* [B+1]                                                          */
+    float *obs;             /* [out_cap][7][28]   re_state                       TIS:289      */
+    float *reward;          /* [out_cap]          incl. -10 / +5 overrides       TIS:320-357  */
+    int32_t *ids;           /* [out_cap][4]       env, lane, j (pre-removal), uid TIS:291     */
+    int32_t *cpv;           /* [out_cap]          collisions_per_veh[k][0]       TIS:339      */
+    uint8_t *status;        /* [out_cap]          PVE_ST_* bits                               */
+    float *jerk_sum;        /* [out_cap]          veh["jerk_sum"] after the tick TIS:321      */
+    int32_t *env_collisions;/* [B]  `collisions`                                 TIS:337      */
+    int32_t *env_lock;      /* [B]  `lock`                                       TIS:365-370  */
+    int32_t *env_removed;   /* [B]  len(delete_veh)                              TIS:348      */
+} pve_outputs;
+
+/* End-of-rollout statistics (MAIN:407-415, 566-581), summed over the handle's intersections.
+ * Multi-GPU callers all-reduce this 16-double vector (NCCL sum). */
+typedef struct pve_counters {
+    double agent_steps, vehicle_steps, env_steps, spawned, passed, passed_step_total,
+        passed_jerk_sum, collided_agent_steps, lock_events, reward_sum, reward_sq_sum,
+        removed, overflow, q5_undefined, reserved0, reserved1;
+} pve_counters;
+
+typedef struct pve_scene pve_scene;
+
+const char *pve_backend(void);                 /* "cuda-sm_100a" (or the test-only emulation) */
+int32_t pve_default_config(pve_config *cfg, int32_t n_envs, double vm);
+int32_t pve_create(const pve_config *cfg, int32_t device, pve_scene **out);
+void pve_destroy(pve_scene *s);
+const char *pve_last_error(const pve_scene *s);
+
+/* TrafficInteraction(arrive_time, ...) TIS:195-220.  spawn_tick_dev: int32 [B][K][12] built by
+ * the host from the arrival tables; borrowed, must outlive the rollout.
+ * warmup != 0 advances every intersection to its first arrival like TIS:214-220. */
+int32_t pve_reset(pve_scene *s, const int32_t *spawn_tick_dev, int32_t K, int32_t warmup, void *stream);
+
+/* step(i, j, a) for every vehicle (TIS:1501, MAIN:398-406) + scene_update() (TIS:222) +
+ * delete_vehicle() (TIS:435).  actions_dev: float [B][veh_cap]. */
+int32_t pve_step(pve_scene *s, const float *actions_dev, const pve_outputs *out_dev, void *stream);
+
+/* Same tick through HOST buffers: copies actions host->device, runs the tick, copies the
+ * selected outputs device->host and synchronises.  `copy_mask` bit0: reward/ids/cpv/status/
+ * jerk_sum/agent_offset/env_* ; bit1: obs.  `out_host` arrays need `pve_next_agent_total()` rows. */
+int32_t pve_step_host(pve_scene *s, const float *actions_host, const pve_outputs *out_dev,
+                      const pve_outputs *out_host, int32_t copy_mask, void *stream);
+
+/* rows the NEXT pve_step will emit (device scan result; synchronises `stream`) */
+int64_t pve_next_agent_total(pve_scene *s, void *stream);
+
+int32_t pve_set_state(pve_scene *s, const pve_state_view *in, void *stream);
+int32_t pve_get_state(pve_scene *s, const pve_state_view *out, void *stream);
+
+/* device views for a device-side actor: stored row 0 of every slot, and the packed meta */
+const float *pve_row0_dev(const pve_scene *s);
+const pve_veh_meta *pve_meta_dev(const pve_scene *s);
+const pve_env_header *pve_hdr_dev(const pve_scene *s);
+
+int32_t pve_stats(pve_scene *s, pve_counters *out_dev, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

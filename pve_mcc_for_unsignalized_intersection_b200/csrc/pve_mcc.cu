@@ -1,0 +1,587 @@
+/*
+ * pve_mcc.cu -- C ABI (include/pve_mcc.h) and kernel launches of the batched PVE-MCC
+ * environment step for B200 (sm_100a).
+ *
+ * Build (see __graft_entry__.build):
+ *   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -fmad=false -shared
+ *        -Xcompiler -fPIC -I include pve_mcc.cu -o libpve_mcc.so
+ *
+ * With -DPVE_HOST_EMULATION and g++ the same file builds the sequential kernel-logic
+ * emulation used ONLY by the CPU test tier (tests/emul/); pve_backend() tells them apart and
+ * the Python product wrapper refuses anything but the CUDA backend.
+ */
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <new>
+
+#include "scene_step.cuh"
+
+#ifndef PVE_HOST_EMULATION
+#include <cuda_runtime.h>
+#define PVE_BACKEND "cuda-sm_100a"
+typedef cudaStream_t pve_stream_t;
+#else
+#define PVE_BACKEND "host-emulation(test-only)"
+typedef void *pve_stream_t;
+#endif
+
+namespace {
+
+const int8_t kLane2Lane[PVE_NLANE][4] = {            /* TIS:153-166 */
+    {10, 3, 9, 7}, {10, 6, 3, 4}, {-1, -1, -1, -1}, {1, 6, 0, 10}, {1, 9, 6, 7}, {-1, -1, -1, -1},
+    {4, 9, 3, 1},  {4, 0, 9, 10}, {-1, -1, -1, -1}, {7, 0, 6, 4},  {7, 3, 0, 1}, {-1, -1, -1, -1}};
+
+}  // namespace
+
+struct pve_scene {
+    pve_config cfg;
+    PveParams prm;
+    PveState st;
+    int device;
+    int threads;
+    size_t smem_bytes;
+    int phase;
+    const int32_t *spawn_tick;   /* borrowed */
+    float *actions_dev;          /* staging for pve_step_host */
+    double *counters_dev;
+    int32_t *pinned_i32;         /* host-visible scratch: [0] next agent total */
+    int64_t next_total;          /* rows of the next tick if known, else -1 */
+    char err[512];
+};
+
+/* =============================================================================================
+ * runtime layer: CUDA, or plain host memory for the test-only emulation
+ * =========================================================================================== */
+#ifndef PVE_HOST_EMULATION
+#define RT_CHECK(s, call)                                                                     \
+    do {                                                                                      \
+        cudaError_t e_ = (call);                                                              \
+        if (e_ != cudaSuccess) {                                                              \
+            snprintf((s)->err, sizeof((s)->err), "%s failed: %s (%s:%d)", #call,              \
+                     cudaGetErrorString(e_), __FILE__, __LINE__);                             \
+            return PVE_ECUDA;                                                                 \
+        }                                                                                     \
+    } while (0)
+static cudaError_t rt_alloc(void **p, size_t n) { return cudaMalloc(p, n ? n : 16); }
+static void rt_free(void *p) { if (p) cudaFree(p); }
+static cudaError_t rt_memset(void *p, int v, size_t n, pve_stream_t s) { return cudaMemsetAsync(p, v, n, s); }
+static cudaError_t rt_copy(void *d, const void *s, size_t n, pve_stream_t st) {
+    return cudaMemcpyAsync(d, s, n, cudaMemcpyDefault, st);
+}
+static cudaError_t rt_sync(pve_stream_t s) { return cudaStreamSynchronize(s); }
+static cudaError_t rt_host_alloc(void **p, size_t n) { return cudaHostAlloc(p, n, cudaHostAllocDefault); }
+static void rt_host_free(void *p) { if (p) cudaFreeHost(p); }
+#else
+#define RT_CHECK(s, call)                                                                     \
+    do {                                                                                      \
+        if ((call) != 0) {                                                                    \
+            snprintf((s)->err, sizeof((s)->err), "%s failed (%s:%d)", #call, __FILE__, __LINE__); \
+            return PVE_ECUDA;                                                                 \
+        }                                                                                     \
+    } while (0)
+static int rt_alloc(void **p, size_t n) { *p = calloc(1, n ? n : 16); return *p ? 0 : 1; }
+static void rt_free(void *p) { free(p); }
+static int rt_memset(void *p, int v, size_t n, pve_stream_t) { memset(p, v, n); return 0; }
+static int rt_copy(void *d, const void *s, size_t n, pve_stream_t) { memmove(d, s, n); return 0; }
+static int rt_sync(pve_stream_t) { return 0; }
+static int rt_host_alloc(void **p, size_t n) { return rt_alloc(p, n); }
+static void rt_host_free(void *p) { free(p); }
+#endif
+
+/* =============================================================================================
+ * kernels
+ * =========================================================================================== */
+#ifndef PVE_HOST_EMULATION
+
+template <int NT>
+__global__ void __launch_bounds__(NT)
+pve_step_kernel(const PveParams P, const PveState S, const pve_outputs O, const int32_t *spawn_tick,
+                const float *actions, const int phase) {
+    extern __shared__ __align__(16) unsigned char pve_smem[];
+    pve_step_block<NT>(P, S, O, spawn_tick, actions, phase, (int)blockIdx.x, pve_smem);
+}
+
+/* agent_offset[b] = sum of n_ctrl[0..b): rows of the dense per-agent outputs.  One CTA. */
+__global__ void __launch_bounds__(1024)
+pve_offset_scan_kernel(const int32_t *__restrict__ n_ctrl, int32_t *__restrict__ agent_offset, int B) {
+    __shared__ int wsum[32];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int chunk = (B + 1023) / 1024;
+    const int lo = min(B, tid * chunk), hi = min(B, lo + chunk);
+    int s = 0;
+    for (int b = lo; b < hi; ++b) s += n_ctrl[b];
+    int inc = s;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, inc, d);
+        if (lane >= d) inc += t;
+    }
+    if (lane == 31) wsum[warp] = inc;
+    __syncthreads();
+    if (warp == 0) {
+        int w = wsum[lane];
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, w, d);
+            if (lane >= d) w += t;
+        }
+        wsum[lane] = w;
+    }
+    __syncthreads();
+    int run = inc - s + (warp > 0 ? wsum[warp - 1] : 0);
+    for (int b = lo; b < hi; ++b) { agent_offset[b] = run; run += n_ctrl[b]; }
+    if (tid == 1023) agent_offset[B] = wsum[31];
+}
+
+__global__ void pve_reset_kernel(PveState S, const int32_t *__restrict__ spawn_tick, int B, int K, int warmup) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    pve_env_header h;
+    memset(&h, 0, sizeof h);
+    int first = PVE_NEVER;
+    for (int i = 0; i < PVE_NLANE; ++i) {
+        const int t = (K > 0) ? spawn_tick[(size_t)b * K * PVE_NLANE + i] : PVE_NEVER;
+        h.next_spawn[i] = t;
+        h.head_lane[i] = -1;
+        first = min(first, t);
+    }
+    /* TIS:214-220: empty scene updates until the first arrival; the tick that spawns it is run by
+     * pve_reset as an ordinary (empty) step */
+    h.tick = (warmup && first != PVE_NEVER) ? max(first - 1, 0) : 0;
+    S.hdr[b] = h;
+    S.n_ctrl[b] = 0;
+    S.n_veh[b] = 0;
+    for (int q = 0; q < PVE_NSTAT; ++q) S.stats[(size_t)b * PVE_NSTAT + q] = 0.0;
+}
+
+/* after pve_set_state: recompute the derived header fields */
+__global__ void pve_recount_kernel(PveState S, const int32_t *__restrict__ spawn_tick, int B, int VC, int K) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    pve_env_header *h = S.hdr + b;
+    int nv = 0, nc = 0;
+    for (int i = 0; i < PVE_NLANE; ++i) nv += h->lane_n[i];
+    nv = min(nv, VC);
+    for (int k = 0; k < nv; ++k) nc += (S.meta[(size_t)b * VC + k].packed >> 24) & PVE_F_CONTROL;
+    h->n_veh = nv;
+    h->n_ctrl = nc;
+    for (int i = 0; i < PVE_NLANE; ++i) {
+        const int rec = h->veh_rec[i];
+        h->next_spawn[i] = (spawn_tick && rec < K) ? spawn_tick[((size_t)b * K + rec) * PVE_NLANE + i] : PVE_NEVER;
+    }
+    S.n_ctrl[b] = nc;
+    S.n_veh[b] = nv;
+}
+
+/* K5: end-of-rollout statistics, one CTA, deterministic order */
+__global__ void __launch_bounds__(256)
+pve_stats_kernel(PveState S, int B, double *out) {
+    __shared__ double sh[16][256];
+    const int tid = threadIdx.x;
+    double acc[16];
+    for (int q = 0; q < 16; ++q) acc[q] = 0;
+    for (int b = tid; b < B; b += 256) {
+        const double *st = S.stats + (size_t)b * PVE_NSTAT;
+        const pve_env_header *h = S.hdr + b;
+        acc[0] += st[PVE_STAT_AGENT]; acc[1] += st[PVE_STAT_VEH];
+        acc[2] += st[PVE_STAT_STEPS]; acc[13] += st[PVE_STAT_Q5U];
+        acc[3] += (double)h->id_seq; acc[4] += (double)h->passed_veh; acc[5] += (double)h->passed_step_total;
+        acc[6] += st[PVE_STAT_JERK]; acc[7] += st[PVE_STAT_COLL]; acc[8] += st[PVE_STAT_LOCK];
+        acc[9] += st[PVE_STAT_RSUM]; acc[10] += st[PVE_STAT_RSQ]; acc[11] += st[PVE_STAT_REMOVED];
+        acc[12] += (double)h->overflow;
+    }
+    for (int q = 0; q < 16; ++q) sh[q][tid] = acc[q];
+    __syncthreads();
+    if (tid < 16) {
+        double s = 0;
+        for (int t = 0; t < 256; ++t) s += sh[tid][t];
+        out[tid] = s;
+    }
+}
+
+#else  /* ------------------------------- host emulation ------------------------------------ */
+
+static void emul_offset_scan(const int32_t *n_ctrl, int32_t *agent_offset, int B) {
+    int run = 0;
+    for (int b = 0; b < B; ++b) { agent_offset[b] = run; run += n_ctrl[b]; }
+    agent_offset[B] = run;
+}
+static void emul_reset(PveState S, const int32_t *spawn_tick, int B, int K, int warmup) {
+    for (int b = 0; b < B; ++b) {
+        pve_env_header h;
+        memset(&h, 0, sizeof h);
+        int first = PVE_NEVER;
+        for (int i = 0; i < PVE_NLANE; ++i) {
+            const int t = (K > 0) ? spawn_tick[(size_t)b * K * PVE_NLANE + i] : PVE_NEVER;
+            h.next_spawn[i] = t; h.head_lane[i] = -1;
+            first = t < first ? t : first;
+        }
+        h.tick = (warmup && first != PVE_NEVER) ? (first - 1 > 0 ? first - 1 : 0) : 0;
+        S.hdr[b] = h; S.n_ctrl[b] = 0; S.n_veh[b] = 0;
+        for (int q = 0; q < PVE_NSTAT; ++q) S.stats[(size_t)b * PVE_NSTAT + q] = 0.0;
+    }
+}
+static void emul_recount(PveState S, const int32_t *spawn_tick, int B, int VC, int K) {
+    for (int b = 0; b < B; ++b) {
+        pve_env_header *h = S.hdr + b;
+        int nv = 0, nc = 0;
+        for (int i = 0; i < PVE_NLANE; ++i) nv += h->lane_n[i];
+        nv = nv < VC ? nv : VC;
+        for (int k = 0; k < nv; ++k) nc += (S.meta[(size_t)b * VC + k].packed >> 24) & PVE_F_CONTROL;
+        h->n_veh = nv; h->n_ctrl = nc;
+        for (int i = 0; i < PVE_NLANE; ++i) {
+            const int rec = h->veh_rec[i];
+            h->next_spawn[i] = (spawn_tick && rec < K) ? spawn_tick[((size_t)b * K + rec) * PVE_NLANE + i] : PVE_NEVER;
+        }
+        S.n_ctrl[b] = nc; S.n_veh[b] = nv;
+    }
+}
+static void emul_stats(PveState S, int B, double *out) {
+    for (int q = 0; q < 16; ++q) out[q] = 0;
+    for (int b = 0; b < B; ++b) {
+        const double *st = S.stats + (size_t)b * PVE_NSTAT;
+        const pve_env_header *h = S.hdr + b;
+        out[0] += st[PVE_STAT_AGENT]; out[1] += st[PVE_STAT_VEH];
+        out[2] += st[PVE_STAT_STEPS]; out[13] += st[PVE_STAT_Q5U];
+        out[3] += (double)h->id_seq; out[4] += (double)h->passed_veh; out[5] += (double)h->passed_step_total;
+        out[6] += st[PVE_STAT_JERK]; out[7] += st[PVE_STAT_COLL]; out[8] += st[PVE_STAT_LOCK];
+        out[9] += st[PVE_STAT_RSUM]; out[10] += st[PVE_STAT_RSQ]; out[11] += st[PVE_STAT_REMOVED];
+        out[12] += (double)h->overflow;
+    }
+}
+#endif
+
+/* =============================================================================================
+ * launch helpers
+ * =========================================================================================== */
+static int32_t launch_scan(pve_scene *s, pve_stream_t stream) {
+#ifndef PVE_HOST_EMULATION
+    pve_offset_scan_kernel<<<1, 1024, 0, stream>>>(s->st.n_ctrl, s->st.agent_offset, s->cfg.n_envs);
+    RT_CHECK(s, cudaGetLastError());
+#else
+    (void)stream;
+    emul_offset_scan(s->st.n_ctrl, s->st.agent_offset, s->cfg.n_envs);
+#endif
+    return PVE_OK;
+}
+
+static int32_t launch_step(pve_scene *s, const float *actions, const pve_outputs &O, pve_stream_t stream) {
+    const int B = s->cfg.n_envs;
+#ifndef PVE_HOST_EMULATION
+    switch (s->threads) {
+        case 64:
+            pve_step_kernel<64><<<B, 64, s->smem_bytes, stream>>>(s->prm, s->st, O, s->spawn_tick, actions, s->phase);
+            break;
+        case 256:
+            pve_step_kernel<256><<<B, 256, s->smem_bytes, stream>>>(s->prm, s->st, O, s->spawn_tick, actions, s->phase);
+            break;
+        default:
+            pve_step_kernel<128><<<B, 128, s->smem_bytes, stream>>>(s->prm, s->st, O, s->spawn_tick, actions, s->phase);
+            break;
+    }
+    RT_CHECK(s, cudaGetLastError());
+#else
+    (void)stream;
+    unsigned char *smem = (unsigned char *)aligned_alloc(64, (s->smem_bytes + 63) / 64 * 64);
+    if (!smem) return PVE_ENOMEM;
+    for (int b = 0; b < B; ++b) {
+        memset(smem, 0xA5, s->smem_bytes);      /* poison: catches reads of unwritten shared memory */
+        pve_step_block<64>(s->prm, s->st, O, s->spawn_tick, actions, s->phase, b, smem);
+    }
+    free(smem);
+#endif
+    s->phase ^= 1;
+    return PVE_OK;
+}
+
+static pve_outputs null_outputs() {
+    pve_outputs o;
+    memset(&o, 0, sizeof o);
+    return o;
+}
+
+/* =============================================================================================
+ * C ABI
+ * =========================================================================================== */
+extern "C" {
+
+const char *pve_backend(void) { return PVE_BACKEND; }
+
+int32_t pve_config_bytes(void) { return (int32_t)sizeof(pve_config); }
+
+int32_t pve_default_config(pve_config *c, int32_t n_envs, double vm) {
+    if (!c) return PVE_EINVAL;
+    memset(c, 0, sizeof *c);
+    const double dis_ctl = 150, cw = 2.5;
+    c->n_envs = n_envs; c->veh_cap = 160; c->agent_cap = 96; c->threads = 0;
+    c->out_cap = (int64_t)n_envs * 96;
+    c->dt = 0.1; c->dt2 = pow(0.1, 2);
+    c->vm = vm; c->vM = 13; c->am = -3; c->aM = 3; c->v0 = 10; c->collision_thr = 2;
+    c->lane_cw = cw;
+    c->lane_in = dis_ctl - 6 * cw;
+    c->lane_len[0] = 3.1415 / 2 * 7 * cw; c->lane_len[1] = 12 * cw; c->lane_len[2] = 3.1415 / 2 * cw;
+    c->remove_p = -dis_ctl + (int)((12 + 1) / 2) * cw;
+    const double cita = (2 * sqrt(10.0) - 6) * cw;
+    const double alpha = atan((6 * cw + cita) / (3 * cw));
+    const double beta = M_PI / 2 - alpha;
+    const double gama = atan((sqrt(13.0) * cw) / (6 * cw));
+    const double gama2 = M_PI / 2 - gama;
+    /* straight ego (TIS:733-766) */
+    c->vd_a1[1][0] = 3 * cw;         c->vd_a2[1][0] = 0;     c->vd_b[1][0] = 9 * cw;
+    c->vd_a1[1][1] = beta * 7 * cw;  c->vd_a2[1][1] = 0;     c->vd_b[1][1] = 6 * cw + cita;
+    c->vd_a1[1][2] = alpha * 7 * cw; c->vd_a2[1][2] = 0;     c->vd_b[1][2] = 6 * cw - cita;
+    c->vd_a1[1][3] = 9 * cw;         c->vd_a2[1][3] = 0;     c->vd_b[1][3] = 3 * cw;
+    /* left-turn ego (TIS:771-799) */
+    c->vd_a1[0][0] = 6 * cw;         c->vd_a2[0][0] = cita;  c->vd_b[0][0] = alpha * 7 * cw;
+    c->vd_a1[0][1] = gama * 7 * cw;  c->vd_a2[0][1] = 0;     c->vd_b[0][1] = gama2 * 7 * cw;
+    c->vd_a1[0][2] = gama2 * 7 * cw; c->vd_a2[0][2] = 0;     c->vd_b[0][2] = gama * 7 * cw;
+    c->vd_a1[0][3] = 6 * cw;         c->vd_a2[0][3] = -cita; c->vd_b[0][3] = beta * 7 * cw;
+    for (int k = 0; k < 4; ++k) {
+        const double rot = 3.141593 / 2 * k;
+        c->rot_cos[k] = cos(rot); c->rot_sin[k] = sin(rot);
+    }
+    return PVE_OK;
+}
+
+const char *pve_last_error(const pve_scene *s) { return s ? s->err : "null handle"; }
+
+void pve_destroy(pve_scene *s) {
+    if (!s) return;
+    rt_free(s->st.hdr); rt_free(s->st.p); rt_free(s->st.v); rt_free(s->st.a); rt_free(s->st.js);
+    rt_free(s->st.meta); rt_free(s->st.row0[0]); rt_free(s->st.row0[1]);
+    rt_free(s->st.n_ctrl); rt_free(s->st.n_veh); rt_free(s->st.stats); rt_free(s->st.agent_offset);
+    rt_free(s->actions_dev); rt_free(s->counters_dev);
+    rt_host_free(s->pinned_i32);
+    delete s;
+}
+
+int32_t pve_create(const pve_config *cfg, int32_t device, pve_scene **out) {
+    if (!cfg || !out) return PVE_EINVAL;
+    *out = nullptr;
+    pve_scene *s = new (std::nothrow) pve_scene();
+    if (!s) return PVE_ENOMEM;
+    memset(s, 0, sizeof *s);
+    *out = s;                       /* returned even on failure so that pve_last_error works */
+    s->cfg = *cfg;
+    s->device = device;
+    s->next_total = -1;
+    const int B = cfg->n_envs, VC = cfg->veh_cap, AC = cfg->agent_cap;
+    if (B <= 0 || VC <= 0 || VC > 1024 || AC <= 0 || AC > VC || cfg->out_cap < 0) {
+        snprintf(s->err, sizeof s->err, "invalid config: n_envs=%d veh_cap=%d agent_cap=%d", B, VC, AC);
+        return PVE_EINVAL;
+    }
+    s->threads = cfg->threads == 0 ? 128 : cfg->threads;
+    if (s->threads != 64 && s->threads != 128 && s->threads != 256) {
+        snprintf(s->err, sizeof s->err, "threads must be 0, 64, 128 or 256");
+        return PVE_EINVAL;
+    }
+    PveParams &P = s->prm;
+    memset(&P, 0, sizeof P);
+    P.dt = cfg->dt; P.dt2 = cfg->dt2; P.vm = cfg->vm; P.vM = cfg->vM; P.am = cfg->am; P.aM = cfg->aM;
+    P.v0 = cfg->v0; P.thr = cfg->collision_thr; P.lane_in = cfg->lane_in; P.remove_p = cfg->remove_p;
+    P.lane_cw = cfg->lane_cw; P.abs_am = fabs(cfg->am); P.two_abs_am = 2 * fabs(cfg->am);     /* TIS:1513-1514 */
+    P.aspan = (double)(cfg->aM - cfg->am);                                                     /* TIS:319 */
+    for (int m = 0; m < 3; ++m) { P.lane_len[m] = cfg->lane_len[m]; P.spawn_p[m] = cfg->lane_in + cfg->lane_len[m]; }  /* TIS:395 */
+    memcpy(P.vd_a1, cfg->vd_a1, sizeof P.vd_a1); memcpy(P.vd_a2, cfg->vd_a2, sizeof P.vd_a2);
+    memcpy(P.vd_b, cfg->vd_b, sizeof P.vd_b);
+    memcpy(P.rot_cos, cfg->rot_cos, sizeof P.rot_cos); memcpy(P.rot_sin, cfg->rot_sin, sizeof P.rot_sin);
+    memcpy(P.l2l, kLane2Lane, sizeof P.l2l);
+    memset(P.rev_dir, -1, sizeof P.rev_dir);
+    for (int L = 0; L < PVE_NLANE; ++L) {
+        int n = 0;
+        for (int d = 0; d < PVE_NLANE; ++d)
+            for (int k = 0; k < 4; ++k)
+                if (kLane2Lane[d][k] == L && n < 4) { P.rev_dir[L][n] = (int8_t)d; P.rev_k[L][n] = (int8_t)k; ++n; }
+        if ((L % 3 != 2 && n != 4) || (L % 3 == 2 && n != 0)) {
+            snprintf(s->err, sizeof s->err, "internal: conflict table is not 4-regular");
+            return PVE_EINVAL;
+        }
+    }
+    P.B = B; P.VC = VC; P.AC = AC; P.K = 0; P.out_cap = cfg->out_cap;
+    s->smem_bytes = pve_smem_carve(nullptr, nullptr, VC, AC);
+#ifndef PVE_HOST_EMULATION
+    RT_CHECK(s, cudaSetDevice(device));
+    if (s->smem_bytes > 227 * 1024) {
+        snprintf(s->err, sizeof s->err, "veh_cap/agent_cap need %zu bytes of shared memory (> 227 KB)", s->smem_bytes);
+        return PVE_EINVAL;
+    }
+    RT_CHECK(s, cudaFuncSetAttribute(pve_step_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->smem_bytes));
+    RT_CHECK(s, cudaFuncSetAttribute(pve_step_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->smem_bytes));
+    RT_CHECK(s, cudaFuncSetAttribute(pve_step_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->smem_bytes));
+#endif
+    const size_t nv = (size_t)B * VC;
+    RT_CHECK(s, rt_alloc((void **)&s->st.hdr, sizeof(pve_env_header) * (size_t)B));
+    RT_CHECK(s, rt_alloc((void **)&s->st.p, sizeof(double) * nv));
+    RT_CHECK(s, rt_alloc((void **)&s->st.v, sizeof(double) * nv));
+    RT_CHECK(s, rt_alloc((void **)&s->st.a, sizeof(double) * nv));
+    RT_CHECK(s, rt_alloc((void **)&s->st.js, sizeof(double) * nv));
+    RT_CHECK(s, rt_alloc((void **)&s->st.meta, sizeof(pve_veh_meta) * nv));
+    RT_CHECK(s, rt_alloc((void **)&s->st.row0[0], sizeof(float) * nv * PVE_OBS_W));
+    RT_CHECK(s, rt_alloc((void **)&s->st.row0[1], sizeof(float) * nv * PVE_OBS_W));
+    RT_CHECK(s, rt_alloc((void **)&s->st.n_ctrl, sizeof(int32_t) * (size_t)B));
+    RT_CHECK(s, rt_alloc((void **)&s->st.n_veh, sizeof(int32_t) * (size_t)B));
+    RT_CHECK(s, rt_alloc((void **)&s->st.stats, sizeof(double) * (size_t)B * PVE_NSTAT));
+    RT_CHECK(s, rt_alloc((void **)&s->st.agent_offset, sizeof(int32_t) * ((size_t)B + 1)));
+    RT_CHECK(s, rt_alloc((void **)&s->counters_dev, sizeof(double) * 16));
+    RT_CHECK(s, rt_host_alloc((void **)&s->pinned_i32, sizeof(int32_t) * 16));
+    return pve_reset(s, nullptr, 0, 0, nullptr);
+}
+
+int32_t pve_reset(pve_scene *s, const int32_t *spawn_tick_dev, int32_t K, int32_t warmup, void *stream_) {
+    if (!s) return PVE_EINVAL;
+    pve_stream_t stream = (pve_stream_t)stream_;
+    const int B = s->cfg.n_envs;
+    const size_t nv = (size_t)B * s->cfg.veh_cap;
+    s->spawn_tick = spawn_tick_dev;
+    s->prm.K = spawn_tick_dev ? K : 0;
+    s->phase = 0;
+    s->next_total = -1;
+    RT_CHECK(s, rt_memset(s->st.p, 0, sizeof(double) * nv, stream));
+    RT_CHECK(s, rt_memset(s->st.v, 0, sizeof(double) * nv, stream));
+    RT_CHECK(s, rt_memset(s->st.a, 0, sizeof(double) * nv, stream));
+    RT_CHECK(s, rt_memset(s->st.js, 0, sizeof(double) * nv, stream));
+    RT_CHECK(s, rt_memset(s->st.meta, 0, sizeof(pve_veh_meta) * nv, stream));
+    RT_CHECK(s, rt_memset(s->st.row0[0], 0, sizeof(float) * nv * PVE_OBS_W, stream));
+    RT_CHECK(s, rt_memset(s->st.row0[1], 0, sizeof(float) * nv * PVE_OBS_W, stream));
+#ifndef PVE_HOST_EMULATION
+    pve_reset_kernel<<<(B + 127) / 128, 128, 0, stream>>>(s->st, s->spawn_tick, B, s->prm.K, warmup);
+    RT_CHECK(s, cudaGetLastError());
+#else
+    emul_reset(s->st, s->spawn_tick, B, s->prm.K, warmup);
+#endif
+    int32_t rc = launch_scan(s, stream);
+    if (rc != PVE_OK) return rc;
+    if (warmup && spawn_tick_dev && K > 0) {
+        /* the tick that brings the first vehicle(s) in: nothing to step, nothing to emit */
+        if (!s->actions_dev) RT_CHECK(s, rt_alloc((void **)&s->actions_dev, sizeof(float) * nv));
+        rc = launch_step(s, s->actions_dev, null_outputs(), stream);
+        if (rc != PVE_OK) return rc;
+        rc = launch_scan(s, stream);
+    }
+    return rc;
+}
+
+int32_t pve_step(pve_scene *s, const float *actions_dev, const pve_outputs *out_dev, void *stream_) {
+    if (!s || !actions_dev) return PVE_EINVAL;
+    pve_stream_t stream = (pve_stream_t)stream_;
+    const pve_outputs O = out_dev ? *out_dev : null_outputs();
+    if (O.agent_offset)
+        RT_CHECK(s, rt_copy(O.agent_offset, s->st.agent_offset, sizeof(int32_t) * ((size_t)s->cfg.n_envs + 1), stream));
+    int32_t rc = launch_step(s, actions_dev, O, stream);
+    if (rc != PVE_OK) return rc;
+    s->next_total = -1;
+    return launch_scan(s, stream);        /* row offsets of the NEXT tick */
+}
+
+int64_t pve_next_agent_total(pve_scene *s, void *stream_) {
+    if (!s) return PVE_EINVAL;
+    pve_stream_t stream = (pve_stream_t)stream_;
+    if (s->next_total < 0) {
+        RT_CHECK(s, rt_copy(s->pinned_i32, s->st.agent_offset + s->cfg.n_envs, sizeof(int32_t), stream));
+        RT_CHECK(s, rt_sync(stream));
+        s->next_total = s->pinned_i32[0];
+    }
+    return s->next_total;
+}
+
+int32_t pve_step_host(pve_scene *s, const float *actions_host, const pve_outputs *out_dev,
+                      const pve_outputs *out_host, int32_t copy_mask, void *stream_) {
+    if (!s || !actions_host || !out_dev) return PVE_EINVAL;
+    pve_stream_t stream = (pve_stream_t)stream_;
+    const int B = s->cfg.n_envs;
+    const size_t nv = (size_t)B * s->cfg.veh_cap;
+    const int64_t A = pve_next_agent_total(s, stream_);
+    if (A < 0) return (int32_t)A;
+    if (A > s->cfg.out_cap) {
+        snprintf(s->err, sizeof s->err, "tick emits %lld rows but out_cap is %lld", (long long)A, (long long)s->cfg.out_cap);
+        return PVE_ESTATE;
+    }
+    if (!s->actions_dev) RT_CHECK(s, rt_alloc((void **)&s->actions_dev, sizeof(float) * nv));
+    RT_CHECK(s, rt_copy(s->actions_dev, actions_host, sizeof(float) * nv, stream));
+    int32_t rc = pve_step(s, s->actions_dev, out_dev, stream_);
+    if (rc != PVE_OK) return rc;
+    const size_t a = (size_t)A;
+    if (out_host && (copy_mask & 1)) {
+#define D2H(field, bytes) \
+        if (out_host->field && out_dev->field) RT_CHECK(s, rt_copy(out_host->field, out_dev->field, (bytes), stream))
+        D2H(agent_offset, sizeof(int32_t) * ((size_t)B + 1));
+        D2H(reward, sizeof(float) * a);
+        D2H(ids, sizeof(int32_t) * 4 * a);
+        D2H(cpv, sizeof(int32_t) * a);
+        D2H(status, sizeof(uint8_t) * a);
+        D2H(jerk_sum, sizeof(float) * a);
+        D2H(env_collisions, sizeof(int32_t) * (size_t)B);
+        D2H(env_lock, sizeof(int32_t) * (size_t)B);
+        D2H(env_removed, sizeof(int32_t) * (size_t)B);
+    }
+    if (out_host && (copy_mask & 2)) {
+        D2H(obs, sizeof(float) * PVE_OBS_H * PVE_OBS_W * a);
+#undef D2H
+    }
+    RT_CHECK(s, rt_copy(s->pinned_i32, s->st.agent_offset + B, sizeof(int32_t), stream));
+    RT_CHECK(s, rt_sync(stream));
+    s->next_total = s->pinned_i32[0];
+    return PVE_OK;
+}
+
+int32_t pve_set_state(pve_scene *s, const pve_state_view *in, void *stream_) {
+    if (!s || !in) return PVE_EINVAL;
+    pve_stream_t stream = (pve_stream_t)stream_;
+    const int B = s->cfg.n_envs;
+    const size_t nv = (size_t)B * s->cfg.veh_cap;
+    RT_CHECK(s, rt_copy(s->st.hdr, in->hdr, sizeof(pve_env_header) * (size_t)B, stream));
+    RT_CHECK(s, rt_copy(s->st.p, in->p, sizeof(double) * nv, stream));
+    RT_CHECK(s, rt_copy(s->st.v, in->v, sizeof(double) * nv, stream));
+    RT_CHECK(s, rt_copy(s->st.a, in->a, sizeof(double) * nv, stream));
+    RT_CHECK(s, rt_copy(s->st.js, in->jerk_sum, sizeof(double) * nv, stream));
+    RT_CHECK(s, rt_copy(s->st.meta, in->meta, sizeof(pve_veh_meta) * nv, stream));
+    RT_CHECK(s, rt_copy(s->st.row0[s->phase], in->row0, sizeof(float) * nv * PVE_OBS_W, stream));
+#ifndef PVE_HOST_EMULATION
+    pve_recount_kernel<<<(B + 127) / 128, 128, 0, stream>>>(s->st, s->spawn_tick, B, s->cfg.veh_cap, s->prm.K);
+    RT_CHECK(s, cudaGetLastError());
+#else
+    emul_recount(s->st, s->spawn_tick, B, s->cfg.veh_cap, s->prm.K);
+#endif
+    s->next_total = -1;
+    return launch_scan(s, stream);
+}
+
+int32_t pve_get_state(pve_scene *s, const pve_state_view *out, void *stream_) {
+    if (!s || !out) return PVE_EINVAL;
+    pve_stream_t stream = (pve_stream_t)stream_;
+    const int B = s->cfg.n_envs;
+    const size_t nv = (size_t)B * s->cfg.veh_cap;
+    RT_CHECK(s, rt_copy(out->hdr, s->st.hdr, sizeof(pve_env_header) * (size_t)B, stream));
+    RT_CHECK(s, rt_copy(out->p, s->st.p, sizeof(double) * nv, stream));
+    RT_CHECK(s, rt_copy(out->v, s->st.v, sizeof(double) * nv, stream));
+    RT_CHECK(s, rt_copy(out->a, s->st.a, sizeof(double) * nv, stream));
+    RT_CHECK(s, rt_copy(out->jerk_sum, s->st.js, sizeof(double) * nv, stream));
+    RT_CHECK(s, rt_copy(out->meta, s->st.meta, sizeof(pve_veh_meta) * nv, stream));
+    RT_CHECK(s, rt_copy(out->row0, s->st.row0[s->phase], sizeof(float) * nv * PVE_OBS_W, stream));
+    RT_CHECK(s, rt_sync(stream));
+    return PVE_OK;
+}
+
+const float *pve_row0_dev(const pve_scene *s) { return s ? s->st.row0[s->phase] : nullptr; }
+const pve_veh_meta *pve_meta_dev(const pve_scene *s) { return s ? s->st.meta : nullptr; }
+const pve_env_header *pve_hdr_dev(const pve_scene *s) { return s ? s->st.hdr : nullptr; }
+int64_t pve_smem_bytes(const pve_scene *s) { return s ? (int64_t)s->smem_bytes : 0; }
+int32_t pve_threads(const pve_scene *s) { return s ? s->threads : 0; }
+
+int32_t pve_stats(pve_scene *s, pve_counters *out_dev, void *stream_) {
+    if (!s || !out_dev) return PVE_EINVAL;
+    pve_stream_t stream = (pve_stream_t)stream_;
+#ifndef PVE_HOST_EMULATION
+    pve_stats_kernel<<<1, 256, 0, stream>>>(s->st, s->cfg.n_envs, s->counters_dev);
+    RT_CHECK(s, cudaGetLastError());
+#else
+    emul_stats(s->st, s->cfg.n_envs, s->counters_dev);
+#endif
+    RT_CHECK(s, rt_copy(out_dev, s->counters_dev, sizeof(double) * 16, stream));
+    return PVE_OK;
+}
+
+}  /* extern "C" */

@@ -1,0 +1,130 @@
+"""CPU tier: the CUDA kernel SOURCE, compiled as a sequential emulation, against the oracle.
+
+This checks the order-free reformulation in
+pve_mcc_for_unsignalized_intersection_b200/csrc/scene_step.cuh without a GPU.  The same checks run
+on the real CUDA build in tests/test_gpu_parity.py.
+"""
+import numpy as np
+import pytest
+
+import parity as P
+from golden_io import ROLLOUTS, STATE_KEYS_E, load_crafted, load_rollout, snapshot_to_state
+from pve_mcc_for_unsignalized_intersection_b200.arrivals import stress_arrivals, synthetic_arrivals
+
+BACKEND = "emul"
+
+
+def free_run(backend, tables, vm, ticks, seed, veh_cap=160, agent_cap=96, policy="uniform"):
+    B = tables.shape[0]
+    scene = P.make_scene(backend, B, vm=vm, veh_cap=veh_cap, agent_cap=agent_cap)
+    orc = P.make_oracle(B, vm=vm, veh_cap=veh_cap)
+    scene.reset(tables, warmup=True)
+    orc.reset(tables, warmup=True)
+    P.compare_states(scene.get_state(), orc.get_state(), "after reset")
+    rng = np.random.RandomState(seed)
+    agent_steps = 0
+    for t in range(ticks):
+        st = orc.get_state()
+        ctrl = (st["flags"] & 1) != 0
+        if policy == "uniform":
+            act = P.random_actions(rng, ctrl)
+        elif policy == "brake":
+            act = np.where(ctrl, -3.0, 0.0).astype(np.float32)
+        else:
+            act = np.where(ctrl, 3.0, 0.0).astype(np.float32)
+        o_ref = orc.step(act)
+        o_dev = P.outputs_to_numpy(scene.step(P.to_device_actions(scene, act)))
+        P.compare_outputs(o_dev, o_ref, "tick %d" % t)
+        assert o_ref["overflow"] == 0 and o_ref["q5_undefined"].sum() == 0
+        agent_steps += len(o_ref["reward"])
+        if t % 10 == 0 or t == ticks - 1:
+            P.compare_states(scene.get_state(), orc.get_state(), "tick %d" % t)
+    return scene, agent_steps
+
+
+def test_free_running_matches_oracle_mixed_densities():
+    tabs = np.concatenate([synthetic_arrivals(2, lam, 50.0, seed=lam, rows=40) for lam in (400, 1000, 1200)])
+    scene, n = free_run(BACKEND, tabs, vm=5, ticks=420, seed=1)
+    assert n > 20000
+    s = scene.stats()
+    assert s["agent_steps"] == n and s["overflow"] == 0
+
+
+def test_free_running_train_setting_vm6_accel():
+    tabs = synthetic_arrivals(3, 1000, 40.0, seed=77, rows=32)
+    free_run(BACKEND, tabs, vm=6, ticks=330, seed=2, policy="accel")
+
+
+def test_stress_occupancy_brake():
+    tabs = stress_arrivals(1, 40.0)
+    free_run(BACKEND, tabs, vm=5, ticks=300, seed=3, veh_cap=384, agent_cap=320, policy="brake")
+
+
+@pytest.mark.parametrize("name", ROLLOUTS)
+def test_golden_rollout_direct(name):
+    """Kernel logic against the reference's own trace (no oracle in between)."""
+    z, r = load_rollout(name)
+    big = name == "stress_brake"
+    scene = P.make_scene(BACKEND, 1, vm=float(z["vm"]), veh_cap=384 if big else 160, agent_cap=320 if big else 96)
+    scene.reset(z["table"], warmup=True)
+    obs_at = {int(t): k for k, t in enumerate(z["obs_ticks"])}
+    for t in range(int(z["n_ticks"])):
+        act = np.zeros((1, scene.veh_cap), np.float32)
+        a_in = r["actions_in", t]
+        act[0, :len(a_in)] = a_in
+        o = P.outputs_to_numpy(scene.step(P.to_device_actions(scene, act)))
+        np.testing.assert_array_equal(o["ids"][:, 1:3], r["ids", t], err_msg="%s ids t=%d" % (name, t))
+        np.testing.assert_array_equal(o["ids"][:, 3], r["uid", t])
+        np.testing.assert_array_equal(o["cpv"], r["cpv", t][:, 0], err_msg="%s cpv t=%d" % (name, t))
+        np.testing.assert_array_equal(o["status"] & 1, r["done", t])
+        np.testing.assert_array_equal((o["status"] >> 1) & 1, r["removed", t])
+        P.assert_rel(o["reward"], r["reward", t], "%s reward t=%d" % (name, t))
+        P.assert_rel(o["jerk_sum"][(o["status"] & 4) != 0], r["jerks", t], "%s jerks t=%d" % (name, t))
+        assert o["collisions"][0] == z["t_collisions"][t] and o["lock"][0] == z["t_lock"][t], (name, t)
+        assert o["n_removed"][0] == z["t_n_removed"][t]
+        if t in obs_at:
+            P.assert_rel(o["obs"], r["obs", obs_at[t]], "%s obs t=%d" % (name, t))
+    st = scene.get_state()
+    t = int(z["n_ticks"]) - 1
+    V = int(st["lane_n"][0].sum())
+    for k in ("p", "v", "a", "jerk_sum", "collision", "step", "uid", "lock_a"):
+        np.testing.assert_array_equal(st[k][0, :V], r["post_" + k, t], err_msg="%s final %s" % (name, k))
+    np.testing.assert_array_equal(st["head_lane"][0], z["t_head_lane"][t])
+    np.testing.assert_array_equal(st["head_j"][0], z["t_head_j"][t])
+    assert int(st["passed_step_total"][0]) == int(z["t_passed_step_total"][t])
+
+
+def test_crafted_order_dependence_cases():
+    """Q1-Q6 crafted states from the reference, teacher-forced through set_state."""
+    z, r = load_crafted()
+    for c, name in enumerate(str(n) for n in z["names"]):
+        snap = {k: r["in_" + k, c] for k in
+                ["p", "v", "a", "jerk_sum", "collision", "step", "seq_in_lane", "uid", "control", "finish",
+                 "lock", "lock_a", "row0"] + STATE_KEYS_E}
+        scene = P.make_scene(BACKEND, 1, vm=5, veh_cap=64, agent_cap=64)
+        scene.reset(r["table", c], warmup=False)
+        scene.set_state(P.oracle_state_for_device(snapshot_to_state(snap, 1, 64)))
+        act = np.zeros((1, 64), np.float32)
+        a_in = r["actions_in", c]
+        act[0, :len(a_in)] = a_in
+        o = P.outputs_to_numpy(scene.step(P.to_device_actions(scene, act)))
+        np.testing.assert_array_equal(o["ids"][:, 1:3], r["ids", c], err_msg=name)
+        np.testing.assert_array_equal(o["cpv"], r["cpv", c][:, 0], err_msg=name + " cpv")
+        np.testing.assert_array_equal(o["status"] & 1, r["done", c], err_msg=name + " done")
+        np.testing.assert_array_equal((o["status"] >> 1) & 1, r["removed", c], err_msg=name + " removed")
+        P.assert_rel(o["reward"], r["reward", c], name + " reward")
+        P.assert_rel(o["obs"], r["obs", c], name + " obs")
+        P.assert_rel(o["jerk_sum"][(o["status"] & 4) != 0], r["jerks", c], name + " jerks")
+        assert o["collisions"][0] == r["collisions", c][0], name
+        assert o["lock"][0] == r["lock", c][0], name
+        assert o["n_removed"][0] == r["n_removed", c][0], name
+        st = scene.get_state()
+        V = int(st["lane_n"][0].sum())
+        assert V == len(r["post_p", c]), name
+        for k in ("p", "v", "a", "jerk_sum", "collision", "step", "uid", "lock_a"):
+            np.testing.assert_array_equal(st[k][0, :V], r["post_" + k, c], err_msg="%s %s" % (name, k))
+        np.testing.assert_array_equal(st["flags"][0, :V] & 1, r["post_control", c], err_msg=name)
+        np.testing.assert_array_equal((st["flags"][0, :V] >> 2) & 1, r["post_lock", c], err_msg=name)
+        for k in ("lane_n", "veh_rec", "head_lane", "head_j"):
+            np.testing.assert_array_equal(st[k][0], r["post_" + k, c], err_msg="%s %s" % (name, k))
+        P.assert_rel(st["row0"][0, :V], r["post_row0", c], name + " row0")
