@@ -1,0 +1,339 @@
+#!/usr/bin/env python
+"""Benchmark of the batched PVE-MCC environment step (BASELINE.json metric).
+
+    python bench.py --gpus N --steps K --warmup W [--impl reference]
+
+A "step" is one tick (step() for every vehicle + scene_update() + delete_vehicle()) of every
+intersection of the batch.  Workload at N = 1: BASELINE config 2 -- 4,096 intersections,
+synthetic Poisson arrivals (1000 veh/h/lane; the train-set table is missing from the reference
+checkout), actions U(-3, 3), vm = 6 (train setting, main.py:230).  With N > 1 every
+rank runs its own 4,096 intersections (weak scaling, no step-path communication); NCCL is used
+only to all-reduce the end-of-rollout statistics and to take the max of the timings.
+
+Reported: `value` = vehicle-agent env-steps/s with inputs resident in HBM (CUDA events, L2
+flushed between timed steps); `e2e` = the same metric through the host-buffer C-ABI call
+(pinned host actions H2D, results D2H each step); `roofline` = algorithmic bytes
+(68*V + 1028*A) / step-kernel time against the measured HBM peak;
+`cpu_baseline` = the CPU oracle port on the host cores, timed in the same run.
+
+`--impl reference` times the reference algorithm's CPU port (oracle/scene_oracle.c, all host
+threads; the reference itself is pure Python and cannot travel to the GPU box).
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "vehicle-agent env-steps/sec"
+UNIT = "agent-steps/s"
+ENVS_PER_GPU = 4096
+DENSITY = 1000
+VM = 6
+PRIME_TICKS = 400          # untimed: fill the intersections to steady-state occupancy
+VEH_CAP, AGENT_CAP = 160, 96
+BYTES_PER_VEH, BYTES_PER_AGENT = 68, 1028        # SURVEY.md 8(d) / BASELINE.md section 4
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="graft", choices=["graft", "reference"])
+    ap.add_argument("--envs", type=int, default=ENVS_PER_GPU, help="intersections per GPU")
+    ap.add_argument("--density", type=int, default=DENSITY)
+    ap.add_argument("--threads", type=int, default=0, help="CTA size override (64/128/256)")
+    ap.add_argument("--workload", default="poisson", choices=["poisson", "stress"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+def workload_name(args):
+    if args.workload == "stress":
+        return "stress: headway 1.0 s on all 12 lanes, all-brake policy, %d intersections per GPU" % args.envs
+    return ("%d intersections per GPU, synthetic Poisson arrivals %d veh/h/lane, actions U(-3,3), vm=%d"
+            % (args.envs, args.density, VM))
+
+
+def make_tables(args, n_envs, seed, horizon_s):
+    from pve_mcc_for_unsignalized_intersection_b200.arrivals import stress_arrivals, synthetic_arrivals
+    if args.workload == "stress":
+        return stress_arrivals(n_envs, horizon_s)
+    return synthetic_arrivals(n_envs, args.density, horizon_s, seed=seed)
+
+
+# ---------------------------------------------------------------------------------------------
+# CPU legs (oracle port): cpu_baseline inside the default run, and the whole `--impl reference` arm
+# ---------------------------------------------------------------------------------------------
+def cpu_port_run(args, n_envs, prime, timed_steps, warmup_steps, n_threads, seed=1234):
+    """Times the oracle port: `timed_steps` ticks of `n_envs` intersections after priming."""
+    from oracle.oracle import OracleScene, scene_params
+    horizon = (prime + warmup_steps + timed_steps) * 0.1 + 30.0
+    tabs = make_tables(args, n_envs, seed, horizon)
+    cap = 384 if args.workload == "stress" else VEH_CAP
+    orc = OracleScene(n_envs, cap, scene_params(vm=5 if args.workload == "stress" else VM), n_threads=n_threads)
+    orc.reset(tabs, warmup=True)
+    rng = np.random.RandomState(seed)
+
+    def actions():
+        if args.workload == "stress":
+            return np.full((n_envs, cap), -3.0, np.float32)
+        return rng.uniform(-3, 3, size=(n_envs, cap)).astype(np.float32)
+
+    pool = [actions() for _ in range(8)]
+    for t in range(prime + warmup_steps):
+        orc.step(pool[t % 8])
+    agent_steps, veh_steps = 0, 0
+    per_step = []
+    for t in range(timed_steps):
+        a = pool[t % 8]
+        t0 = time.perf_counter()
+        o = orc.step(a)
+        per_step.append(time.perf_counter() - t0)
+        agent_steps += len(o["reward"])
+    elapsed = float(sum(per_step))
+    return {"agent_steps": agent_steps, "elapsed": elapsed, "n_envs": n_envs}
+
+
+def reference_arm(args, rank):
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    n_envs = max(64, min(1024, 16 * cores))
+    r = cpu_port_run(args, n_envs, PRIME_TICKS, args.steps, args.warmup, cores)
+    value = r["agent_steps"] / r["elapsed"]
+    sample = ("each step = one tick of %d intersections (bounded sample of the workload) on %d host threads, "
+              "after %d priming ticks" % (n_envs, cores, PRIME_TICKS))
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * r["elapsed"] / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": workload_name(args), "reference_sample_envs": n_envs},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------
+# clocks sampler (nvidia-smi equivalent through NVML), running during the timed region
+# ---------------------------------------------------------------------------------------------
+class ClockSampler(threading.Thread):
+    REASONS = {0x1: "gpu_idle", 0x2: "applications_clocks_setting", 0x4: "sw_power_cap", 0x8: "hw_slowdown",
+               0x10: "sync_boost", 0x20: "sw_thermal_slowdown", 0x40: "hw_thermal_slowdown",
+               0x80: "hw_power_brake_slowdown", 0x100: "display_clock_setting"}
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.stop_flag, self.sm, self.reasons, self.max_mhz = index, False, [], set(), None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def run(self):
+        while not self.stop_flag and self.nv is not None:
+            try:
+                self.sm.append(self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM))
+                mask = self.nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                for bit, name in self.REASONS.items():
+                    if mask & bit and name != "gpu_idle":
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(0.05)
+
+    def result(self):
+        return {"sm_mhz": float(np.median(self.sm)) if self.sm else None, "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(self.sm)}
+
+
+# ---------------------------------------------------------------------------------------------
+# the GPU arm
+# ---------------------------------------------------------------------------------------------
+def graft_arm(args, rank, world, local_rank):
+    import torch
+    import torch.distributed as dist
+    from pve_mcc_for_unsignalized_intersection_b200 import SceneConfig
+    from pve_mcc_for_unsignalized_intersection_b200.scene import BatchedScene
+
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py needs a CUDA device: the environment step has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    B = args.envs
+    K, W = args.steps, args.warmup
+    stress = args.workload == "stress"
+    veh_cap, agent_cap = (384, 320) if stress else (VEH_CAP, AGENT_CAP)
+    horizon = (PRIME_TICKS + 3 * (K + W) + 50) * 0.1 + 30.0
+    tabs = make_tables(args, B, 1000 + rank, horizon)
+    scene = BatchedScene(B, SceneConfig(vm=5 if stress else VM), veh_cap=veh_cap, agent_cap=agent_cap,
+                         device=dev, threads=args.threads)
+    scene.reset(tabs, warmup=True)
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(99 + rank)
+    if stress:
+        pool = [torch.full((B, veh_cap), -3.0, device=dev) for _ in range(2)]
+    else:
+        pool = [(torch.rand(B, veh_cap, device=dev, generator=gen) * 6.0 - 3.0).contiguous() for _ in range(16)]
+    flush = torch.empty(384 * 1024 * 1024, dtype=torch.uint8, device=dev)     # > 126 MB L2
+
+    for t in range(PRIME_TICKS):
+        scene.step(pool[t % len(pool)])
+    torch.cuda.synchronize()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---------------- device-resident timing (value, roofline) ----------------
+    scene.set_profiling(True)
+    for t in range(W):
+        flush.fill_(t & 0xFF)
+        scene.step(pool[t % len(pool)])
+    s0 = scene.stats()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
+    kern_ms, scan_ms = [], []
+    barrier()
+    wall0 = time.perf_counter()
+    for t in range(K):
+        flush.fill_(t & 0xFF)                  # L2 flush between timed iterations (not timed)
+        ev[t][0].record()
+        scene.step(pool[t % len(pool)])
+        ev[t][1].record()
+        a, b = scene.kernel_ms()               # waits for this step's kernels
+        kern_ms.append(a)
+        scan_ms.append(b)
+    barrier()
+    wall1 = time.perf_counter()
+    sampler.stop_flag = True
+    step_ms = [e0.elapsed_time(e1) for e0, e1 in ev]
+    s1 = scene.stats()
+    dA = s1["agent_steps"] - s0["agent_steps"]
+    dV = s1["vehicle_steps"] - s0["vehicle_steps"]
+    total_ms = float(sum(step_ms))
+    total_kern_ms = float(sum(kern_ms))
+
+    # ---------------- end-to-end through host buffers ----------------
+    e2e = None
+    if not args.no_e2e:
+        host = scene.make_host_outputs()
+        hact = [p.cpu().pin_memory() for p in pool[:4]]
+        for t in range(max(3, W)):
+            scene.step_host(hact[t % len(hact)], host)
+        barrier()
+        t0 = time.perf_counter()
+        n_rows = 0
+        for t in range(K):
+            n_rows += scene.step_host(hact[t % len(hact)], host)
+        barrier()
+        e2e_s = time.perf_counter() - t0
+        d2h = n_rows / K * (4 + 16 + 4 + 1 + 4) + (B + 1) * 4 + 3 * B * 4
+        e2e = {"agent_steps": n_rows, "seconds": e2e_s, "h2d": B * veh_cap * 4, "d2h": d2h}
+    scene.set_profiling(False)
+
+    # ---------------- reduce over ranks ----------------
+    vec = torch.tensor([total_ms, total_kern_ms, e2e["seconds"] if e2e else 0.0], dtype=torch.float64, device=dev)
+    sums = torch.tensor([dA, dV, e2e["agent_steps"] if e2e else 0.0], dtype=torch.float64, device=dev)
+    counters = scene.stats_tensor().clone()
+    if world > 1:
+        dist.all_reduce(vec, op=dist.ReduceOp.MAX)         # slowest rank defines the time
+        dist.all_reduce(sums, op=dist.ReduceOp.SUM)
+        dist.all_reduce(counters, op=dist.ReduceOp.SUM)    # end-of-rollout statistics over NVLink
+    total_ms, total_kern_ms, e2e_s = [float(x) for x in vec.tolist()]
+    dA_all, dV_all, e2e_rows = [float(x) for x in sums.tolist()]
+
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        peak = float(peaks.get("hbm_gbs", 6650.0))
+        peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6.65 TB/s"
+        # per-GPU achieved bandwidth of the step kernel: this rank's algorithmic bytes / its kernel time
+        alg_bytes = BYTES_PER_VEH * dV + BYTES_PER_AGENT * dA
+        my_kern_ms = float(sum(kern_ms))
+        achieved = alg_bytes / (my_kern_ms * 1e-3) / 1e9
+        line = {
+            "metric": METRIC, "value": dA_all / (total_ms * 1e-3), "unit": UNIT, "n_gpus": world,
+            "steps": K, "warmup": W, "ms_per_step": total_ms / K, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": workload_name(args), "l2": "flushed between timed steps (384 MiB fill)",
+                       "prime_ticks": PRIME_TICKS, "veh_cap": veh_cap, "agent_cap": agent_cap,
+                       "threads_per_cta": scene.threads, "smem_per_cta": scene.smem_bytes,
+                       "agents_per_env_step": dA / (K * B), "vehicles_per_env_step": dV / (K * B),
+                       "env_steps_per_s": world * B * K / (total_ms * 1e-3)},
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                         "kernel": "pve_step_kernel", "kernel_ms_per_launch": my_kern_ms / K,
+                         "scan_ms_per_launch": float(sum(scan_ms)) / K,
+                         "algorithmic_bytes_per_launch": alg_bytes / K},
+            "gpu_launches": 2 * K,
+            "clocks": sampler.result(),
+            "stats": {k: float(v) for k, v in zip(
+                ["agent_steps", "vehicle_steps", "env_steps", "spawned", "passed", "passed_step_total",
+                 "passed_jerk_sum", "collided_agent_steps", "lock_events", "reward_sum", "reward_sq_sum",
+                 "removed", "overflow"], counters.tolist())},
+            "wall_s_timed_region": wall1 - wall0,
+        }
+        if e2e:
+            line["e2e"] = {"value": e2e_rows / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(e2e["h2d"]),
+                           "d2h_bytes_per_step": int(e2e["d2h"]),
+                           "note": "pve_step_host: pinned host actions in; reward/ids/cpv/status/jerk_sum/"
+                                   "offsets/per-env counters out; observations stay in HBM for the device-side actor"}
+        if world == 1 and not args.no_cpu_baseline:
+            cores = os.cpu_count() or 1
+            n_envs = max(64, min(512, 8 * cores))
+            r = cpu_port_run(args, n_envs, PRIME_TICKS, 100, 5, cores)
+            r1 = cpu_port_run(args, 32, PRIME_TICKS, 100, 5, 1)
+            line["cpu_baseline"] = {
+                "value": r["agent_steps"] / r["elapsed"], "unit": UNIT, "cores": cores, "kind": "port",
+                "single_thread_value": r1["agent_steps"] / r1["elapsed"],
+                "sample": "oracle/scene_oracle.c (C port of the reference scene): %d intersections x 100 ticks "
+                          "after %d priming ticks on %d threads; single-thread figure on 32 intersections"
+                          % (n_envs, PRIME_TICKS, cores)}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        reference_arm(args, rank)
+        return
+    if world != args.gpus and world == 1 and args.gpus > 1:
+        # plain `python bench.py --gpus N`: re-launch under torchrun, one rank per GPU
+        import subprocess
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(args.gpus),
+               "--master-addr", "127.0.0.1", "--master-port", "29531", os.path.abspath(__file__)] + sys.argv[1:]
+        sys.exit(subprocess.call(cmd))
+    graft_arm(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

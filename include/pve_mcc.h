@@ -162,6 +162,14 @@ const pve_env_header *pve_hdr_dev(const pve_scene *s);
 
 int32_t pve_stats(pve_scene *s, pve_counters *out_dev, void *stream);
 
+/* measurement aids: CUDA events around the step kernel and the offset scan of the last pve_step
+ * (pve_kernel_ms waits for them), launch geometry, struct size for binding checks */
+int32_t pve_set_profiling(pve_scene *s, int32_t on);
+int32_t pve_kernel_ms(pve_scene *s, float *step_ms, float *scan_ms);
+int64_t pve_smem_bytes(const pve_scene *s);
+int32_t pve_threads(const pve_scene *s);
+int32_t pve_config_bytes(void);
+
 #ifdef __cplusplus
 }
 #endif

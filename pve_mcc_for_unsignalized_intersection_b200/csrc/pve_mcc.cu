@@ -49,6 +49,10 @@ struct pve_scene {
     double *counters_dev;
     int32_t *pinned_i32;         /* host-visible scratch: [0] next agent total */
     int64_t next_total;          /* rows of the next tick if known, else -1 */
+    int profiling;               /* record events around the step and scan kernels */
+#ifndef PVE_HOST_EMULATION
+    cudaEvent_t ev[3];
+#endif
     char err[512];
 };
 
@@ -271,6 +275,7 @@ static int32_t launch_scan(pve_scene *s, pve_stream_t stream) {
 static int32_t launch_step(pve_scene *s, const float *actions, const pve_outputs &O, pve_stream_t stream) {
     const int B = s->cfg.n_envs;
 #ifndef PVE_HOST_EMULATION
+    if (s->profiling) RT_CHECK(s, cudaEventRecord(s->ev[0], stream));
     switch (s->threads) {
         case 64:
             pve_step_kernel<64><<<B, 64, s->smem_bytes, stream>>>(s->prm, s->st, O, s->spawn_tick, actions, s->phase);
@@ -283,6 +288,7 @@ static int32_t launch_step(pve_scene *s, const float *actions, const pve_outputs
             break;
     }
     RT_CHECK(s, cudaGetLastError());
+    if (s->profiling) RT_CHECK(s, cudaEventRecord(s->ev[1], stream));
 #else
     (void)stream;
     unsigned char *smem = (unsigned char *)aligned_alloc(64, (s->smem_bytes + 63) / 64 * 64);
@@ -355,6 +361,9 @@ void pve_destroy(pve_scene *s) {
     rt_free(s->st.n_ctrl); rt_free(s->st.n_veh); rt_free(s->st.stats); rt_free(s->st.agent_offset);
     rt_free(s->actions_dev); rt_free(s->counters_dev);
     rt_host_free(s->pinned_i32);
+#ifndef PVE_HOST_EMULATION
+    for (int i = 0; i < 3; ++i) if (s->ev[i]) cudaEventDestroy(s->ev[i]);
+#endif
     delete s;
 }
 
@@ -473,7 +482,36 @@ int32_t pve_step(pve_scene *s, const float *actions_dev, const pve_outputs *out_
     int32_t rc = launch_step(s, actions_dev, O, stream);
     if (rc != PVE_OK) return rc;
     s->next_total = -1;
-    return launch_scan(s, stream);        /* row offsets of the NEXT tick */
+    rc = launch_scan(s, stream);          /* row offsets of the NEXT tick */
+#ifndef PVE_HOST_EMULATION
+    if (rc == PVE_OK && s->profiling) RT_CHECK(s, cudaEventRecord(s->ev[2], stream));
+#endif
+    return rc;
+}
+
+/* CUDA-event timing of the two kernels of the last pve_step (bench.py's roofline numbers).
+ * pve_kernel_ms synchronises on the last event. */
+int32_t pve_set_profiling(pve_scene *s, int32_t on) {
+    if (!s) return PVE_EINVAL;
+#ifndef PVE_HOST_EMULATION
+    if (on && !s->ev[0])
+        for (int i = 0; i < 3; ++i) RT_CHECK(s, cudaEventCreate(&s->ev[i]));
+#endif
+    s->profiling = on ? 1 : 0;
+    return PVE_OK;
+}
+
+int32_t pve_kernel_ms(pve_scene *s, float *step_ms, float *scan_ms) {
+    if (!s || !s->profiling) return PVE_EINVAL;
+#ifndef PVE_HOST_EMULATION
+    RT_CHECK(s, cudaEventSynchronize(s->ev[2]));
+    if (step_ms) RT_CHECK(s, cudaEventElapsedTime(step_ms, s->ev[0], s->ev[1]));
+    if (scan_ms) RT_CHECK(s, cudaEventElapsedTime(scan_ms, s->ev[1], s->ev[2]));
+#else
+    if (step_ms) *step_ms = 0.f;
+    if (scan_ms) *scan_ms = 0.f;
+#endif
+    return PVE_OK;
 }
 
 int64_t pve_next_agent_total(pve_scene *s, void *stream_) {

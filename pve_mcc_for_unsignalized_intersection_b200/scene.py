@@ -233,6 +233,16 @@ class BatchedScene:
         live = torch.arange(self.veh_cap, device=self.device)[None, :] < n_veh[:, None]
         return (((meta[:, :, 1] >> 24) & N.F_CONTROL) != 0) & live
 
+    # ---- measurement -------------------------------------------------------------------------
+    def set_profiling(self, on=True):
+        self._check(self.lib.pve_set_profiling(self._h, int(bool(on))))
+
+    def kernel_ms(self):
+        """(step kernel ms, offset-scan kernel ms) of the last ``step``; waits for it to finish."""
+        a, b = C.c_float(), C.c_float()
+        self._check(self.lib.pve_kernel_ms(self._h, C.byref(a), C.byref(b)))
+        return a.value, b.value
+
     # ---- end-of-rollout statistics ----------------------------------------------------------
     def stats_tensor(self):
         """16 float64 counters on the device (see ``pve_counters``); all-reduce them across ranks."""

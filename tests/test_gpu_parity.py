@@ -1,0 +1,127 @@
+"""GPU tier: the CUDA build (through the C ABI) against the CPU oracle and the golden traces."""
+import numpy as np
+import pytest
+import torch
+
+import parity as P
+import test_kernel_logic_emul as E
+from pve_mcc_for_unsignalized_intersection_b200.arrivals import stress_arrivals, synthetic_arrivals
+
+pytestmark = pytest.mark.gpu
+
+
+def test_backend_is_cuda():
+    scene = P.make_scene("cuda", 4)
+    assert scene.backend == "cuda-sm_100a"
+    assert torch.cuda.get_device_capability(0)[0] == 10
+
+
+@pytest.mark.parametrize("threads", [64, 128, 256])
+def test_free_running_matches_oracle(threads):
+    tabs = np.concatenate([synthetic_arrivals(4, lam, 50.0, seed=lam, rows=40) for lam in (400, 1000, 1200)])
+    B = tabs.shape[0]
+    scene = P.make_scene("cuda", B, vm=5, threads=threads)
+    orc = P.make_oracle(B, vm=5)
+    scene.reset(tabs, warmup=True)
+    orc.reset(tabs, warmup=True)
+    rng = np.random.RandomState(threads)
+    for t in range(420):
+        st = orc.get_state()
+        act = P.random_actions(rng, (st["flags"] & 1) != 0)
+        o_ref = orc.step(act)
+        o_dev = P.outputs_to_numpy(scene.step(P.to_device_actions(scene, act)))
+        P.compare_outputs(o_dev, o_ref, "threads=%d tick %d" % (threads, t))
+        if t % 20 == 0 or t == 419:
+            P.compare_states(scene.get_state(), orc.get_state(), "tick %d" % t)
+
+
+def test_train_setting_vm6_accel():
+    E.free_run("cuda", synthetic_arrivals(3, 1000, 40.0, seed=77, rows=32), vm=6, ticks=330, seed=2, policy="accel")
+
+
+def test_stress_occupancy_brake():
+    E.free_run("cuda", stress_arrivals(2, 40.0), vm=5, ticks=300, seed=3, veh_cap=384, agent_cap=320, policy="brake")
+
+
+@pytest.mark.parametrize("name", E.ROLLOUTS)
+def test_golden_rollout_direct(name, monkeypatch):
+    monkeypatch.setattr(E, "BACKEND", "cuda")
+    E.test_golden_rollout_direct(name)
+
+
+def test_crafted_order_dependence_cases(monkeypatch):
+    monkeypatch.setattr(E, "BACKEND", "cuda")
+    E.test_crafted_order_dependence_cases()
+
+
+def test_teacher_forced_every_tick():
+    """North-star protocol: every tick starts from the oracle's state copied onto the device."""
+    tabs = synthetic_arrivals(8, 1000, 45.0, seed=5, rows=40)
+    B = tabs.shape[0]
+    scene = P.make_scene("cuda", B, vm=5)
+    orc = P.make_oracle(B, vm=5)
+    scene.reset(tabs, warmup=True)
+    orc.reset(tabs, warmup=True)
+    rng = np.random.RandomState(9)
+    for t in range(400):
+        st = orc.get_state()
+        scene.set_state(P.oracle_state_for_device(st))
+        act = P.random_actions(rng, (st["flags"] & 1) != 0)
+        o_ref = orc.step(act)
+        o_dev = P.outputs_to_numpy(scene.step(P.to_device_actions(scene, act)))
+        P.compare_outputs(o_dev, o_ref, "teacher-forced tick %d" % t)
+        P.compare_states(scene.get_state(), orc.get_state(), "teacher-forced tick %d" % t)
+
+
+def test_full_size_4096_intersections_vs_oracle():
+    """BASELINE config 2 size: 4,096 intersections, density 1000, random actions; every 50th tick
+    compared row by row with the oracle running the same batch on the host cores."""
+    B = 4096
+    tabs = synthetic_arrivals(B, 1000, 32.0, seed=11, rows=24)
+    scene = P.make_scene("cuda", B, vm=5)
+    orc = P.make_oracle(B, vm=5, n_threads=32)
+    scene.reset(tabs, warmup=True)
+    orc.reset(tabs, warmup=True)
+    rng = np.random.RandomState(4)
+    total = 0
+    for t in range(260):
+        st_ctrl = scene.control_mask().cpu().numpy()
+        act = P.random_actions(rng, st_ctrl)
+        o_ref = orc.step(act)
+        out = scene.step(P.to_device_actions(scene, act))
+        total += out.n_agents
+        assert out.n_agents == len(o_ref["reward"]), t
+        if t % 50 == 0 or t == 259:
+            P.compare_outputs(P.outputs_to_numpy(out), o_ref, "B=4096 tick %d" % t)
+    P.compare_states(scene.get_state(), orc.get_state(), "B=4096 final")
+    s = scene.stats()
+    assert s["agent_steps"] == total and s["overflow"] == 0
+
+
+def test_step_host_end_to_end_matches_device_outputs():
+    B = 64
+    tabs = synthetic_arrivals(B, 1000, 30.0, seed=3, rows=24)
+    scene = P.make_scene("cuda", B)
+    scene.reset(tabs, warmup=True)
+    host = scene.make_host_outputs()
+    act = torch.zeros(B, scene.veh_cap, dtype=torch.float32).pin_memory()
+    rng = np.random.RandomState(0)
+    for t in range(150):
+        act.copy_(torch.from_numpy(rng.uniform(-3, 3, size=(B, scene.veh_cap)).astype(np.float32)))
+        n = scene.step_host(act, host, copy_obs=True)
+        assert n == int(host.agent_offset[-1])
+        for f in ("reward", "cpv", "status", "jerk_sum", "ids", "obs"):
+            assert torch.equal(getattr(host, f)[:n], getattr(scene.out, f)[:n].cpu()), (f, t)
+    assert n > 0
+
+
+def test_capacity_overflow_is_flagged_not_silent():
+    tabs = stress_arrivals(1, 30.0)
+    scene = P.make_scene("cuda", 1, veh_cap=64, agent_cap=48)
+    scene.reset(tabs, warmup=True)
+    act = torch.full((1, 64), -3.0, device="cuda")
+    for _ in range(200):
+        scene.step(act)
+    st = scene.get_state()
+    assert st["overflow"][0] > 0 and st["n_veh"][0] <= 64 and st["n_ctrl"][0] <= 48
+    assert scene.stats()["overflow"] > 0
