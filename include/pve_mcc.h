@@ -53,7 +53,7 @@ extern "C" {
  */
 typedef struct pve_config {
     int32_t n_envs;        /* B: intersections on this GPU                                   */
-    int32_t veh_cap;       /* dense vehicle slots per intersection (<= 1024)                  */
+    int32_t veh_cap;       /* dense vehicle slots per intersection (<= 576; rounded up to a class) */
     int32_t agent_cap;     /* controlled vehicles per intersection (<= veh_cap)               */
     int32_t threads;       /* CTA size: 0 = default, else 64 / 128 / 256                      */
     int64_t out_cap;       /* rows of the per-agent output arrays the caller will provide     */
@@ -168,6 +168,10 @@ int32_t pve_set_profiling(pve_scene *s, int32_t on);
 int32_t pve_kernel_ms(pve_scene *s, float *step_ms, float *scan_ms);
 int64_t pve_smem_bytes(const pve_scene *s);
 int32_t pve_threads(const pve_scene *s);
+/* capacities actually in use: the requested ones rounded up to a compiled capacity class
+ * (128/96, 192/128, 384/320, 576/416); every [B][veh_cap] array uses pve_veh_cap() as its stride */
+int32_t pve_veh_cap(const pve_scene *s);
+int32_t pve_agent_cap(const pve_scene *s);
 int32_t pve_config_bytes(void);
 
 #ifdef __cplusplus

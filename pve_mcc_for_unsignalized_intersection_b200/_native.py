@@ -73,6 +73,8 @@ def load_library(path=None):
     lib.pve_smem_bytes.argtypes = [vp]
     lib.pve_smem_bytes.restype = i64
     lib.pve_threads.argtypes = [vp]
+    lib.pve_veh_cap.argtypes = [vp]
+    lib.pve_agent_cap.argtypes = [vp]
     lib.pve_stats.argtypes = [vp, vp, vp]
     lib.pve_set_profiling.argtypes = [vp, i32]
     lib.pve_kernel_ms.argtypes = [vp, C.POINTER(C.c_float), C.POINTER(C.c_float)]

@@ -100,12 +100,12 @@ static void rt_host_free(void *p) { free(p); }
  * =========================================================================================== */
 #ifndef PVE_HOST_EMULATION
 
-template <int NT>
+template <int NT, int VC, int AC>
 __global__ void __launch_bounds__(NT)
 pve_step_kernel(const PveParams P, const PveState S, const pve_outputs O, const int32_t *spawn_tick,
                 const float *actions, const int phase) {
     extern __shared__ __align__(16) unsigned char pve_smem[];
-    pve_step_block<NT>(P, S, O, spawn_tick, actions, phase, (int)blockIdx.x, pve_smem);
+    pve_step_block<NT, VC, AC>(P, S, O, spawn_tick, actions, phase, (int)blockIdx.x, pve_smem);
 }
 
 /* agent_offset[b] = sum of n_ctrl[0..b): rows of the dense per-agent outputs.  One CTA. */
@@ -272,32 +272,67 @@ static int32_t launch_scan(pve_scene *s, pve_stream_t stream) {
     return PVE_OK;
 }
 
+/* capacity classes (compile-time shared-memory layouts): veh_cap / agent_cap are rounded up to one */
+#define PVE_CLASSES(X) X(128, 96) X(192, 128) X(384, 320) X(576, 416)
+
+static bool pick_class(int veh_cap, int agent_cap, int *VC, int *AC, size_t *smem) {
+#define X(vc, ac) if (veh_cap <= vc && agent_cap <= ac) { *VC = vc; *AC = ac; *smem = PveLayout<vc, ac>::BYTES; return true; }
+    PVE_CLASSES(X)
+#undef X
+    return false;
+}
+
+#ifndef PVE_HOST_EMULATION
+template <int NT, int VC, int AC>
+static cudaError_t launch_one(pve_scene *s, const float *actions, const pve_outputs &O, pve_stream_t stream) {
+    static bool attr_set[16] = {false};
+    int dev = s->device & 15;
+    if (!attr_set[dev]) {
+        cudaError_t e = cudaFuncSetAttribute(pve_step_kernel<NT, VC, AC>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             (int)PveLayout<VC, AC>::BYTES);
+        if (e != cudaSuccess) return e;
+        attr_set[dev] = true;
+    }
+    pve_step_kernel<NT, VC, AC><<<s->cfg.n_envs, NT, PveLayout<VC, AC>::BYTES, stream>>>(
+        s->prm, s->st, O, s->spawn_tick, actions, s->phase);
+    return cudaGetLastError();
+}
+#endif
+
 static int32_t launch_step(pve_scene *s, const float *actions, const pve_outputs &O, pve_stream_t stream) {
-    const int B = s->cfg.n_envs;
+    const int VCc = s->prm.VC, ACc = s->prm.AC;
 #ifndef PVE_HOST_EMULATION
     if (s->profiling) RT_CHECK(s, cudaEventRecord(s->ev[0], stream));
-    switch (s->threads) {
-        case 64:
-            pve_step_kernel<64><<<B, 64, s->smem_bytes, stream>>>(s->prm, s->st, O, s->spawn_tick, actions, s->phase);
-            break;
-        case 256:
-            pve_step_kernel<256><<<B, 256, s->smem_bytes, stream>>>(s->prm, s->st, O, s->spawn_tick, actions, s->phase);
-            break;
-        default:
-            pve_step_kernel<128><<<B, 128, s->smem_bytes, stream>>>(s->prm, s->st, O, s->spawn_tick, actions, s->phase);
-            break;
+    bool done = false;
+#define X(vc, ac)                                                                              \
+    if (!done && VCc == vc && ACc == ac) {                                                     \
+        done = true;                                                                           \
+        if (s->threads == 64) RT_CHECK(s, (launch_one<64, vc, ac>(s, actions, O, stream)));    \
+        else if (s->threads == 256) RT_CHECK(s, (launch_one<256, vc, ac>(s, actions, O, stream))); \
+        else RT_CHECK(s, (launch_one<128, vc, ac>(s, actions, O, stream)));                    \
     }
-    RT_CHECK(s, cudaGetLastError());
+    PVE_CLASSES(X)
+#undef X
+    if (!done) { snprintf(s->err, sizeof s->err, "internal: no kernel for class %d/%d", VCc, ACc); return PVE_EINVAL; }
     if (s->profiling) RT_CHECK(s, cudaEventRecord(s->ev[1], stream));
 #else
     (void)stream;
+    const int B = s->cfg.n_envs;
     unsigned char *smem = (unsigned char *)aligned_alloc(64, (s->smem_bytes + 63) / 64 * 64);
     if (!smem) return PVE_ENOMEM;
-    for (int b = 0; b < B; ++b) {
-        memset(smem, 0xA5, s->smem_bytes);      /* poison: catches reads of unwritten shared memory */
-        pve_step_block<64>(s->prm, s->st, O, s->spawn_tick, actions, s->phase, b, smem);
+    bool done = false;
+#define X(vc, ac)                                                                              \
+    if (!done && VCc == vc && ACc == ac) {                                                     \
+        done = true;                                                                           \
+        for (int b = 0; b < B; ++b) {                                                          \
+            memset(smem, 0xA5, s->smem_bytes); /* poison: catches reads of unwritten shared memory */ \
+            pve_step_block<64, vc, ac>(s->prm, s->st, O, s->spawn_tick, actions, s->phase, b, smem); \
+        }                                                                                      \
     }
+    PVE_CLASSES(X)
+#undef X
     free(smem);
+    if (!done) return PVE_EINVAL;
 #endif
     s->phase ^= 1;
     return PVE_OK;
@@ -377,11 +412,16 @@ int32_t pve_create(const pve_config *cfg, int32_t device, pve_scene **out) {
     s->cfg = *cfg;
     s->device = device;
     s->next_total = -1;
-    const int B = cfg->n_envs, VC = cfg->veh_cap, AC = cfg->agent_cap;
-    if (B <= 0 || VC <= 0 || VC > 1024 || AC <= 0 || AC > VC || cfg->out_cap < 0) {
-        snprintf(s->err, sizeof s->err, "invalid config: n_envs=%d veh_cap=%d agent_cap=%d", B, VC, AC);
+    const int B = cfg->n_envs;
+    int VC = 0, AC = 0;
+    if (B <= 0 || cfg->veh_cap <= 0 || cfg->agent_cap <= 0 || cfg->agent_cap > cfg->veh_cap || cfg->out_cap < 0 ||
+        !pick_class(cfg->veh_cap, cfg->agent_cap, &VC, &AC, &s->smem_bytes)) {
+        snprintf(s->err, sizeof s->err, "invalid config: n_envs=%d veh_cap=%d agent_cap=%d (largest class is 576/416)",
+                 B, cfg->veh_cap, cfg->agent_cap);
         return PVE_EINVAL;
     }
+    s->cfg.veh_cap = VC;          /* rounded up to the capacity class; see pve_veh_cap() */
+    s->cfg.agent_cap = AC;
     s->threads = cfg->threads == 0 ? 128 : cfg->threads;
     if (s->threads != 64 && s->threads != 128 && s->threads != 256) {
         snprintf(s->err, sizeof s->err, "threads must be 0, 64, 128 or 256");
@@ -410,16 +450,8 @@ int32_t pve_create(const pve_config *cfg, int32_t device, pve_scene **out) {
         }
     }
     P.B = B; P.VC = VC; P.AC = AC; P.K = 0; P.out_cap = cfg->out_cap;
-    s->smem_bytes = pve_smem_carve(nullptr, nullptr, VC, AC);
 #ifndef PVE_HOST_EMULATION
     RT_CHECK(s, cudaSetDevice(device));
-    if (s->smem_bytes > 227 * 1024) {
-        snprintf(s->err, sizeof s->err, "veh_cap/agent_cap need %zu bytes of shared memory (> 227 KB)", s->smem_bytes);
-        return PVE_EINVAL;
-    }
-    RT_CHECK(s, cudaFuncSetAttribute(pve_step_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->smem_bytes));
-    RT_CHECK(s, cudaFuncSetAttribute(pve_step_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->smem_bytes));
-    RT_CHECK(s, cudaFuncSetAttribute(pve_step_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->smem_bytes));
 #endif
     const size_t nv = (size_t)B * VC;
     RT_CHECK(s, rt_alloc((void **)&s->st.hdr, sizeof(pve_env_header) * (size_t)B));
@@ -608,6 +640,8 @@ const pve_veh_meta *pve_meta_dev(const pve_scene *s) { return s ? s->st.meta : n
 const pve_env_header *pve_hdr_dev(const pve_scene *s) { return s ? s->st.hdr : nullptr; }
 int64_t pve_smem_bytes(const pve_scene *s) { return s ? (int64_t)s->smem_bytes : 0; }
 int32_t pve_threads(const pve_scene *s) { return s ? s->threads : 0; }
+int32_t pve_veh_cap(const pve_scene *s) { return s ? s->cfg.veh_cap : 0; }
+int32_t pve_agent_cap(const pve_scene *s) { return s ? s->cfg.agent_cap : 0; }
 
 int32_t pve_stats(pve_scene *s, pve_counters *out_dev, void *stream_) {
     if (!s || !out_dev) return PVE_EINVAL;

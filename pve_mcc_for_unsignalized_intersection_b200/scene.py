@@ -67,7 +67,7 @@ class StepOutputs:
 class BatchedScene:
     """B independent 12-lane intersections resident on one GPU."""
 
-    def __init__(self, n_envs, config=None, veh_cap=160, agent_cap=96, out_cap=None, device="cuda:0",
+    def __init__(self, n_envs, config=None, veh_cap=128, agent_cap=96, out_cap=None, device="cuda:0",
                  threads=0, _library=None):
         self.cfg = config or SceneConfig()
         self.B, self.veh_cap, self.agent_cap = int(n_envs), int(veh_cap), int(agent_cap)
@@ -90,6 +90,9 @@ class BatchedScene:
         dev_index = self.device.index or 0
         rc = self.lib.pve_create(C.byref(ncfg), dev_index, C.byref(self._h))
         self._check(rc)
+        # capacities are rounded up to a compiled capacity class; the class value is the array stride
+        self.veh_cap = int(self.lib.pve_veh_cap(self._h))
+        self.agent_cap = int(self.lib.pve_agent_cap(self._h))
         self.out = StepOutputs(self.B, self.out_cap, self.device)
         self._out_native = self.out.native()
         self._spawn = None

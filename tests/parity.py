@@ -18,7 +18,7 @@ from oracle.oracle import OracleScene, scene_params  # noqa: E402
 RTOL = 1e-5          # north-star tolerance: fp32 outputs against the float64 reference
 
 
-def make_scene(backend, B, vm=5, collision_thr=2, veh_cap=160, agent_cap=96, threads=0, out_cap=None):
+def make_scene(backend, B, vm=5, collision_thr=2, veh_cap=128, agent_cap=96, threads=0, out_cap=None):
     cfg = SceneConfig(vm=vm, collision_thr=collision_thr)
     if backend == "cuda":
         return BatchedScene(B, cfg, veh_cap=veh_cap, agent_cap=agent_cap, out_cap=out_cap, device="cuda:0",
@@ -28,7 +28,7 @@ def make_scene(backend, B, vm=5, collision_thr=2, veh_cap=160, agent_cap=96, thr
                         _library=build_emul())
 
 
-def make_oracle(B, vm=5, collision_thr=2, veh_cap=160, n_threads=4):
+def make_oracle(B, vm=5, collision_thr=2, veh_cap=128, n_threads=4):
     return OracleScene(B, veh_cap, scene_params(vm=vm, collision_thr=collision_thr), n_threads=n_threads)
 
 

@@ -21,7 +21,7 @@ def test_free_running_matches_oracle(threads):
     tabs = np.concatenate([synthetic_arrivals(4, lam, 50.0, seed=lam, rows=40) for lam in (400, 1000, 1200)])
     B = tabs.shape[0]
     scene = P.make_scene("cuda", B, vm=5, threads=threads)
-    orc = P.make_oracle(B, vm=5)
+    orc = P.make_oracle(B, vm=5, veh_cap=scene.veh_cap)
     scene.reset(tabs, warmup=True)
     orc.reset(tabs, warmup=True)
     rng = np.random.RandomState(threads)
@@ -59,7 +59,7 @@ def test_teacher_forced_every_tick():
     tabs = synthetic_arrivals(8, 1000, 45.0, seed=5, rows=40)
     B = tabs.shape[0]
     scene = P.make_scene("cuda", B, vm=5)
-    orc = P.make_oracle(B, vm=5)
+    orc = P.make_oracle(B, vm=5, veh_cap=scene.veh_cap)
     scene.reset(tabs, warmup=True)
     orc.reset(tabs, warmup=True)
     rng = np.random.RandomState(9)
@@ -79,7 +79,7 @@ def test_full_size_4096_intersections_vs_oracle():
     B = 4096
     tabs = synthetic_arrivals(B, 1000, 32.0, seed=11, rows=24)
     scene = P.make_scene("cuda", B, vm=5)
-    orc = P.make_oracle(B, vm=5, n_threads=32)
+    orc = P.make_oracle(B, vm=5, veh_cap=scene.veh_cap, n_threads=32)
     scene.reset(tabs, warmup=True)
     orc.reset(tabs, warmup=True)
     rng = np.random.RandomState(4)
@@ -119,9 +119,9 @@ def test_capacity_overflow_is_flagged_not_silent():
     tabs = stress_arrivals(1, 30.0)
     scene = P.make_scene("cuda", 1, veh_cap=64, agent_cap=48)
     scene.reset(tabs, warmup=True)
-    act = torch.full((1, 64), -3.0, device="cuda")
-    for _ in range(200):
+    act = torch.full((1, scene.veh_cap), -3.0, device="cuda")
+    for _ in range(300):
         scene.step(act)
     st = scene.get_state()
-    assert st["overflow"][0] > 0 and st["n_veh"][0] <= 64 and st["n_ctrl"][0] <= 48
+    assert st["overflow"][0] > 0 and st["n_veh"][0] <= scene.veh_cap and st["n_ctrl"][0] <= scene.agent_cap
     assert scene.stats()["overflow"] > 0

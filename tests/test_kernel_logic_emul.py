@@ -14,10 +14,10 @@ from pve_mcc_for_unsignalized_intersection_b200.arrivals import stress_arrivals,
 BACKEND = "emul"
 
 
-def free_run(backend, tables, vm, ticks, seed, veh_cap=160, agent_cap=96, policy="uniform"):
+def free_run(backend, tables, vm, ticks, seed, veh_cap=128, agent_cap=96, policy="uniform"):
     B = tables.shape[0]
     scene = P.make_scene(backend, B, vm=vm, veh_cap=veh_cap, agent_cap=agent_cap)
-    orc = P.make_oracle(B, vm=vm, veh_cap=veh_cap)
+    orc = P.make_oracle(B, vm=vm, veh_cap=scene.veh_cap)
     scene.reset(tables, warmup=True)
     orc.reset(tables, warmup=True)
     P.compare_states(scene.get_state(), orc.get_state(), "after reset")
@@ -65,7 +65,7 @@ def test_golden_rollout_direct(name):
     """Kernel logic against the reference's own trace (no oracle in between)."""
     z, r = load_rollout(name)
     big = name == "stress_brake"
-    scene = P.make_scene(BACKEND, 1, vm=float(z["vm"]), veh_cap=384 if big else 160, agent_cap=320 if big else 96)
+    scene = P.make_scene(BACKEND, 1, vm=float(z["vm"]), veh_cap=384 if big else 128, agent_cap=320 if big else 96)
     scene.reset(z["table"], warmup=True)
     obs_at = {int(t): k for k, t in enumerate(z["obs_ticks"])}
     for t in range(int(z["n_ticks"])):
@@ -102,9 +102,10 @@ def test_crafted_order_dependence_cases():
                 ["p", "v", "a", "jerk_sum", "collision", "step", "seq_in_lane", "uid", "control", "finish",
                  "lock", "lock_a", "row0"] + STATE_KEYS_E}
         scene = P.make_scene(BACKEND, 1, vm=5, veh_cap=64, agent_cap=64)
+        cap = scene.veh_cap                      # rounded up to a capacity class
         scene.reset(r["table", c], warmup=False)
-        scene.set_state(P.oracle_state_for_device(snapshot_to_state(snap, 1, 64)))
-        act = np.zeros((1, 64), np.float32)
+        scene.set_state(P.oracle_state_for_device(snapshot_to_state(snap, 1, cap)))
+        act = np.zeros((1, cap), np.float32)
         a_in = r["actions_in", c]
         act[0, :len(a_in)] = a_in
         o = P.outputs_to_numpy(scene.step(P.to_device_actions(scene, act)))
