@@ -140,7 +140,9 @@ struct PveLayout {
     static constexpr uint32_t Q5 = HIT + AC;
     static constexpr uint32_t FIN5 = Q5 + AC;
     static constexpr uint32_t STATUS = FIN5 + AC;
-    static constexpr uint32_t BYTES = a16(STATUS + AC);
+    static constexpr uint32_t EDIR = STATUS + AC;                /* u8[EC] direction of each unsorted entry */
+    static constexpr uint32_t ZERO16 = a16(EDIR + EC);           /* 16 zero bytes: source of absent neighbour rows */
+    static constexpr uint32_t BYTES = ZERO16 + 16;
     static_assert(VC % 16 == 0 && AC % 16 == 0 && AC <= VC && VC <= 1024, "capacity class");
 };
 
@@ -156,10 +158,12 @@ enum { SRC_ZERO = 0, SRC_NEW = 1, SRC_PREV = 2 };
  * block collectives.  Device: warp ballot / shuffle + one smem exchange.  Host emulation:
  * sequential loops over the same shared arrays.
  * ------------------------------------------------------------------------------------------- */
-/* out[k] = number of set flags before k (k = 0..n), i.e. an exclusive scan; out[n] = total.
- * This is the stream-compaction index used for agent numbering and for vehicle removal. */
+/* out[k] = number of set flags before k (k = 0..n), i.e. an exclusive scan; out[n] = total, which is
+ * also returned to every thread.  This is the stream-compaction index used for agent numbering and
+ * for vehicle removal.  NO trailing barrier: thread t may read the out[k] it wrote itself
+ * (k = t, t + NT, ...) right away; the caller's next phase boundary publishes the rest. */
 template <int NT>
-PVE_DEV void pve_block_excl_scan(const uint8_t *flag, uint16_t *out, int n, int32_t *wsum) {
+PVE_DEV int pve_block_excl_scan(const uint8_t *flag, uint16_t *out, int n, int32_t *wsum) {
 #ifdef __CUDACC__
     const int tid = (int)threadIdx.x, lane = tid & 31, warp = tid >> 5;
     constexpr int NW = NT / 32;
@@ -179,12 +183,13 @@ PVE_DEV void pve_block_excl_scan(const uint8_t *flag, uint16_t *out, int n, int3
         carry += tot;
     }
     if (tid == 0) out[n] = (uint16_t)carry;
-    __syncthreads();
+    return carry;
 #else
     (void)wsum;
     int c = 0;
     for (int k = 0; k < n; ++k) { out[k] = (uint16_t)c; c += (flag[k] != 0); }
     out[n] = (uint16_t)c;
+    return c;
 #endif
 }
 
@@ -283,7 +288,8 @@ PVE_DEV void pve_step_block(const PveParams &P, const PveState &S, const pve_out
     uint8_t *const del = smem + L::DEL, *const slock = smem + L::SLOCK, *const ctl0 = smem + L::CTL0;
     int8_t *const slocka = (int8_t *)(smem + L::SLOCKA);
     uint8_t *const hit = smem + L::HIT, *const q5 = smem + L::Q5, *const fin5 = smem + L::FIN5;
-    uint8_t *const status = smem + L::STATUS;
+    uint8_t *const status = smem + L::STATUS, *const edir = smem + L::EDIR;
+    const pve_v4 *const zero16 = (const pve_v4 *)(smem + L::ZERO16);
 
     const size_t vbase = (size_t)b * (size_t)VC;
 
@@ -293,6 +299,7 @@ PVE_DEV void pve_step_block(const PveParams &P, const PveState &S, const pve_out
             ((pve_v4 *)hdr)[tid] = ((const pve_v4 *)(S.hdr + b))[tid];
         for (int q = tid; q < M_COUNT; q += NT) misc[q] = 0;
         if (tid < 16) { vl_cnt[tid] = 0; headk[tid] = -1; }
+        if (tid == 16) { pve_v4 z; z.x = 0; z.y = 0; z.z = 0; z.w = 0; *(pve_v4 *)(smem + L::ZERO16) = z; }
     PVE_END_TID
 
     /* ---- L1: lane offsets (every lane of warp 0 sums its own prefix) ----------------------- */
@@ -400,53 +407,68 @@ PVE_DEV void pve_step_block(const PveParams &P, const PveState &S, const pve_out
     PVE_END_TID
 
     /* ---- agent numbering: controlled at step() time == gets outputs this tick ------------- */
-    pve_block_excl_scan<NT>(ctl0, acnt, V, wsum);
-    const int A = acnt[V];
+    const int A = pve_block_excl_scan<NT>(ctl0, acnt, V, wsum);
 
-    /* ---- D: agent tables; capacity of each virtual lane ------------------------------------ */
+    /* ---- D: agent tables (each thread uses only the counts it wrote itself) ---------------- */
     PVE_FOR_TID(tid)
         for (int k = tid; k < V; k += NT)
             if (ctl0[k]) vidx[acnt[k]] = (uint16_t)k;
         for (int g = tid; g < A; g += NT) {
             incb[g] = 0; inct[g] = 0; q5[g] = 0; fin5[g] = 0; status[g] = 0; hit[g] = 0;
         }
-        if (tid <= PVE_NLANE) {
-            /* own agents + agents of the 4 conflicting lanes, for every non-empty lane before tid */
+        for (int e = tid; e < (L::EC + 3) / 4; e += NT) ((uint32_t *)edir)[e] = 0xFFFFFFFFu;
+    PVE_END_TID
+
+    /* ---- D2: capacity of each virtual lane: own agents + agents of the 4 conflicting lanes - */
+    PVE_FOR_TID(tid)
+        if (tid < PVE_NLANE) {
+            const int d = tid;
             int o = 0;
-            for (int d = 0; d < tid; ++d)
-                if (hdr->lane_n[d] > 0) {                                        /* TIS:234 */
-                    o += (int)acnt[lane_off[d + 1]] - (int)acnt[lane_off[d]];
-                    if (d % 3 != 2)
-                        for (int q = 0; q < 4; ++q) {
-                            const int Lq = P.l2l[d][q];
-                            o += (int)acnt[lane_off[Lq + 1]] - (int)acnt[lane_off[Lq]];
-                        }
+            if (hdr->lane_n[d] > 0) {                                            /* TIS:234 */
+                o = (int)acnt[lane_off[d + 1]] - (int)acnt[lane_off[d]];
+                if (d % 3 != 2) {
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const int Lq = P.l2l[d][q];
+                        o += (int)acnt[lane_off[Lq + 1]] - (int)acnt[lane_off[Lq]];
+                    }
                 }
+            }
+            wsum[16 + d] = o;
+        }
+    PVE_END_TID
+    PVE_FOR_TID(tid)
+        if (tid <= PVE_NLANE) {
+            int o = 0;
+            for (int d = 0; d < tid; ++d) o += wsum[16 + d];
             vl_base[tid] = o;
         }
     PVE_END_TID
 
-    /* ---- E: virtual-lane membership, one (agent, target lane) pair per work item ---------- */
+    /* ---- E: virtual-lane membership: each agent offers itself to its own lane and to the four
+     *         lanes it conflicts with --------------------------------------------------------- */
     PVE_FOR_TID(tid)
-        for (int it = tid; it < 5 * A; it += NT) {
-            const int g = it / 5, s = it - g * 5;
+        for (int g = tid; g < A; g += NT) {
             const int k = vidx[g];
             const int Lk = lane_of[k];
-            int d = -1;
-            double pos = 0;
-            if (s == 0) {
-                d = Lk; pos = sp[k];                                             /* TIS:242-249 */
-            } else if (Lk % 3 != 2) {
-                const int dd = P.rev_dir[Lk][s - 1], q = P.rev_k[Lk][s - 1];
-                if (hdr->lane_n[dd] > 0) {                                       /* TIS:234, 259 */
-                    const int mv = dd % 3;
-                    const double delta = (sp[k] - P.vd_a1[mv][q]) + P.vd_a2[mv][q];      /* TIS:733-803 */
-                    if (delta > 0) { d = dd; pos = P.vd_b[mv][q] + delta; }
-                }
+            const double p = sp[k];
+            {
+                const int e = vl_base[Lk] + PVE_ATOMIC_ADD(&vl_cnt[Lk], 1);     /* TIS:242-249 */
+                epos[e] = p; eidx[e] = (uint16_t)k; edir[e] = (uint8_t)Lk;
             }
-            if (d >= 0) {
-                const int e = vl_base[d] + PVE_ATOMIC_ADD(&vl_cnt[d], 1);
-                epos[e] = pos; eidx[e] = (uint16_t)k;
+            if (Lk % 3 != 2) {
+#pragma unroll
+                for (int s = 0; s < 4; ++s) {
+                    const int dd = P.rev_dir[Lk][s], q = P.rev_k[Lk][s];
+                    if (hdr->lane_n[dd] > 0) {                                   /* TIS:234, 259 */
+                        const int mv = dd % 3;
+                        const double delta = (p - P.vd_a1[mv][q]) + P.vd_a2[mv][q];      /* TIS:733-803 */
+                        if (delta > 0) {
+                            const int e = vl_base[dd] + PVE_ATOMIC_ADD(&vl_cnt[dd], 1);
+                            epos[e] = P.vd_b[mv][q] + delta; eidx[e] = (uint16_t)k; edir[e] = (uint8_t)dd;
+                        }
+                    }
+                }
             }
         }
     PVE_END_TID
@@ -454,21 +476,21 @@ PVE_DEV void pve_step_block(const PveParams &P, const PveState &S, const pve_out
     /* ---- F: stable sort by position (TIS:271) as a rank count on the key (pos, slot) ------ */
     PVE_FOR_TID(tid)
         for (int e = tid; e < vl_base[PVE_NLANE]; e += NT) {
-            int d = 0;
-#pragma unroll
-            for (int q = 1; q < PVE_NLANE; ++q) d += (e >= vl_base[q]) ? 1 : 0;
-            const int base = vl_base[d], n = vl_cnt[d];
-            if (e - base < n) {
+            const int d = edir[e];
+            if (d != 0xFF) {
+                const int base = vl_base[d], n = vl_cnt[d];
                 const double pos = epos[e];
                 const int idx = eidx[e];
-                int rank = 0, ties = 0;
-                for (int t = 0; t < n; ++t) {
-                    const double pt = epos[base + t];
-                    rank += (pt < pos) ? 1 : 0;
-                    ties += (pt == pos) ? 1 : 0;
+                int less = 0, leq = 0, t = 0;
+                for (; t + 2 <= n; t += 2) {
+                    const double p0 = epos[base + t], p1 = epos[base + t + 1];
+                    less += (p0 < pos) ? 1 : 0; leq += (p0 <= pos) ? 1 : 0;
+                    less += (p1 < pos) ? 1 : 0; leq += (p1 <= pos) ? 1 : 0;
                 }
-                if (ties > 1)                       /* equal positions keep insertion (slot) order */
-                    for (int t = 0; t < n; ++t)
+                if (t < n) { const double p0 = epos[base + t]; less += (p0 < pos) ? 1 : 0; leq += (p0 <= pos) ? 1 : 0; }
+                int rank = less;
+                if (leq - less > 1)                 /* equal positions keep insertion (slot) order */
+                    for (t = 0; t < n; ++t)
                         rank += (epos[base + t] == pos && (int)eidx[base + t] < idx) ? 1 : 0;
                 spos[base + rank] = pos; sidx[base + rank] = (uint16_t)idx;
                 if (lane_of[idx] == d) arank[acnt[idx]] = (uint16_t)rank;
@@ -619,10 +641,10 @@ PVE_DEV void pve_step_block(const PveParams &P, const PveState &S, const pve_out
             vd0s[g] = fin5[g] ? sjs[k] : 0.0;                                    /* TIS:358 (statistics) */
             if (!((spk[k] >> 24) & PVE_F_CONTROL) || del[k]) continue;
             int t = g, len = 0;
+#pragma unroll
             for (int hop = 1; hop <= 10; ++hop) {                                /* TIS:1470-1478 */
-                t = hdra[t];
-                if (t < 0) break;
-                if (t == g) { len = hop; break; }
+                t = (t >= 0 && len == 0) ? (int)hdra[t] : -1;
+                len = (t == g) ? hop : len;
             }
             if (len == 0) continue;
             slock[k] = 1;                                                        /* TIS:1482 */
@@ -660,6 +682,9 @@ PVE_DEV void pve_step_block(const PveParams &P, const PveState &S, const pve_out
 
     /* ---- removal by stream compaction (TIS:435-444): survivors keep their order ----------- */
     pve_block_excl_scan<NT>(fbits, surv, V, wsum);
+    PVE_FOR_TID(tid)
+        (void)tid;
+    PVE_END_TID
 
     /* ---- J: arrivals (TIS:378-433) and header update, one thread per lane ------------------ */
     PVE_FOR_TID(tid)
@@ -790,34 +815,39 @@ PVE_DEV void pve_step_block(const PveParams &P, const PveState &S, const pve_out
                 if (O.status) O.status[obase + g] = status[g];
                 if (O.jerk_sum) O.jerk_sum[obase + g] = (float)sjs[k];
             }
-            /* 7 x 28 observation: row 0 = own row, row q+1 = neighbour q's stored row (Q3).  Work item =
-             * one 16-byte piece; 8 lanes per row (7 active), loads of four pieces are issued together. */
+            /* 7 x 28 observation: row 0 = own row, row q+1 = neighbour q's stored row (Q3).  Eight lanes
+             * per 112-byte row (7 active, one 16-byte piece each); a thread keeps its piece index and walks
+             * the rows, so there is no index division; the source (this tick's row in shared memory, last
+             * tick's row in HBM, or zeros) is one generic pointer, so there is no divergence; the loads
+             * of four rows are issued before their stores. */
             if (O.obs) {
-                pve_v4 *PVE_RESTRICT dst = (pve_v4 *)O.obs + obase * (PVE_OBS_H * PVE_OBS_W / 4);
-                const pve_v4 *PVE_RESTRICT prev4 = (const pve_v4 *)(S.row0[phase] + vbase * PVE_OBS_W);
-                const pve_v4 *new4 = (const pve_v4 *)row0;
-                const int n_items = A * 7 * 8;
-                for (int it0 = tid; it0 < n_items; it0 += 4 * NT) {
-                    pve_v4 val[4];
-                    int dsti[4];
+                constexpr int RPI = NT / 8;                 /* rows per pass of the CTA */
+                const int q = tid & 7;
+                if (q < 7) {
+                    pve_v4 *PVE_RESTRICT dst = (pve_v4 *)O.obs + obase * (PVE_OBS_H * PVE_OBS_W / 4) + q;
+                    const pve_v4 *PVE_RESTRICT prev4 = (const pve_v4 *)(S.row0[phase] + vbase * PVE_OBS_W) + q;
+                    const pve_v4 *new4 = (const pve_v4 *)row0 + q;
+                    const int n_rows = A * 7;
+                    int gr = tid >> 3;
+                    int g = gr / 7, rw = gr - g * 7;
+                    for (; gr < n_rows; gr += 4 * RPI) {
+                        pve_v4 val[4];
 #pragma unroll
-                    for (int u = 0; u < 4; ++u) {
-                        const int it = it0 + u * NT;
-                        const int q = it & 7, gr = it >> 3;       /* gr = g * 7 + row */
-                        dsti[u] = -1;
-                        val[u].x = 0; val[u].y = 0; val[u].z = 0; val[u].w = 0;
-                        if (it < n_items && q < 7) {
-                            const int g = gr / 7;
-                            const int code = srcc[g * 8 + (gr - g * 7)];
-                            const int kind = code >> 14, idx = code & 0x3FFF;
-                            dsti[u] = gr * 7 + q;
-                            if (kind == SRC_NEW) val[u] = new4[idx * 7 + q];
-                            else if (kind == SRC_PREV) val[u] = prev4[idx * 7 + q];
+                        for (int u = 0; u < 4; ++u) {
+                            const pve_v4 *src = zero16;
+                            if (gr + u * RPI < n_rows) {
+                                const int code = srcc[g * 8 + rw];
+                                const int kind = code >> 14, idx = code & 0x3FFF;
+                                src = (kind == SRC_PREV) ? prev4 + idx * 7 : ((kind == SRC_NEW) ? new4 + idx * 7 : zero16);
+                            }
+                            val[u] = *src;
+                            rw += RPI % 7; g += RPI / 7;
+                            if (rw >= 7) { rw -= 7; g += 1; }
                         }
-                    }
 #pragma unroll
-                    for (int u = 0; u < 4; ++u)
-                        if (dsti[u] >= 0) dst[dsti[u]] = val[u];
+                        for (int u = 0; u < 4; ++u)
+                            if (gr + u * RPI < n_rows) dst[(gr + u * RPI) * 7] = val[u];
+                    }
                 }
             }
         }
