@@ -31,6 +31,7 @@
 #pragma once
 #include <math.h>
 #include <stdint.h>
+#include <string.h>
 
 #include "pve_mcc.h"
 
@@ -83,8 +84,10 @@ enum { PVE_STAT_AGENT = 0, PVE_STAT_VEH, PVE_STAT_COLL, PVE_STAT_LOCK, PVE_STAT_
 /* ---------------------------------------------------------------------------------------------
  * shared-memory layout: compile-time offsets for a capacity class (VC vehicle slots, AC agents,
  * EC = 5*AC virtual-lane entries).  Regions R1 and R2 are reused along the tick:
- *   R1: step candidates (phases A-C) -> unsorted virtual-lane entries (E-F) -> row 0 of every agent (G1-M)
+ *   R1: step candidates (phases A-C) -> unsorted virtual-lane entries (E-F)
  *   R2: sorted virtual lanes (F-G1) -> world coordinates of the agents (G2-G3)
+ * The 28-float observation rows are never staged in shared memory: each agent writes its row 0
+ * straight into its output block and later phases read it back through L2.
  * ------------------------------------------------------------------------------------------- */
 template <int VC, int AC>
 struct PveLayout {
@@ -98,11 +101,10 @@ struct PveLayout {
     static constexpr uint32_t SJR = SA + 8 * VC;     /* jerk / dt */
     static constexpr uint32_t SJS = SJR + 8 * VC;
     static constexpr uint32_t R1 = a16(SJS + 8 * VC);
-    static constexpr uint32_t CTA0 = R1, CTA1 = CTA0 + 8 * VC, CP0 = CTA1 + 8 * VC, CV0 = CP0 + 8 * VC,
+    static constexpr uint32_t CTA0 = R1, CP0 = CTA0 + 8 * VC, CV0 = CP0 + 8 * VC,
                               CP1 = CV0 + 8 * VC, CV1 = CP1 + 8 * VC;
     static constexpr uint32_t EPOS = R1, EIDX = EPOS + 8 * EC;
-    static constexpr uint32_t ROW0 = R1;
-    static constexpr uint32_t R1_BYTES = mx(mx(48 * VC, a16(10 * EC)), 112 * AC);
+    static constexpr uint32_t R1_BYTES = mx(40 * VC, a16(10 * EC));
     static constexpr uint32_t R2 = a16(R1 + R1_BYTES);
     static constexpr uint32_t SPOS = R2, SIDX = SPOS + 8 * EC;
     static constexpr uint32_t XY = R2;
@@ -141,8 +143,7 @@ struct PveLayout {
     static constexpr uint32_t FIN5 = Q5 + AC;
     static constexpr uint32_t STATUS = FIN5 + AC;
     static constexpr uint32_t EDIR = STATUS + AC;                /* u8[EC] direction of each unsorted entry */
-    static constexpr uint32_t ZERO16 = a16(EDIR + EC);           /* 16 zero bytes: source of absent neighbour rows */
-    static constexpr uint32_t BYTES = ZERO16 + 16;
+    static constexpr uint32_t BYTES = a16(EDIR + EC);
     static_assert(VC % 16 == 0 && AC % 16 == 0 && AC <= VC && VC <= 1024, "capacity class");
 };
 
@@ -151,8 +152,25 @@ enum { M_V = 0, M_NREM, M_PASSED, M_COLL, M_LOCK, M_NCTRL, M_Q5U, M_PSTEP, M_COL
        M_COUNT = M_NEWN0 + 12 };
 static_assert(M_COUNT <= 48, "misc block");
 
-/* gather codes for the 7 x 28 observation (phase M): kind << 14 | index */
-enum { SRC_ZERO = 0, SRC_NEW = 1, SRC_PREV = 2 };
+/* gather codes for observation rows 1..6 (phase M): bit 15 clear -> this tick's row 0 of agent
+ * `index` (in the output block), bit 15 set -> last tick's stored row of vehicle slot `index`.  The
+ * last slot of every intersection (VC - 1) is never occupied and its stored row stays zero: it is
+ * the source of absent neighbours' rows (TIS:1335). */
+#define PVE_SRC_PREV 0x8000u
+
+PVE_DEV uint32_t pve_fbits(float f) { uint32_t u; memcpy(&u, &f, sizeof u); return u; }
+PVE_DEV pve_v4 pve_pack4(float a, float b, float c, float d) {
+    pve_v4 r; r.x = pve_fbits(a); r.y = pve_fbits(b); r.z = pve_fbits(c); r.w = pve_fbits(d); return r;
+}
+/* read back data this CTA wrote to global memory earlier in the kernel: L2, not L1 */
+#ifdef __CUDACC__
+PVE_DEV pve_v4 pve_ld_l2(const pve_v4 *p) {
+    const uint4 v = __ldcg(reinterpret_cast<const uint4 *>(p));
+    pve_v4 r; r.x = v.x; r.y = v.y; r.z = v.z; r.w = v.w; return r;
+}
+#else
+PVE_DEV pve_v4 pve_ld_l2(const pve_v4 *p) { return *p; }
+#endif
 
 /* ---------------------------------------------------------------------------------------------
  * block collectives.  Device: warp ballot / shuffle + one smem exchange.  Host emulation:
@@ -262,12 +280,11 @@ PVE_DEV void pve_step_block(const PveParams &P, const PveState &S, const pve_out
     double *const sp = (double *)(smem + L::SP), *const sv = (double *)(smem + L::SV);
     double *const sa = (double *)(smem + L::SA), *const sjr = (double *)(smem + L::SJR);
     double *const sjs = (double *)(smem + L::SJS);
-    double *const cta0 = (double *)(smem + L::CTA0), *const cta1 = (double *)(smem + L::CTA1);
+    double *const cta0 = (double *)(smem + L::CTA0);
     double *const cp0 = (double *)(smem + L::CP0), *const cv0 = (double *)(smem + L::CV0);
     double *const cp1 = (double *)(smem + L::CP1), *const cv1 = (double *)(smem + L::CV1);
     double *const epos = (double *)(smem + L::EPOS), *const spos = (double *)(smem + L::SPOS);
     uint16_t *const eidx = (uint16_t *)(smem + L::EIDX), *const sidx = (uint16_t *)(smem + L::SIDX);
-    float *const row0 = (float *)(smem + L::ROW0);
     double *const xy = (double *)(smem + L::XY);
     double *const virdis = (double *)(smem + L::VIRDIS), *const vd0s = (double *)(smem + L::VD0);
     double *const dsum = (double *)(smem + L::DSUM);
@@ -289,7 +306,6 @@ PVE_DEV void pve_step_block(const PveParams &P, const PveState &S, const pve_out
     int8_t *const slocka = (int8_t *)(smem + L::SLOCKA);
     uint8_t *const hit = smem + L::HIT, *const q5 = smem + L::Q5, *const fin5 = smem + L::FIN5;
     uint8_t *const status = smem + L::STATUS, *const edir = smem + L::EDIR;
-    const pve_v4 *const zero16 = (const pve_v4 *)(smem + L::ZERO16);
 
     const size_t vbase = (size_t)b * (size_t)VC;
 
@@ -299,7 +315,6 @@ PVE_DEV void pve_step_block(const PveParams &P, const PveState &S, const pve_out
             ((pve_v4 *)hdr)[tid] = ((const pve_v4 *)(S.hdr + b))[tid];
         for (int q = tid; q < M_COUNT; q += NT) misc[q] = 0;
         if (tid < 16) { vl_cnt[tid] = 0; headk[tid] = -1; }
-        if (tid == 16) { pve_v4 z; z.x = 0; z.y = 0; z.z = 0; z.w = 0; *(pve_v4 *)(smem + L::ZERO16) = z; }
     PVE_END_TID
 
     /* ---- L1: lane offsets (every lane of warp 0 sums its own prefix) ----------------------- */
@@ -317,6 +332,10 @@ PVE_DEV void pve_step_block(const PveParams &P, const PveState &S, const pve_out
         }
     PVE_END_TID
     const int V = misc[M_V];
+    const int64_t obase = (int64_t)S.agent_offset[b];
+    /* this intersection's block of the dense observation output (null: rows are not emitted) */
+    pve_v4 *const oblk = (O.obs != nullptr && misc[M_OUTOK]) ? (pve_v4 *)O.obs + obase * (PVE_OBS_H * PVE_OBS_W / 4)
+                                                             : nullptr;
 
     /* ---- A: load vehicles, both candidate next states (Q1) --------------------------------- */
     PVE_FOR_TID(tid)
@@ -342,7 +361,7 @@ PVE_DEV void pve_step_block(const PveParams &P, const PveState &S, const pve_out
             double v0n = fmin(P.vM, fmax(v + ta0 * P.dt, P.vm));                 /* TIS:1530 */
             double v1n = fmin(P.vM, fmax(v + ta1 * P.dt, P.vm));
             if (!ctrl) { v0n = P.v0; v1n = P.v0; }                               /* TIS:1535 */
-            cta0[k] = ta0; cta1[k] = ta1;
+            cta0[k] = ta0;
             cp0[k] = pv - 0.5 * ta0 * P.dt2;                                     /* TIS:1528 */
             cp1[k] = pv - 0.5 * ta1 * P.dt2;
             cv0[k] = v0n; cv1[k] = v1n;
@@ -350,7 +369,8 @@ PVE_DEV void pve_step_block(const PveParams &P, const PveState &S, const pve_out
             suid[k] = mt.uid; spk[k] = mt.packed;
             lane_of[k] = (uint8_t)i;
             ctl0[k] = ctrl ? 1 : 0;
-            del[k] = 0; slock[k] = 0; slocka[k] = 0;
+            del[k] = forced ? 1 : 0;        /* borrowed until phase C */
+            slock[k] = 0; slocka[k] = 0;
         }
     PVE_END_TID
 
@@ -391,7 +411,8 @@ PVE_DEV void pve_step_block(const PveParams &P, const PveState &S, const pve_out
     PVE_FOR_TID(tid)
         for (int k = tid; k < V; k += NT) {
             const int s = ssel[k];
-            const double a_new = s ? cta1[k] : cta0[k];
+            const double a_new = (s && !del[k]) ? P.am : cta0[k];                /* TIS:1516-1520 */
+            del[k] = 0;
             const double jr = (a_new - sa[k]) / P.dt;                            /* TIS:1522, 316, 321 */
             sjr[k] = jr;
             if (ctl0[k]) sjs[k] += fabs(jr);                                     /* TIS:321 */
@@ -512,9 +533,8 @@ PVE_DEV void pve_step_block(const PveParams &P, const PveState &S, const pve_out
             /* six nearest by |delta|, ties to the lower list index (stable sort, TIS:1389) */
             int lo = r - 1, hi = r + 1, run_cur = 0, run_end = -1;
             double run_d = 0;
-            float *row = row0 + (size_t)g * PVE_OBS_W;
-            row[0] = (float)pe; row[1] = (float)sv[k]; row[2] = (float)sa[k]; row[3] = (float)d;   /* TIS:1336 */
-            srcc[g * 8] = (uint16_t)((SRC_NEW << 14) | g);
+            pve_v4 *const orow = oblk ? oblk + g * (PVE_OBS_H * PVE_OBS_W / 4) : nullptr;   /* obs[g][0][:] */
+            if (orow) orow[0] = pve_pack4((float)pe, (float)sv[k], (float)sa[k], (float)d);   /* TIS:1336 */
             nn0[g] = 0xFFFFu;
             vd0s[g] = 0.0;
             for (int q = 0; q < PVE_NNBR; ++q) {
@@ -528,19 +548,17 @@ PVE_DEV void pve_step_block(const PveParams &P, const PveState &S, const pve_out
                 int pick = -1;
                 if (has_lo && (!has_hi || run_d <= fabs(spos[base + hi] - pe))) pick = run_cur++;
                 else if (has_hi) pick = hi++;
-                float *o4 = row + 4 * (q + 1);
                 if (pick >= 0) {
                     const int kn = sidx[base + pick];
                     const double vd = spos[base + pick];
-                    o4[0] = (float)vd; o4[1] = (float)sv[kn]; o4[2] = (float)sa[kn];
-                    o4[3] = (float)lane_of[kn];                                  /* TIS:1330 */
+                    if (orow) orow[q + 1] = pve_pack4((float)vd, (float)sv[kn], (float)sa[kn],
+                                                      (float)lane_of[kn]);       /* TIS:1330 */
                     /* Q3: neighbour already processed this tick -> its new row, else last tick's */
-                    srcc[g * 8 + q + 1] = (kn < k) ? (uint16_t)((SRC_NEW << 14) | acnt[kn])
-                                                   : (uint16_t)((SRC_PREV << 14) | kn);
+                    srcc[g * 8 + q + 1] = (kn < k) ? (uint16_t)acnt[kn] : (uint16_t)(PVE_SRC_PREV | kn);
                     if (q == 0) { nn0[g] = (uint16_t)kn; vd0s[g] = vd; }
                 } else {
-                    o4[0] = 0.f; o4[1] = 0.f; o4[2] = 0.f; o4[3] = 0.f;          /* TIS:1334 */
-                    srcc[g * 8 + q + 1] = (uint16_t)(SRC_ZERO << 14);
+                    if (orow) orow[q + 1] = pve_pack4(0.f, 0.f, 0.f, 0.f);       /* TIS:1334 */
+                    srcc[g * 8 + q + 1] = (uint16_t)(PVE_SRC_PREV | (VC - 1));   /* the always-zero row */
                 }
             }
         }
@@ -701,7 +719,7 @@ PVE_DEV void pve_step_block(const PveParams &P, const PveState &S, const pve_out
             }
             /* arrivals are granted in lane order while there is room (capacity is a sticky error) */
             const int total = surv[V], nctrl = misc[M_NCTRL];
-            int room = VC - total;
+            int room = (VC - 1) - total;         /* slot VC-1 stays empty: its stored row is the zero row */
             room = (AC - nctrl) < room ? (AC - nctrl) : room;
             int before = 0, want = 0, surv_i = 0;
             for (int q = 0; q <= i; ++q) {
@@ -768,19 +786,19 @@ PVE_DEV void pve_step_block(const PveParams &P, const PveState &S, const pve_out
             for (int q = 0; q < PVE_OBS_W / 4; ++q) ((pve_v4 *)(row0_next + (size_t)np * PVE_OBS_W))[q] = z;
         }
         /* stored row 0 of every surviving agent -> next tick's neighbour rows / actor input */
-        for (int it = tid; it < A * 8; it += NT) {
-            const int g = it >> 3, q = it & 7;
-            const int k = vidx[g];
-            if (q < 7 && !del[k]) {
-                const int np = (int)surv[k] + misc[M_SPREF0 + lane_of[k]];
-                ((pve_v4 *)(row0_next + (size_t)np * PVE_OBS_W))[q] = ((const pve_v4 *)(row0 + (size_t)g * PVE_OBS_W))[q];
+        if (oblk)
+            for (int it = tid; it < A * 8; it += NT) {
+                const int g = it >> 3, q = it & 7;
+                const int k = vidx[g];
+                if (q < 7 && !del[k]) {
+                    const int np = (int)surv[k] + misc[M_SPREF0 + lane_of[k]];
+                    ((pve_v4 *)(row0_next + (size_t)np * PVE_OBS_W))[q] = pve_ld_l2(oblk + g * 49 + q);
+                }
             }
-        }
     PVE_END_TID
 
     /* ---- M: outputs ------------------------------------------------------------------------ */
     pve_warp0_sums<NT>(rew, vd0s, A, dsum);
-    const int64_t obase = (int64_t)S.agent_offset[b];
     const bool out_ok = misc[M_OUTOK] != 0;
     PVE_FOR_TID(tid)
         if (tid < PVE_HDR_BYTES / 16) ((pve_v4 *)(S.hdr + b))[tid] = ((const pve_v4 *)hdr)[tid];
@@ -815,39 +833,41 @@ PVE_DEV void pve_step_block(const PveParams &P, const PveState &S, const pve_out
                 if (O.status) O.status[obase + g] = status[g];
                 if (O.jerk_sum) O.jerk_sum[obase + g] = (float)sjs[k];
             }
-            /* 7 x 28 observation: row 0 = own row, row q+1 = neighbour q's stored row (Q3).  Eight lanes
-             * per 112-byte row (7 active, one 16-byte piece each); a thread keeps its piece index and walks
-             * the rows, so there is no index division; the source (this tick's row in shared memory, last
-             * tick's row in HBM, or zeros) is one generic pointer, so there is no divergence; the loads
-             * of four rows are issued before their stores. */
-            if (O.obs) {
-                constexpr int RPI = NT / 8;                 /* rows per pass of the CTA */
-                const int q = tid & 7;
-                if (q < 7) {
-                    pve_v4 *PVE_RESTRICT dst = (pve_v4 *)O.obs + obase * (PVE_OBS_H * PVE_OBS_W / 4) + q;
-                    const pve_v4 *PVE_RESTRICT prev4 = (const pve_v4 *)(S.row0[phase] + vbase * PVE_OBS_W) + q;
-                    const pve_v4 *new4 = (const pve_v4 *)row0 + q;
-                    const int n_rows = A * 7;
-                    int gr = tid >> 3;
-                    int g = gr / 7, rw = gr - g * 7;
-                    for (; gr < n_rows; gr += 4 * RPI) {
-                        pve_v4 val[4];
+        }
+        /* 7 x 28 observation: row 0 was written by the agent itself (phase G1); row q+1 is neighbour
+         * q's stored row (Q3): this tick's row 0 of an agent processed earlier (read back from the
+         * output block through L2) or last tick's row from the state buffer; the empty slot VC-1
+         * supplies zeros.  Eight lanes per 112-byte row (7 active, one 16-byte piece each); a thread
+         * keeps its piece and walks the rows, so there is no index division and no divergence; the
+         * loads of four rows are issued before their stores. */
+        if (oblk) {
+            constexpr int RPI = NT / 8;                 /* rows per pass of the CTA */
+            const int q = tid & 7;
+            if (q < 7) {
+                pve_v4 *PVE_RESTRICT obsq = oblk + q;
+                const pve_v4 *PVE_RESTRICT prevq = (const pve_v4 *)(S.row0[phase] + vbase * PVE_OBS_W) + q;
+                const int n_rows = A * 6;
+                int gr = tid >> 3;
+                int g = gr / 6, rw = gr - g * 6;
+                for (; gr < n_rows; gr += 4 * RPI) {
+                    pve_v4 val[4];
+                    int doff[4];
 #pragma unroll
-                        for (int u = 0; u < 4; ++u) {
-                            const pve_v4 *src = zero16;
-                            if (gr + u * RPI < n_rows) {
-                                const int code = srcc[g * 8 + rw];
-                                const int kind = code >> 14, idx = code & 0x3FFF;
-                                src = (kind == SRC_PREV) ? prev4 + idx * 7 : ((kind == SRC_NEW) ? new4 + idx * 7 : zero16);
-                            }
-                            val[u] = *src;
-                            rw += RPI % 7; g += RPI / 7;
-                            if (rw >= 7) { rw -= 7; g += 1; }
+                    for (int u = 0; u < 4; ++u) {
+                        doff[u] = -1;
+                        if (gr + u * RPI < n_rows) {
+                            const uint32_t code = srcc[g * 8 + rw + 1];
+                            const int idx = (int)(code & 0x7FFFu);
+                            const pve_v4 *src = (code & PVE_SRC_PREV) ? prevq + idx * 7 : obsq + idx * 49;
+                            val[u] = pve_ld_l2(src);
+                            doff[u] = g * 49 + (rw + 1) * 7;
                         }
-#pragma unroll
-                        for (int u = 0; u < 4; ++u)
-                            if (gr + u * RPI < n_rows) dst[(gr + u * RPI) * 7] = val[u];
+                        rw += RPI % 6; g += RPI / 6;
+                        if (rw >= 6) { rw -= 6; g += 1; }
                     }
+#pragma unroll
+                    for (int u = 0; u < 4; ++u)
+                        if (doff[u] >= 0) obsq[doff[u]] = val[u];
                 }
             }
         }

@@ -205,8 +205,8 @@ class BatchedScene:
 
     def set_state(self, st):
         n_ctrl = ((st["flags"] & N.F_CONTROL) != 0).sum(axis=1)
-        if int(st["lane_n"].sum(axis=1).max()) > self.veh_cap or int(n_ctrl.max()) > self.agent_cap:
-            raise ValueError("state does not fit veh_cap=%d / agent_cap=%d" % (self.veh_cap, self.agent_cap))
+        if int(st["lane_n"].sum(axis=1).max()) > self.veh_cap - 1 or int(n_ctrl.max()) > self.agent_cap:
+            raise ValueError("state does not fit veh_cap-1=%d vehicles / agent_cap=%d agents" % (self.veh_cap - 1, self.agent_cap))
         packed = N.pack_state(st, self.B, self.veh_cap)
         self._check(self.lib.pve_set_state(self._h, C.byref(self._view(packed)), self._stream()))
         if self.device.type == "cuda":
