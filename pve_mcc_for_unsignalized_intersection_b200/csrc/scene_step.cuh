@@ -162,6 +162,15 @@ PVE_DEV uint32_t pve_fbits(float f) { uint32_t u; memcpy(&u, &f, sizeof u); retu
 PVE_DEV pve_v4 pve_pack4(float a, float b, float c, float d) {
     pve_v4 r; r.x = pve_fbits(a); r.y = pve_fbits(b); r.z = pve_fbits(c); r.w = pve_fbits(d); return r;
 }
+/* 1 if x < 0 else 0 (x is a difference of two finite doubles: a - b < 0 <=> a < b, and a - b is
+ * +0 exactly when a == b) */
+PVE_DEV uint32_t pve_isneg(double x) {
+#ifdef __CUDACC__
+    return (uint32_t)__double2hiint(x) >> 31;
+#else
+    uint64_t u; memcpy(&u, &x, sizeof u); return (uint32_t)(u >> 63);
+#endif
+}
 /* read back data this CTA wrote to global memory earlier in the kernel: L2, not L1 */
 #ifdef __CUDACC__
 PVE_DEV pve_v4 pve_ld_l2(const pve_v4 *p) {
@@ -502,15 +511,16 @@ PVE_DEV void pve_step_block(const PveParams &P, const PveState &S, const pve_out
                 const int base = vl_base[d], n = vl_cnt[d];
                 const double pos = epos[e];
                 const int idx = eidx[e];
-                int less = 0, leq = 0, t = 0;
-                for (; t + 2 <= n; t += 2) {
-                    const double p0 = epos[base + t], p1 = epos[base + t + 1];
-                    less += (p0 < pos) ? 1 : 0; leq += (p0 <= pos) ? 1 : 0;
-                    less += (p1 < pos) ? 1 : 0; leq += (p1 <= pos) ? 1 : 0;
+                uint32_t less = 0, greater = 0;
+                int t = 0;
+#pragma unroll 4
+                for (t = 0; t < n; ++t) {
+                    const double pt = epos[base + t];
+                    less += pve_isneg(pt - pos);
+                    greater += pve_isneg(pos - pt);
                 }
-                if (t < n) { const double p0 = epos[base + t]; less += (p0 < pos) ? 1 : 0; leq += (p0 <= pos) ? 1 : 0; }
-                int rank = less;
-                if (leq - less > 1)                 /* equal positions keep insertion (slot) order */
+                int rank = (int)less;
+                if (n - (int)less - (int)greater > 1)   /* equal positions keep insertion (slot) order */
                     for (t = 0; t < n; ++t)
                         rank += (epos[base + t] == pos && (int)eidx[base + t] < idx) ? 1 : 0;
                 spos[base + rank] = pos; sidx[base + rank] = (uint16_t)idx;
@@ -566,10 +576,13 @@ PVE_DEV void pve_step_block(const PveParams &P, const PveState &S, const pve_out
 
     /* ---- G2: two work items per agent: reward (TIS:293-320), world position (TIS:1250-1290) */
     PVE_FOR_TID(tid)
-        for (int it = tid; it < 2 * A; it += NT) {
-            const int g = it >> 1;
+        const int A32 = (A + 31) & ~31;         /* the two item kinds start on warp boundaries */
+        for (int it = tid; it < A32 + A; it += NT) {
+            const bool is_xy = it >= A32;
+            const int g = is_xy ? it - A32 : it;
+            if (g >= A) continue;
             const int k = vidx[g];
-            if (it & 1) {
+            if (is_xy) {
                 double x, y;
                 pve_world_xy(P, sp[k], lane_of[k], &x, &y);
                 xy[2 * g] = x; xy[2 * g + 1] = y;
@@ -749,7 +762,7 @@ PVE_DEV void pve_step_block(const PveParams &P, const PveState &S, const pve_out
     PVE_END_TID
 
     /* ---- K: write the state back, compacted ------------------------------------------------ */
-    float *const row0_next = S.row0[phase ^ 1] + vbase * PVE_OBS_W;
+    float *const row0_next = (phase ? S.row0[0] : S.row0[1]) + vbase * PVE_OBS_W;
     PVE_FOR_TID(tid)
         if (tid == 0) hdr->tick += 1;
         if (tid >= 32 && tid < 32 + PVE_NLANE) {
@@ -787,12 +800,16 @@ PVE_DEV void pve_step_block(const PveParams &P, const PveState &S, const pve_out
         }
         /* stored row 0 of every surviving agent -> next tick's neighbour rows / actor input */
         if (oblk)
-            for (int it = tid; it < A * 8; it += NT) {
-                const int g = it >> 3, q = it & 7;
+            for (int it = tid; it < A * 4; it += NT) {      /* 4 lanes per row: pieces {0,1} {2,3} {4,5} {6} */
+                const int g = it >> 2, pc = (it & 3) * 2;
                 const int k = vidx[g];
-                if (q < 7 && !del[k]) {
+                if (!del[k]) {
                     const int np = (int)surv[k] + misc[M_SPREF0 + lane_of[k]];
-                    ((pve_v4 *)(row0_next + (size_t)np * PVE_OBS_W))[q] = pve_ld_l2(oblk + g * 49 + q);
+                    const pve_v4 *src = oblk + g * 49 + pc;
+                    pve_v4 *dst = (pve_v4 *)(row0_next + (size_t)np * PVE_OBS_W) + pc;
+                    const pve_v4 v0 = pve_ld_l2(src);
+                    if (pc < 6) { const pve_v4 v1 = pve_ld_l2(src + 1); dst[1] = v1; }
+                    dst[0] = v0;
                 }
             }
     PVE_END_TID
@@ -837,38 +854,41 @@ PVE_DEV void pve_step_block(const PveParams &P, const PveState &S, const pve_out
         /* 7 x 28 observation: row 0 was written by the agent itself (phase G1); row q+1 is neighbour
          * q's stored row (Q3): this tick's row 0 of an agent processed earlier (read back from the
          * output block through L2) or last tick's row from the state buffer; the empty slot VC-1
-         * supplies zeros.  Eight lanes per 112-byte row (7 active, one 16-byte piece each); a thread
-         * keeps its piece and walks the rows, so there is no index division and no divergence; the
-         * loads of four rows are issued before their stores. */
+         * supplies zeros.  Four lanes per 112-byte row (two 16-byte pieces each, one for the last lane); a
+         * thread keeps its pieces and walks the rows, so there is no index division and no divergence;
+         * the loads of two rows are issued before their stores. */
         if (oblk) {
-            constexpr int RPI = NT / 8;                 /* rows per pass of the CTA */
-            const int q = tid & 7;
-            if (q < 7) {
-                pve_v4 *PVE_RESTRICT obsq = oblk + q;
-                const pve_v4 *PVE_RESTRICT prevq = (const pve_v4 *)(S.row0[phase] + vbase * PVE_OBS_W) + q;
-                const int n_rows = A * 6;
-                int gr = tid >> 3;
-                int g = gr / 6, rw = gr - g * 6;
-                for (; gr < n_rows; gr += 4 * RPI) {
-                    pve_v4 val[4];
-                    int doff[4];
+            constexpr int RPI = NT / 4;                 /* rows per pass of the CTA */
+            const int pc = (tid & 3) * 2;               /* pieces {0,1} {2,3} {4,5} {6} of the 112-byte row */
+            const bool two = pc < 6;
+            pve_v4 *PVE_RESTRICT obsq = oblk + pc;
+            const pve_v4 *PVE_RESTRICT prevq = (const pve_v4 *)((phase ? S.row0[1] : S.row0[0]) + vbase * PVE_OBS_W) + pc;
+            const int n_rows = A * 6;
+            int gr = tid >> 2;
+            int g = gr / 6, rw = gr - g * 6;
+            for (; gr < n_rows; gr += 2 * RPI) {
+                pve_v4 va[2], vb[2];
+                int doff[2];
 #pragma unroll
-                    for (int u = 0; u < 4; ++u) {
-                        doff[u] = -1;
-                        if (gr + u * RPI < n_rows) {
-                            const uint32_t code = srcc[g * 8 + rw + 1];
-                            const int idx = (int)(code & 0x7FFFu);
-                            const pve_v4 *src = (code & PVE_SRC_PREV) ? prevq + idx * 7 : obsq + idx * 49;
-                            val[u] = pve_ld_l2(src);
-                            doff[u] = g * 49 + (rw + 1) * 7;
-                        }
-                        rw += RPI % 6; g += RPI / 6;
-                        if (rw >= 6) { rw -= 6; g += 1; }
+                for (int u = 0; u < 2; ++u) {
+                    doff[u] = -1;
+                    if (gr + u * RPI < n_rows) {
+                        const uint32_t code = srcc[g * 8 + rw + 1];
+                        const int idx = (int)(code & 0x7FFFu);
+                        const pve_v4 *src = (code & PVE_SRC_PREV) ? prevq + idx * 7 : obsq + idx * 49;
+                        va[u] = pve_ld_l2(src);
+                        if (two) vb[u] = pve_ld_l2(src + 1);
+                        doff[u] = g * 49 + (rw + 1) * 7;
                     }
-#pragma unroll
-                    for (int u = 0; u < 4; ++u)
-                        if (doff[u] >= 0) obsq[doff[u]] = val[u];
+                    rw += RPI % 6; g += RPI / 6;
+                    if (rw >= 6) { rw -= 6; g += 1; }
                 }
+#pragma unroll
+                for (int u = 0; u < 2; ++u)
+                    if (doff[u] >= 0) {
+                        obsq[doff[u]] = va[u];
+                        if (two) obsq[doff[u] + 1] = vb[u];
+                    }
             }
         }
     PVE_END_TID

@@ -25,7 +25,11 @@ for r in rows:
         ln = int(r[0])
     except ValueError:
         continue
-    f = lambda name: int(float(r[col[name]])) if r[col[name]] not in ("", "-") else 0
+    def f(name):
+        try:
+            return int(float(r[col[name]]))
+        except ValueError:
+            return 0
     data.append((cur_file, ln, f("Instructions Executed"), f("# Samples"), f("Thread Instructions Executed"),
                  f("stall_barrier"), f("stall_long_sb"), f("stall_short_sb"), f("stall_wait"), r[1]))
 tot = sum(d[2] for d in data)

@@ -24,7 +24,9 @@ for r in rows:
     if col is None or "Instructions Executed" not in col or len(r)<len(hdr): continue
     try: ln=int(r[0])
     except ValueError: continue
-    f=lambda n:int(float(r[col[n]])) if r[col[n]] not in ("","-") else 0
+    def f(n):
+        try: return int(float(r[col[n]]))
+        except ValueError: return 0
     key = phase_of(ln) if cur=="scene_step.cuh" else "other: "+cur
     if key not in agg: agg[key]=[0,0,0,0,0,0,0]; order.append(key)
     a=agg[key]; a[0]+=f("Instructions Executed"); a[1]+=f("# Samples"); a[2]+=f("Thread Instructions Executed")
