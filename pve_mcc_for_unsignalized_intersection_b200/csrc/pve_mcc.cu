@@ -50,6 +50,7 @@ struct pve_scene {
     int32_t *pinned_i32;         /* host-visible scratch: [0] next agent total */
     int64_t next_total;          /* rows of the next tick if known, else -1 */
     int profiling;               /* record events around the step and scan kernels */
+    size_t smem_pad;             /* experiment knob (env PVE_SMEM_PAD): extra dynamic shared memory per CTA */
 #ifndef PVE_HOST_EMULATION
     cudaEvent_t ev[3];
 #endif
@@ -289,11 +290,11 @@ static cudaError_t launch_one(pve_scene *s, const float *actions, const pve_outp
     int dev = s->device & 15;
     if (!attr_set[dev]) {
         cudaError_t e = cudaFuncSetAttribute(pve_step_kernel<NT, VC, AC>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             (int)PveLayout<VC, AC>::BYTES);
+                                             (int)(PveLayout<VC, AC>::BYTES + s->smem_pad));
         if (e != cudaSuccess) return e;
         attr_set[dev] = true;
     }
-    pve_step_kernel<NT, VC, AC><<<s->cfg.n_envs, NT, PveLayout<VC, AC>::BYTES, stream>>>(
+    pve_step_kernel<NT, VC, AC><<<s->cfg.n_envs, NT, PveLayout<VC, AC>::BYTES + s->smem_pad, stream>>>(
         s->prm, s->st, O, s->spawn_tick, actions, s->phase);
     return cudaGetLastError();
 }
@@ -423,6 +424,7 @@ int32_t pve_create(const pve_config *cfg, int32_t device, pve_scene **out) {
     s->cfg.veh_cap = VC;          /* rounded up to the capacity class; see pve_veh_cap() */
     s->cfg.agent_cap = AC;
     s->threads = cfg->threads == 0 ? 128 : cfg->threads;
+    if (const char *pad = getenv("PVE_SMEM_PAD")) s->smem_pad = (size_t)atoi(pad);
     if (s->threads != 64 && s->threads != 128 && s->threads != 256) {
         snprintf(s->err, sizeof s->err, "threads must be 0, 64, 128 or 256");
         return PVE_EINVAL;

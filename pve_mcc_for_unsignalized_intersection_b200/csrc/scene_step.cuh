@@ -84,10 +84,12 @@ enum { PVE_STAT_AGENT = 0, PVE_STAT_VEH, PVE_STAT_COLL, PVE_STAT_LOCK, PVE_STAT_
 /* ---------------------------------------------------------------------------------------------
  * shared-memory layout: compile-time offsets for a capacity class (VC vehicle slots, AC agents,
  * EC = 5*AC virtual-lane entries).  Regions R1 and R2 are reused along the tick:
- *   R1: step candidates (phases A-C) -> unsorted virtual-lane entries (E-F)
- *   R2: sorted virtual lanes (F-G1) -> world coordinates of the agents (G2-G3)
- * The 28-float observation rows are never staged in shared memory: each agent writes its row 0
- * straight into its output block and later phases read it back through L2.
+ *   R1: step candidates (phases A-C) -> unsorted virtual-lane entries (E-F) -> row 0 of every agent (G1-M)
+ *   R2: sorted virtual lanes (F-G1) -> world coordinates of the agents (G2-G3) -> list of rows to
+ *       fetch from last tick's buffer (M)
+ * Rows that already sit in shared memory (an agent's own row, rows of neighbours processed earlier
+ * this tick, the zero row) leave the SM as 112-byte bulk asynchronous copies (cp.async.bulk, the TMA
+ * engine): one instruction per row instead of seven load/store pairs.
  * ------------------------------------------------------------------------------------------- */
 template <int VC, int AC>
 struct PveLayout {
@@ -104,10 +106,12 @@ struct PveLayout {
     static constexpr uint32_t CTA0 = R1, CP0 = CTA0 + 8 * VC, CV0 = CP0 + 8 * VC,
                               CP1 = CV0 + 8 * VC, CV1 = CP1 + 8 * VC;
     static constexpr uint32_t EPOS = R1, EIDX = EPOS + 8 * EC;
-    static constexpr uint32_t R1_BYTES = mx(40 * VC, a16(10 * EC));
+    static constexpr uint32_t ROW0 = R1;                          /* f32[AC + 1][28]; row AC is all zero */
+    static constexpr uint32_t R1_BYTES = mx(mx(40 * VC, a16(10 * EC)), 112 * (AC + 1));
     static constexpr uint32_t R2 = a16(R1 + R1_BYTES);
     static constexpr uint32_t SPOS = R2, SIDX = SPOS + 8 * EC;
     static constexpr uint32_t XY = R2;
+    static constexpr uint32_t PLIST = R2;                         /* u16[6 * AC] */
     static constexpr uint32_t R2_BYTES = mx(a16(10 * EC), 16 * AC);
     static constexpr uint32_t VIRDIS = a16(R2 + R2_BYTES);
     static constexpr uint32_t VD0 = VIRDIS + 8 * AC;
@@ -121,8 +125,8 @@ struct PveLayout {
     static constexpr uint32_t LANE_OFF = CPV + 4 * AC;           /* int[16] */
     static constexpr uint32_t VL_BASE = LANE_OFF + 64;           /* int[16] */
     static constexpr uint32_t VL_CNT = VL_BASE + 64;             /* int[16] */
-    static constexpr uint32_t MISC = VL_CNT + 64;                /* int[48] */
-    static constexpr uint32_t WSUM = MISC + 192;                 /* int[40] */
+    static constexpr uint32_t MISC = VL_CNT + 64;                /* int[56] */
+    static constexpr uint32_t WSUM = MISC + 224;                 /* int[40] */
     static constexpr uint32_t ACNT = WSUM + 160;                 /* u16[VC+2] */
     static constexpr uint32_t SURV = ACNT + a16(2 * (VC + 2));
     static constexpr uint32_t VIDX = SURV + a16(2 * (VC + 2));
@@ -149,14 +153,44 @@ struct PveLayout {
 
 enum { M_V = 0, M_NREM, M_PASSED, M_COLL, M_LOCK, M_NCTRL, M_Q5U, M_PSTEP, M_COLLAG, M_OUTOK, M_IDSEQ0,
        M_SPAWN0 /* 12 */, M_SPREF0 = M_SPAWN0 + 12 /* 13 */, M_NEWN0 = M_SPREF0 + 13 /* 12 */,
-       M_COUNT = M_NEWN0 + 12 };
-static_assert(M_COUNT <= 48, "misc block");
+       M_NPREV = M_NEWN0 + 12, M_COUNT };
+static_assert(M_COUNT <= 56, "misc block");
 
-/* gather codes for observation rows 1..6 (phase M): bit 15 clear -> this tick's row 0 of agent
- * `index` (in the output block), bit 15 set -> last tick's stored row of vehicle slot `index`.  The
- * last slot of every intersection (VC - 1) is never occupied and its stored row stays zero: it is
- * the source of absent neighbours' rows (TIS:1335). */
+/* gather codes for observation rows 1..6 (phase M): bit 15 clear -> row `index` of the shared-memory
+ * row table (this tick's row 0 of agent `index`; index AC is the zero row of an absent neighbour,
+ * TIS:1335), bit 15 set -> last tick's stored row of vehicle slot `index`. */
 #define PVE_SRC_PREV 0x8000u
+#define PVE_ROW_BYTES (PVE_OBS_W * 4)
+
+/* 112-byte row, shared memory -> global memory, through the TMA engine (SASS: UBLKCP).  The caller
+ * must have ordered the shared-memory writes before the asynchronous proxy (pve_fence_async_smem +
+ * barrier) and must call pve_bulk_drain() before the CTA exits. */
+PVE_DEV void pve_bulk_row_store(void *dst_global, const void *src_smem) {
+#ifdef __CUDACC__
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                 :: "l"(dst_global), "r"((uint32_t)__cvta_generic_to_shared(src_smem)), "n"(PVE_ROW_BYTES) : "memory");
+#else
+    memcpy(dst_global, src_smem, PVE_ROW_BYTES);
+#endif
+}
+PVE_DEV void pve_fence_async_smem() {
+#ifdef __CUDACC__
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+#endif
+}
+PVE_DEV void pve_bulk_drain() {
+#ifdef __CUDACC__
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+#endif
+}
+PVE_DEV void pve_prefetch_l2(const void *p) {
+#ifdef __CUDACC__
+    asm volatile("prefetch.global.L2 [%0];" :: "l"(p));
+#else
+    (void)p;
+#endif
+}
 
 PVE_DEV uint32_t pve_fbits(float f) { uint32_t u; memcpy(&u, &f, sizeof u); return u; }
 PVE_DEV pve_v4 pve_pack4(float a, float b, float c, float d) {
@@ -294,6 +328,8 @@ PVE_DEV void pve_step_block(const PveParams &P, const PveState &S, const pve_out
     double *const cp1 = (double *)(smem + L::CP1), *const cv1 = (double *)(smem + L::CV1);
     double *const epos = (double *)(smem + L::EPOS), *const spos = (double *)(smem + L::SPOS);
     uint16_t *const eidx = (uint16_t *)(smem + L::EIDX), *const sidx = (uint16_t *)(smem + L::SIDX);
+    float *const row0 = (float *)(smem + L::ROW0);
+    uint16_t *const plist = (uint16_t *)(smem + L::PLIST);
     double *const xy = (double *)(smem + L::XY);
     double *const virdis = (double *)(smem + L::VIRDIS), *const vd0s = (double *)(smem + L::VD0);
     double *const dsum = (double *)(smem + L::DSUM);
@@ -346,6 +382,9 @@ PVE_DEV void pve_step_block(const PveParams &P, const PveState &S, const pve_out
     pve_v4 *const oblk = (O.obs != nullptr && misc[M_OUTOK]) ? (pve_v4 *)O.obs + obase * (PVE_OBS_H * PVE_OBS_W / 4)
                                                              : nullptr;
 
+    const float *const row0_prev_base = (phase ? S.row0[1] : S.row0[0]) + vbase * PVE_OBS_W;
+    float *const row0_next = (phase ? S.row0[0] : S.row0[1]) + vbase * PVE_OBS_W;
+
     /* ---- A: load vehicles, both candidate next states (Q1) --------------------------------- */
     PVE_FOR_TID(tid)
         for (int k = tid; k < V; k += NT) {
@@ -376,6 +415,10 @@ PVE_DEV void pve_step_block(const PveParams &P, const PveState &S, const pve_out
             cv0[k] = v0n; cv1[k] = v1n;
             sp[k] = p; sv[k] = v; sa[k] = a; sjs[k] = js;
             suid[k] = mt.uid; spk[k] = mt.packed;
+            if (ctrl) {      /* its stored row will probably be gathered in phase M: start the HBM fetch now */
+                const float *r = row0_prev_base + (size_t)k * PVE_OBS_W;
+                pve_prefetch_l2(r); pve_prefetch_l2(r + PVE_OBS_W - 1);
+            }
             lane_of[k] = (uint8_t)i;
             ctl0[k] = ctrl ? 1 : 0;
             del[k] = forced ? 1 : 0;        /* borrowed until phase C */
@@ -543,8 +586,8 @@ PVE_DEV void pve_step_block(const PveParams &P, const PveState &S, const pve_out
             /* six nearest by |delta|, ties to the lower list index (stable sort, TIS:1389) */
             int lo = r - 1, hi = r + 1, run_cur = 0, run_end = -1;
             double run_d = 0;
-            pve_v4 *const orow = oblk ? oblk + g * (PVE_OBS_H * PVE_OBS_W / 4) : nullptr;   /* obs[g][0][:] */
-            if (orow) orow[0] = pve_pack4((float)pe, (float)sv[k], (float)sa[k], (float)d);   /* TIS:1336 */
+            pve_v4 *const orow = (pve_v4 *)(row0 + (size_t)g * PVE_OBS_W);
+            orow[0] = pve_pack4((float)pe, (float)sv[k], (float)sa[k], (float)d);        /* TIS:1336 */
             nn0[g] = 0xFFFFu;
             vd0s[g] = 0.0;
             for (int q = 0; q < PVE_NNBR; ++q) {
@@ -561,17 +604,18 @@ PVE_DEV void pve_step_block(const PveParams &P, const PveState &S, const pve_out
                 if (pick >= 0) {
                     const int kn = sidx[base + pick];
                     const double vd = spos[base + pick];
-                    if (orow) orow[q + 1] = pve_pack4((float)vd, (float)sv[kn], (float)sa[kn],
-                                                      (float)lane_of[kn]);       /* TIS:1330 */
+                    orow[q + 1] = pve_pack4((float)vd, (float)sv[kn], (float)sa[kn], (float)lane_of[kn]);   /* TIS:1330 */
                     /* Q3: neighbour already processed this tick -> its new row, else last tick's */
                     srcc[g * 8 + q + 1] = (kn < k) ? (uint16_t)acnt[kn] : (uint16_t)(PVE_SRC_PREV | kn);
                     if (q == 0) { nn0[g] = (uint16_t)kn; vd0s[g] = vd; }
                 } else {
-                    if (orow) orow[q + 1] = pve_pack4(0.f, 0.f, 0.f, 0.f);       /* TIS:1334 */
-                    srcc[g * 8 + q + 1] = (uint16_t)(PVE_SRC_PREV | (VC - 1));   /* the always-zero row */
+                    orow[q + 1] = pve_pack4(0.f, 0.f, 0.f, 0.f);                 /* TIS:1334 */
+                    srcc[g * 8 + q + 1] = (uint16_t)AC;                          /* the zero row */
                 }
             }
         }
+        if (tid < PVE_OBS_W / 4) ((pve_v4 *)(row0 + (size_t)AC * PVE_OBS_W))[tid] = pve_pack4(0.f, 0.f, 0.f, 0.f);
+        pve_fence_async_smem();     /* rows are read by the TMA engine from phase K on */
     PVE_END_TID
 
     /* ---- G2: two work items per agent: reward (TIS:293-320), world position (TIS:1250-1290) */
@@ -732,7 +776,7 @@ PVE_DEV void pve_step_block(const PveParams &P, const PveState &S, const pve_out
             }
             /* arrivals are granted in lane order while there is room (capacity is a sticky error) */
             const int total = surv[V], nctrl = misc[M_NCTRL];
-            int room = (VC - 1) - total;         /* slot VC-1 stays empty: its stored row is the zero row */
+            int room = VC - total;
             room = (AC - nctrl) < room ? (AC - nctrl) : room;
             int before = 0, want = 0, surv_i = 0;
             for (int q = 0; q <= i; ++q) {
@@ -762,7 +806,6 @@ PVE_DEV void pve_step_block(const PveParams &P, const PveState &S, const pve_out
     PVE_END_TID
 
     /* ---- K: write the state back, compacted ------------------------------------------------ */
-    float *const row0_next = (phase ? S.row0[0] : S.row0[1]) + vbase * PVE_OBS_W;
     PVE_FOR_TID(tid)
         if (tid == 0) hdr->tick += 1;
         if (tid >= 32 && tid < 32 + PVE_NLANE) {
@@ -799,19 +842,13 @@ PVE_DEV void pve_step_block(const PveParams &P, const PveState &S, const pve_out
             for (int q = 0; q < PVE_OBS_W / 4; ++q) ((pve_v4 *)(row0_next + (size_t)np * PVE_OBS_W))[q] = z;
         }
         /* stored row 0 of every surviving agent -> next tick's neighbour rows / actor input */
-        if (oblk)
-            for (int it = tid; it < A * 4; it += NT) {      /* 4 lanes per row: pieces {0,1} {2,3} {4,5} {6} */
-                const int g = it >> 2, pc = (it & 3) * 2;
-                const int k = vidx[g];
-                if (!del[k]) {
-                    const int np = (int)surv[k] + misc[M_SPREF0 + lane_of[k]];
-                    const pve_v4 *src = oblk + g * 49 + pc;
-                    pve_v4 *dst = (pve_v4 *)(row0_next + (size_t)np * PVE_OBS_W) + pc;
-                    const pve_v4 v0 = pve_ld_l2(src);
-                    if (pc < 6) { const pve_v4 v1 = pve_ld_l2(src + 1); dst[1] = v1; }
-                    dst[0] = v0;
-                }
+        for (int g = tid; g < A; g += NT) {
+            const int k = vidx[g];
+            if (!del[k]) {
+                const int np = (int)surv[k] + misc[M_SPREF0 + lane_of[k]];
+                pve_bulk_row_store(row0_next + (size_t)np * PVE_OBS_W, row0 + (size_t)g * PVE_OBS_W);
             }
+        }
     PVE_END_TID
 
     /* ---- M: outputs ------------------------------------------------------------------------ */
@@ -851,45 +888,47 @@ PVE_DEV void pve_step_block(const PveParams &P, const PveState &S, const pve_out
                 if (O.jerk_sum) O.jerk_sum[obase + g] = (float)sjs[k];
             }
         }
-        /* 7 x 28 observation: row 0 was written by the agent itself (phase G1); row q+1 is neighbour
-         * q's stored row (Q3): this tick's row 0 of an agent processed earlier (read back from the
-         * output block through L2) or last tick's row from the state buffer; the empty slot VC-1
-         * supplies zeros.  Four lanes per 112-byte row (two 16-byte pieces each, one for the last lane); a
-         * thread keeps its pieces and walks the rows, so there is no index division and no divergence;
-         * the loads of two rows are issued before their stores. */
+        /* 7 x 28 observation: row 0 = the agent's own row, row q+1 = neighbour q's stored row (Q3).  Rows
+         * that are in shared memory go out as one bulk copy each; rows of last tick's buffer are listed
+         * for the cooperative gather below. */
         if (oblk) {
-            constexpr int RPI = NT / 4;                 /* rows per pass of the CTA */
-            const int pc = (tid & 3) * 2;               /* pieces {0,1} {2,3} {4,5} {6} of the 112-byte row */
-            const bool two = pc < 6;
-            pve_v4 *PVE_RESTRICT obsq = oblk + pc;
-            const pve_v4 *PVE_RESTRICT prevq = (const pve_v4 *)((phase ? S.row0[1] : S.row0[0]) + vbase * PVE_OBS_W) + pc;
-            const int n_rows = A * 6;
-            int gr = tid >> 2;
-            int g = gr / 6, rw = gr - g * 6;
-            for (; gr < n_rows; gr += 2 * RPI) {
-                pve_v4 va[2], vb[2];
-                int doff[2];
-#pragma unroll
-                for (int u = 0; u < 2; ++u) {
-                    doff[u] = -1;
-                    if (gr + u * RPI < n_rows) {
-                        const uint32_t code = srcc[g * 8 + rw + 1];
-                        const int idx = (int)(code & 0x7FFFu);
-                        const pve_v4 *src = (code & PVE_SRC_PREV) ? prevq + idx * 7 : obsq + idx * 49;
-                        va[u] = pve_ld_l2(src);
-                        if (two) vb[u] = pve_ld_l2(src + 1);
-                        doff[u] = g * 49 + (rw + 1) * 7;
-                    }
-                    rw += RPI % 6; g += RPI / 6;
-                    if (rw >= 6) { rw -= 6; g += 1; }
-                }
-#pragma unroll
-                for (int u = 0; u < 2; ++u)
-                    if (doff[u] >= 0) {
-                        obsq[doff[u]] = va[u];
-                        if (two) obsq[doff[u] + 1] = vb[u];
-                    }
+            for (int it = tid; it < A * 7; it += NT) {
+                const int g = it / 7, rw = it - g * 7;
+                const uint32_t code = rw ? (uint32_t)srcc[g * 8 + rw] : (uint32_t)g;
+                if (code & PVE_SRC_PREV) plist[PVE_ATOMIC_ADD(&misc[M_NPREV], 1)] = (uint16_t)it;
+                else pve_bulk_row_store(oblk + it * 7, row0 + (size_t)code * PVE_OBS_W);
             }
         }
+    PVE_END_TID
+
+    /* ---- M2: rows of last tick's buffer: 8 lanes per 112-byte row (7 active), 4 rows in flight --- */
+    PVE_FOR_TID(tid)
+        if (oblk) {
+            constexpr int RPI = NT / 8;
+            const int q = tid & 7;
+            const int n_prev = misc[M_NPREV];
+            const pve_v4 *PVE_RESTRICT prevq = (const pve_v4 *)row0_prev_base + q;
+            pve_v4 *PVE_RESTRICT obsq = oblk + q;
+            if (q < 7)
+                for (int li = tid >> 3; li < n_prev; li += 4 * RPI) {
+                    pve_v4 val[4];
+                    int dsti[4];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        dsti[u] = -1;
+                        if (li + u * RPI < n_prev) {
+                            const int it = plist[li + u * RPI];
+                            const int g = it / 7, rw = it - g * 7;
+                            const int idx = (int)(srcc[g * 8 + rw] & 0x7FFFu);
+                            val[u] = prevq[idx * 7];
+                            dsti[u] = it * 7;
+                        }
+                    }
+#pragma unroll
+                    for (int u = 0; u < 4; ++u)
+                        if (dsti[u] >= 0) obsq[dsti[u]] = val[u];
+                }
+        }
+        pve_bulk_drain();           /* the TMA engine has finished reading this CTA's shared memory */
     PVE_END_TID
 }
