@@ -469,6 +469,9 @@ int32_t pve_create(const pve_config *cfg, int32_t device, pve_scene **out) {
     RT_CHECK(s, rt_alloc((void **)&s->st.stats, sizeof(double) * (size_t)B * PVE_NSTAT));
     RT_CHECK(s, rt_alloc((void **)&s->st.agent_offset, sizeof(int32_t) * ((size_t)B + 1)));
     RT_CHECK(s, rt_alloc((void **)&s->counters_dev, sizeof(double) * 16));
+#ifdef PVE_PHASE_TIMING
+    RT_CHECK(s, rt_alloc((void **)&s->st.dbg, sizeof(long long) * 48 * (size_t)B));
+#endif
     RT_CHECK(s, rt_host_alloc((void **)&s->pinned_i32, sizeof(int32_t) * 16));
     return pve_reset(s, nullptr, 0, 0, nullptr);
 }
@@ -642,6 +645,9 @@ const pve_veh_meta *pve_meta_dev(const pve_scene *s) { return s ? s->st.meta : n
 const pve_env_header *pve_hdr_dev(const pve_scene *s) { return s ? s->st.hdr : nullptr; }
 int64_t pve_smem_bytes(const pve_scene *s) { return s ? (int64_t)s->smem_bytes : 0; }
 int32_t pve_threads(const pve_scene *s) { return s ? s->threads : 0; }
+#ifdef PVE_PHASE_TIMING
+const void *pve_debug_stamps(const pve_scene *s) { return s ? s->st.dbg : nullptr; }
+#endif
 int32_t pve_veh_cap(const pve_scene *s) { return s ? s->cfg.veh_cap : 0; }
 int32_t pve_agent_cap(const pve_scene *s) { return s ? s->cfg.agent_cap : 0; }
 

@@ -39,7 +39,11 @@
 #define PVE_DEV __device__ __forceinline__
 #define PVE_HD __host__ __device__ __forceinline__
 #define PVE_FOR_TID(tid) { const int tid = (int)threadIdx.x;
+#ifdef PVE_PHASE_TIMING      /* tools/phase_timing.py only: cycle stamp of every phase boundary, CTA thread 0 */
+#define PVE_END_TID } __syncthreads(); if (threadIdx.x == 0 && pve_nstamp < 48) pve_stamp[pve_nstamp++] = clock64();
+#else
 #define PVE_END_TID } __syncthreads();
+#endif
 #define PVE_ATOMIC_ADD(ptr, val) atomicAdd((ptr), (val))
 #define PVE_RESTRICT __restrict__
 #else
@@ -76,6 +80,7 @@ struct PveState {
     int32_t *n_ctrl, *n_veh;  /* [B] copies of the header counts for the offset scan */
     double *stats;            /* [B][PVE_NSTAT] running per-intersection statistics */
     int32_t *agent_offset;    /* [B+1] rows of this tick (written by the scan kernel) */
+    void *dbg;                /* tools/phase_timing.py builds only: [B][48] cycle stamps */
 };
 
 enum { PVE_STAT_AGENT = 0, PVE_STAT_VEH, PVE_STAT_COLL, PVE_STAT_LOCK, PVE_STAT_JERK, PVE_STAT_RSUM,
@@ -85,11 +90,9 @@ enum { PVE_STAT_AGENT = 0, PVE_STAT_VEH, PVE_STAT_COLL, PVE_STAT_LOCK, PVE_STAT_
  * shared-memory layout: compile-time offsets for a capacity class (VC vehicle slots, AC agents,
  * EC = 5*AC virtual-lane entries).  Regions R1 and R2 are reused along the tick:
  *   R1: step candidates (phases A-C) -> unsorted virtual-lane entries (E-F) -> row 0 of every agent (G1-M)
- *   R2: sorted virtual lanes (F-G1) -> world coordinates of the agents (G2-G3) -> list of rows to
- *       fetch from last tick's buffer (M)
- * Rows that already sit in shared memory (an agent's own row, rows of neighbours processed earlier
- * this tick, the zero row) leave the SM as 112-byte bulk asynchronous copies (cp.async.bulk, the TMA
- * engine): one instruction per row instead of seven load/store pairs.
+ *   R2: sorted virtual lanes (F-G1) -> world coordinates of the agents (G2-G3)
+ * (per-row cp.async.bulk stores were measured and rejected: ~225 tiny TMA operations per
+ * intersection saturate the copy engine)
  * ------------------------------------------------------------------------------------------- */
 template <int VC, int AC>
 struct PveLayout {
@@ -111,7 +114,6 @@ struct PveLayout {
     static constexpr uint32_t R2 = a16(R1 + R1_BYTES);
     static constexpr uint32_t SPOS = R2, SIDX = SPOS + 8 * EC;
     static constexpr uint32_t XY = R2;
-    static constexpr uint32_t PLIST = R2;                         /* u16[6 * AC] */
     static constexpr uint32_t R2_BYTES = mx(a16(10 * EC), 16 * AC);
     static constexpr uint32_t VIRDIS = a16(R2 + R2_BYTES);
     static constexpr uint32_t VD0 = VIRDIS + 8 * AC;
@@ -153,7 +155,7 @@ struct PveLayout {
 
 enum { M_V = 0, M_NREM, M_PASSED, M_COLL, M_LOCK, M_NCTRL, M_Q5U, M_PSTEP, M_COLLAG, M_OUTOK, M_IDSEQ0,
        M_SPAWN0 /* 12 */, M_SPREF0 = M_SPAWN0 + 12 /* 13 */, M_NEWN0 = M_SPREF0 + 13 /* 12 */,
-       M_NPREV = M_NEWN0 + 12, M_COUNT };
+       M_COUNT = M_NEWN0 + 12 };
 static_assert(M_COUNT <= 56, "misc block");
 
 /* gather codes for observation rows 1..6 (phase M): bit 15 clear -> row `index` of the shared-memory
@@ -162,28 +164,6 @@ static_assert(M_COUNT <= 56, "misc block");
 #define PVE_SRC_PREV 0x8000u
 #define PVE_ROW_BYTES (PVE_OBS_W * 4)
 
-/* 112-byte row, shared memory -> global memory, through the TMA engine (SASS: UBLKCP).  The caller
- * must have ordered the shared-memory writes before the asynchronous proxy (pve_fence_async_smem +
- * barrier) and must call pve_bulk_drain() before the CTA exits. */
-PVE_DEV void pve_bulk_row_store(void *dst_global, const void *src_smem) {
-#ifdef __CUDACC__
-    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
-                 :: "l"(dst_global), "r"((uint32_t)__cvta_generic_to_shared(src_smem)), "n"(PVE_ROW_BYTES) : "memory");
-#else
-    memcpy(dst_global, src_smem, PVE_ROW_BYTES);
-#endif
-}
-PVE_DEV void pve_fence_async_smem() {
-#ifdef __CUDACC__
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-#endif
-}
-PVE_DEV void pve_bulk_drain() {
-#ifdef __CUDACC__
-    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-#endif
-}
 PVE_DEV void pve_prefetch_l2(const void *p) {
 #ifdef __CUDACC__
     asm volatile("prefetch.global.L2 [%0];" :: "l"(p));
@@ -278,6 +258,87 @@ PVE_DEV void pve_warp0_sums(const float *x, const double *y, int n, double *out3
 }
 
 /* ---------------------------------------------------------------------------------------------
+ * Row mover: the 7 x 28 observation of every agent and the stored row 0 of every surviving agent.
+ * Item it < 7A  : observation row (it % 7) of agent (it / 7); row 0 is the agent's own row, row q+1
+ *                 is neighbour q's stored row (Q3): this tick's row if that neighbour was processed
+ *                 earlier (shared memory), else last tick's row (state buffer in HBM/L2), or zeros.
+ * Item 7A + g   : row 0 of agent g -> next tick's state buffer at the agent's compacted slot.
+ * Device: every lane decodes one item (source and destination address); the warp then moves four
+ * rows per step, 8 lanes per 112-byte row (7 active, 16 bytes each), with the addresses handed
+ * around by shuffles; the source is a generic pointer, so shared and global rows take the same
+ * path without divergence, and four loads are in flight per lane.
+ * ------------------------------------------------------------------------------------------- */
+struct PveRowJob {
+    int A;
+    const uint16_t *srcc, *vidx, *surv;
+    const uint8_t *del, *lane_of;
+    const int32_t *spref;
+    const float *rows_smem;       /* [AC + 1][28], row AC = zeros */
+    const float *rows_prev;       /* last tick's stored rows of this intersection */
+    float *rows_next;             /* next tick's stored rows of this intersection */
+    pve_v4 *oblk;                 /* this intersection's observation block or null */
+    int zero_row;
+};
+
+PVE_DEV void pve_row_decode(const PveRowJob &J, int it, const pve_v4 **src, pve_v4 **dst) {
+    *src = nullptr; *dst = nullptr;
+    const int n_obs = J.A * 7;
+    if (it < n_obs) {
+        if (J.oblk) {
+            const int g = it / 7, rw = it - g * 7;
+            const uint32_t code = rw ? (uint32_t)J.srcc[g * 8 + rw] : (uint32_t)g;
+            const int idx = (int)(code & 0x7FFFu);
+            *src = (const pve_v4 *)(((code & PVE_SRC_PREV) ? J.rows_prev : J.rows_smem) + (size_t)idx * PVE_OBS_W);
+            *dst = J.oblk + (size_t)it * 7;
+        }
+    } else if (it < n_obs + J.A) {
+        const int g = it - n_obs;
+        const int k = J.vidx[g];
+        if (!J.del[k]) {
+            const int np = (int)J.surv[k] + J.spref[J.lane_of[k]];
+            *src = (const pve_v4 *)(J.rows_smem + (size_t)g * PVE_OBS_W);
+            *dst = (pve_v4 *)(J.rows_next + (size_t)np * PVE_OBS_W);
+        }
+    }
+}
+
+template <int NT>
+PVE_DEV void pve_move_rows(const PveRowJob &J) {
+    const int n_items = J.A * 8;
+#ifdef __CUDACC__
+    const int tid = (int)threadIdx.x, lane = tid & 31, q = lane & 7, sub = lane >> 3;
+    for (int chunk = (tid >> 5) * 32; chunk < n_items; chunk += NT) {
+        const pve_v4 *src;
+        pve_v4 *dst;
+        pve_row_decode(J, chunk + lane, &src, &dst);
+        const unsigned long long s64 = (unsigned long long)src, d64 = (unsigned long long)dst;
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+            pve_v4 val[4];
+            pve_v4 *dd[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int from = (half * 4 + u) * 4 + sub;
+                const pve_v4 *ss = (const pve_v4 *)__shfl_sync(0xffffffffu, s64, from);
+                dd[u] = (pve_v4 *)__shfl_sync(0xffffffffu, d64, from);
+                if (q < 7 && dd[u] != nullptr) val[u] = ss[q];
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+                if (q < 7 && dd[u] != nullptr) dd[u][q] = val[u];
+        }
+    }
+#else
+    for (int it = 0; it < n_items; ++it) {
+        const pve_v4 *src;
+        pve_v4 *dst;
+        pve_row_decode(J, it, &src, &dst);
+        if (dst) memcpy(dst, src, PVE_OBS_W * sizeof(float));
+    }
+#endif
+}
+
+/* ---------------------------------------------------------------------------------------------
  * TIS:1250-1290 get_p for lane_num = 12 (yaw is never read by the caller)
  * ------------------------------------------------------------------------------------------- */
 PVE_DEV void pve_world_xy(const PveParams &P, double p, int lane, double *x, double *y) {
@@ -329,7 +390,6 @@ PVE_DEV void pve_step_block(const PveParams &P, const PveState &S, const pve_out
     double *const epos = (double *)(smem + L::EPOS), *const spos = (double *)(smem + L::SPOS);
     uint16_t *const eidx = (uint16_t *)(smem + L::EIDX), *const sidx = (uint16_t *)(smem + L::SIDX);
     float *const row0 = (float *)(smem + L::ROW0);
-    uint16_t *const plist = (uint16_t *)(smem + L::PLIST);
     double *const xy = (double *)(smem + L::XY);
     double *const virdis = (double *)(smem + L::VIRDIS), *const vd0s = (double *)(smem + L::VD0);
     double *const dsum = (double *)(smem + L::DSUM);
@@ -353,6 +413,11 @@ PVE_DEV void pve_step_block(const PveParams &P, const PveState &S, const pve_out
     uint8_t *const status = smem + L::STATUS, *const edir = smem + L::EDIR;
 
     const size_t vbase = (size_t)b * (size_t)VC;
+#if defined(PVE_PHASE_TIMING) && defined(__CUDACC__)
+    long long pve_stamp[48];
+    int pve_nstamp = 0;
+    if (threadIdx.x == 0) pve_stamp[pve_nstamp++] = clock64();
+#endif
 
     /* ---- L0: header -> shared -------------------------------------------------------------- */
     PVE_FOR_TID(tid)
@@ -583,39 +648,88 @@ PVE_DEV void pve_step_block(const PveParams &P, const PveState &S, const pve_out
             /* vir_header / vir_dis, TIS:1349-1354 */
             if (r == 0) { hdra[g] = -1; virdis[g] = 100.0; }
             else { hdra[g] = (int16_t)acnt[sidx[base + r - 1]]; virdis[g] = pe - spos[base + r - 1]; }
-            /* six nearest by |delta|, ties to the lower list index (stable sort, TIS:1389) */
-            int lo = r - 1, hi = r + 1, run_cur = 0, run_end = -1;
-            double run_d = 0;
+            /* Six nearest by |delta|, ties to the lower list index (stable sort, TIS:1389).  Only the six
+             * entries below and the six above the ego can qualify.  Instead of walking outwards (a
+             * serial chain of dependent loads) every candidate computes its position in the stable
+             * order by counting the candidates that precede it: below-side entries have lower list
+             * indices, so on equal |delta| they win against above-side ones, and among themselves the
+             * farther one (lower index) wins. */
             pve_v4 *const orow = (pve_v4 *)(row0 + (size_t)g * PVE_OBS_W);
             orow[0] = pve_pack4((float)pe, (float)sv[k], (float)sa[k], (float)d);        /* TIS:1336 */
             nn0[g] = 0xFFFFu;
             vd0s[g] = 0.0;
-            for (int q = 0; q < PVE_NNBR; ++q) {
-                if (run_cur > run_end && lo >= 0) {
-                    run_end = lo; run_d = fabs(spos[base + lo] - pe);
-                    int x = lo;
-                    while (x - 1 >= 0 && fabs(spos[base + x - 1] - pe) == run_d) --x;
-                    run_cur = x; lo = x - 1;
+            const double INF = 1.0e300;
+            double dl[PVE_NNBR], dh[PVE_NNBR];
+#pragma unroll
+            for (int i = 0; i < PVE_NNBR; ++i) {
+                const int xl = r - 1 - i, xh = r + 1 + i;
+                dl[i] = (xl >= 0) ? fabs(spos[base + (xl >= 0 ? xl : 0)] - pe) : INF;
+                dh[i] = (xh < n) ? fabs(spos[base + (xh < n ? xh : 0)] - pe) : INF;
+            }
+            int ncand = 0;
+            /* a run of equal |delta| that continues below the window puts farther (lower-index) entries
+             * first: resolve that rare case with the reference's own outward walk */
+            const bool edge_tie = (r - 1 - PVE_NNBR >= 0) && dl[PVE_NNBR - 1] != INF &&
+                                  fabs(spos[base + (r - 1 - PVE_NNBR >= 0 ? r - 1 - PVE_NNBR : 0)] - pe) == dl[PVE_NNBR - 1];
+            if (edge_tie) {
+                int lo = r - 1, hi = r + 1, run_cur = 0, run_end = -1;
+                double run_d = 0;
+                for (int q = 0; q < PVE_NNBR; ++q) {
+                    if (run_cur > run_end && lo >= 0) {
+                        run_end = lo; run_d = fabs(spos[base + lo] - pe);
+                        int x = lo;
+                        while (x - 1 >= 0 && fabs(spos[base + x - 1] - pe) == run_d) --x;
+                        run_cur = x; lo = x - 1;
+                    }
+                    const bool has_lo = run_cur <= run_end, has_hi = hi < n;
+                    int pick = -1;
+                    if (has_lo && (!has_hi || run_d <= fabs(spos[base + hi] - pe))) pick = run_cur++;
+                    else if (has_hi) pick = hi++;
+                    if (pick >= 0) {
+                        const int kn = sidx[base + pick];
+                        const double vd = spos[base + pick];
+                        orow[q + 1] = pve_pack4((float)vd, (float)sv[kn], (float)sa[kn], (float)lane_of[kn]);
+                        srcc[g * 8 + q + 1] = (kn < k) ? (uint16_t)acnt[kn] : (uint16_t)(PVE_SRC_PREV | kn);
+                        if (q == 0) { nn0[g] = (uint16_t)kn; vd0s[g] = vd; }
+                        ++ncand;
+                    }
                 }
-                const bool has_lo = run_cur <= run_end, has_hi = hi < n;
-                int pick = -1;
-                if (has_lo && (!has_hi || run_d <= fabs(spos[base + hi] - pe))) pick = run_cur++;
-                else if (has_hi) pick = hi++;
-                if (pick >= 0) {
-                    const int kn = sidx[base + pick];
-                    const double vd = spos[base + pick];
-                    orow[q + 1] = pve_pack4((float)vd, (float)sv[kn], (float)sa[kn], (float)lane_of[kn]);   /* TIS:1330 */
-                    /* Q3: neighbour already processed this tick -> its new row, else last tick's */
-                    srcc[g * 8 + q + 1] = (kn < k) ? (uint16_t)acnt[kn] : (uint16_t)(PVE_SRC_PREV | kn);
-                    if (q == 0) { nn0[g] = (uint16_t)kn; vd0s[g] = vd; }
-                } else {
+            } else
+#pragma unroll
+            for (int side = 0; side < 2; ++side) {
+#pragma unroll
+                for (int i = 0; i < PVE_NNBR; ++i) {
+                    const int x = side ? r + 1 + i : r - 1 - i;
+                    const bool ok = side ? (x < n) : (x >= 0);
+                    const double di = side ? dh[i] : dl[i];
+                    int rk = side ? i : 0;
+#pragma unroll
+                    for (int j = 0; j < PVE_NNBR; ++j) {
+                        if (side) rk += (dl[j] <= di) ? 1 : 0;
+                        else {
+                            if (j != i) rk += (dl[j] < di || (dl[j] == di && j > i)) ? 1 : 0;
+                            rk += (dh[j] < di) ? 1 : 0;
+                        }
+                    }
+                    ncand += ok ? 1 : 0;
+                    if (ok && rk < PVE_NNBR) {
+                        const int kn = sidx[base + x];
+                        const double vd = spos[base + x];
+                        orow[rk + 1] = pve_pack4((float)vd, (float)sv[kn], (float)sa[kn], (float)lane_of[kn]);   /* TIS:1330 */
+                        /* Q3: neighbour already processed this tick -> its new row, else last tick's */
+                        srcc[g * 8 + rk + 1] = (kn < k) ? (uint16_t)acnt[kn] : (uint16_t)(PVE_SRC_PREV | kn);
+                        if (rk == 0) { nn0[g] = (uint16_t)kn; vd0s[g] = vd; }
+                    }
+                }
+            }
+#pragma unroll
+            for (int q = 0; q < PVE_NNBR; ++q)
+                if (q >= ncand) {
                     orow[q + 1] = pve_pack4(0.f, 0.f, 0.f, 0.f);                 /* TIS:1334 */
                     srcc[g * 8 + q + 1] = (uint16_t)AC;                          /* the zero row */
                 }
-            }
         }
         if (tid < PVE_OBS_W / 4) ((pve_v4 *)(row0 + (size_t)AC * PVE_OBS_W))[tid] = pve_pack4(0.f, 0.f, 0.f, 0.f);
-        pve_fence_async_smem();     /* rows are read by the TMA engine from phase K on */
     PVE_END_TID
 
     /* ---- G2: two work items per agent: reward (TIS:293-320), world position (TIS:1250-1290) */
@@ -842,13 +956,6 @@ PVE_DEV void pve_step_block(const PveParams &P, const PveState &S, const pve_out
             for (int q = 0; q < PVE_OBS_W / 4; ++q) ((pve_v4 *)(row0_next + (size_t)np * PVE_OBS_W))[q] = z;
         }
         /* stored row 0 of every surviving agent -> next tick's neighbour rows / actor input */
-        for (int g = tid; g < A; g += NT) {
-            const int k = vidx[g];
-            if (!del[k]) {
-                const int np = (int)surv[k] + misc[M_SPREF0 + lane_of[k]];
-                pve_bulk_row_store(row0_next + (size_t)np * PVE_OBS_W, row0 + (size_t)g * PVE_OBS_W);
-            }
-        }
     PVE_END_TID
 
     /* ---- M: outputs ------------------------------------------------------------------------ */
@@ -888,47 +995,23 @@ PVE_DEV void pve_step_block(const PveParams &P, const PveState &S, const pve_out
                 if (O.jerk_sum) O.jerk_sum[obase + g] = (float)sjs[k];
             }
         }
-        /* 7 x 28 observation: row 0 = the agent's own row, row q+1 = neighbour q's stored row (Q3).  Rows
-         * that are in shared memory go out as one bulk copy each; rows of last tick's buffer are listed
-         * for the cooperative gather below. */
-        if (oblk) {
-            for (int it = tid; it < A * 7; it += NT) {
-                const int g = it / 7, rw = it - g * 7;
-                const uint32_t code = rw ? (uint32_t)srcc[g * 8 + rw] : (uint32_t)g;
-                if (code & PVE_SRC_PREV) plist[PVE_ATOMIC_ADD(&misc[M_NPREV], 1)] = (uint16_t)it;
-                else pve_bulk_row_store(oblk + it * 7, row0 + (size_t)code * PVE_OBS_W);
-            }
-        }
     PVE_END_TID
 
-    /* ---- M2: rows of last tick's buffer: 8 lanes per 112-byte row (7 active), 4 rows in flight --- */
+    /* ---- N: observation rows and stored rows leave the SM ----------------------------------- */
+    {
+        PveRowJob J;
+        J.A = A; J.srcc = srcc; J.vidx = vidx; J.surv = surv; J.del = del; J.lane_of = lane_of;
+        J.spref = misc + M_SPREF0; J.rows_smem = row0; J.rows_prev = row0_prev_base; J.rows_next = row0_next;
+        J.oblk = oblk; J.zero_row = AC;
+        pve_move_rows<NT>(J);
+    }
     PVE_FOR_TID(tid)
-        if (oblk) {
-            constexpr int RPI = NT / 8;
-            const int q = tid & 7;
-            const int n_prev = misc[M_NPREV];
-            const pve_v4 *PVE_RESTRICT prevq = (const pve_v4 *)row0_prev_base + q;
-            pve_v4 *PVE_RESTRICT obsq = oblk + q;
-            if (q < 7)
-                for (int li = tid >> 3; li < n_prev; li += 4 * RPI) {
-                    pve_v4 val[4];
-                    int dsti[4];
-#pragma unroll
-                    for (int u = 0; u < 4; ++u) {
-                        dsti[u] = -1;
-                        if (li + u * RPI < n_prev) {
-                            const int it = plist[li + u * RPI];
-                            const int g = it / 7, rw = it - g * 7;
-                            const int idx = (int)(srcc[g * 8 + rw] & 0x7FFFu);
-                            val[u] = prevq[idx * 7];
-                            dsti[u] = it * 7;
-                        }
-                    }
-#pragma unroll
-                    for (int u = 0; u < 4; ++u)
-                        if (dsti[u] >= 0) obsq[dsti[u]] = val[u];
-                }
-        }
-        pve_bulk_drain();           /* the TMA engine has finished reading this CTA's shared memory */
+        (void)tid;
     PVE_END_TID
+#if defined(PVE_PHASE_TIMING) && defined(__CUDACC__)
+    if (threadIdx.x == 0 && S.stats) {      /* debug build: overwrite this intersection's stats rows with stamps */
+        long long *dbg = (long long *)S.dbg + (size_t)b * 48;
+        for (int q = 0; q < 48; ++q) dbg[q] = q < pve_nstamp ? pve_stamp[q] - pve_stamp[0] : -1;
+    }
+#endif
 }

@@ -1,0 +1,46 @@
+#!/usr/bin/env python
+"""Wall-clock (SM cycles) spent between the kernel's phase boundaries, measured by CTA thread 0.
+
+Builds a DEBUG copy of the library with -DPVE_PHASE_TIMING into gpurun_out/ (never the product
+.so), runs the bench workload and prints the median cycles per phase.  GPU only."""
+import ctypes as C
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from pve_mcc_for_unsignalized_intersection_b200 import SceneConfig, _native  # noqa: E402
+from pve_mcc_for_unsignalized_intersection_b200.arrivals import synthetic_arrivals  # noqa: E402
+from pve_mcc_for_unsignalized_intersection_b200.build import CSRC, INCLUDE, NVCC_FLAGS, find_nvcc  # noqa: E402
+from pve_mcc_for_unsignalized_intersection_b200.scene import BatchedScene  # noqa: E402
+
+out_dir = os.path.join(ROOT, "gpurun_out")
+os.makedirs(out_dir, exist_ok=True)
+lib = os.path.join(out_dir, "libpve_mcc_timing.so")
+subprocess.check_call([find_nvcc()] + NVCC_FLAGS + ["-DPVE_PHASE_TIMING", "-I", INCLUDE, "-I", CSRC,
+                                                    os.path.join(CSRC, "pve_mcc.cu"), "-o", lib])
+threads = int(sys.argv[1]) if len(sys.argv) > 1 else 128
+B = 4096
+scene = BatchedScene(B, SceneConfig(vm=6), device="cuda:0", threads=threads, _library=lib)
+scene.reset(synthetic_arrivals(B, 1000, 120.0, seed=1000), warmup=True)
+acts = [(torch.rand(B, scene.veh_cap, device="cuda") * 6 - 3).contiguous() for _ in range(8)]
+for t in range(420):
+    scene.step(acts[t % 8])
+torch.cuda.synchronize()
+scene.lib.pve_debug_stamps.restype = C.c_void_p
+scene.lib.pve_debug_stamps.argtypes = [C.c_void_p]
+ptr = scene.lib.pve_debug_stamps(scene._h)
+st = scene._wrap(ptr, (B, 48), torch.int64, "<i8").cpu().numpy()
+n = int((st[0] >= 0).sum())
+d = np.diff(st[:, :n], axis=1)
+src = open(os.path.join(CSRC, "scene_step.cuh")).read()
+print("phases recorded:", n - 1, " median total cycles per CTA:", int(np.median(st[:, n - 1])))
+tot = np.median(st[:, n - 1])
+for i in range(n - 1):
+    print("boundary %2d -> %2d : median %6d  p90 %6d  (%4.1f%%)" % (i, i + 1, np.median(d[:, i]), np.percentile(d[:, i], 90),
+                                                                   100 * np.median(d[:, i]) / tot))
