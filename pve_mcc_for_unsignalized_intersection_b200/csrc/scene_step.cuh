@@ -41,18 +41,23 @@
 #define PVE_FOR_TID(tid) { const int tid = (int)threadIdx.x;
 #ifdef PVE_PHASE_TIMING      /* tools/phase_timing.py only: cycle stamp of every phase boundary, CTA thread 0 */
 #define PVE_END_TID } __syncthreads(); if (threadIdx.x == 0 && pve_nstamp < 48) pve_stamp[pve_nstamp++] = clock64();
+#define PVE_END_TID_NOSYNC } if (threadIdx.x == 0 && pve_nstamp < 48) pve_stamp[pve_nstamp++] = clock64();
 #else
 #define PVE_END_TID } __syncthreads();
+#define PVE_END_TID_NOSYNC }      /* the next phase reads nothing this one wrote */
 #endif
 #define PVE_ATOMIC_ADD(ptr, val) atomicAdd((ptr), (val))
+#define PVE_RED_ADD(ptr, val) atomicAdd((ptr), (val))   /* result unused: a RED, nothing to wait for */
 #define PVE_RESTRICT __restrict__
 #else
 #define PVE_DEV static inline
 #define PVE_HD static inline
 #define PVE_FOR_TID(tid) for (int tid = 0; tid < NT; ++tid) {
 #define PVE_END_TID }
+#define PVE_END_TID_NOSYNC }
 static inline int pve_emul_atomic_add(int *p, int v) { int o = *p; *p = o + v; return o; }
 #define PVE_ATOMIC_ADD(ptr, val) pve_emul_atomic_add((ptr), (val))
+#define PVE_RED_ADD(ptr, val) (*(ptr) += (val))
 #define PVE_RESTRICT __restrict__
 #endif
 
@@ -234,6 +239,47 @@ PVE_DEV int pve_block_excl_scan(const uint8_t *flag, uint16_t *out, int n, int32
 #endif
 }
 
+/* Q1 chain: s_k = F_k(s_{k-1}) with F_k a boolean function of one boolean, stored as two bits
+ * (bit x = F_k(x)).  Function composition is associative, so the chain over the dense vehicle
+ * order is an inclusive scan; a lane's front vehicle has the constant function 0, which restarts
+ * the chain, so no segmentation is needed.  Thread t writes sel[k] only for its own k. */
+PVE_HD uint32_t pve_compose(uint32_t later, uint32_t earlier) {      /* (later o earlier) */
+    return ((later >> (earlier & 1u)) & 1u) | (((later >> ((earlier >> 1) & 1u)) & 1u) << 1);
+}
+template <int NT>
+PVE_DEV void pve_resolve_chain(const uint8_t *fbits, uint8_t *sel, int n, int32_t *ws16) {
+#ifdef __CUDACC__
+    const int tid = (int)threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    constexpr int NW = NT / 32;
+    uint32_t carry = 0;                                   /* state entering the chunk */
+    for (int base = 0; base < n; base += NT) {
+        const int k = base + tid;
+        uint32_t g = (k < n) ? (uint32_t)fbits[k] : 2u;   /* 2 = identity */
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t t = __shfl_up_sync(0xffffffffu, g, d);
+            if (lane >= d) g = pve_compose(g, t);
+        }
+        int32_t *ws = ws16 + ((base / NT) & 1) * NW;
+        if (lane == 31) ws[warp] = (int32_t)g;
+        __syncthreads();
+        uint32_t s_in = carry, s_all = carry;
+#pragma unroll
+        for (int w = 0; w < NW; ++w) {
+            const uint32_t tw = (uint32_t)ws[w];
+            s_all = (tw >> s_all) & 1u;
+            if (w < warp) s_in = s_all;
+        }
+        if (k < n) sel[k] = (uint8_t)((g >> s_in) & 1u);
+        carry = s_all;
+    }
+#else
+    (void)ws16;
+    uint32_t st = 0;
+    for (int k = 0; k < n; ++k) { st = ((uint32_t)fbits[k] >> st) & 1u; sel[k] = (uint8_t)st; }
+#endif
+}
+
 /* statistics of the tick, computed by warp 0 only (no barrier): sum r, sum r^2, sum y */
 template <int NT>
 PVE_DEV void pve_warp0_sums(const float *x, const double *y, int n, double *out3) {
@@ -312,20 +358,17 @@ PVE_DEV void pve_move_rows(const PveRowJob &J) {
         pve_v4 *dst;
         pve_row_decode(J, chunk + lane, &src, &dst);
         const unsigned long long s64 = (unsigned long long)src, d64 = (unsigned long long)dst;
+        pve_v4 val[8];
 #pragma unroll
-        for (int half = 0; half < 2; ++half) {
-            pve_v4 val[4];
-            pve_v4 *dd[4];
+        for (int u = 0; u < 8; ++u) {           /* all eight loads of this lane are issued before any store */
+            const int from = u * 4 + sub;
+            const pve_v4 *ss = (const pve_v4 *)__shfl_sync(0xffffffffu, s64, from);
+            if (q < 7 && ss != nullptr) val[u] = ss[q];
+        }
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                const int from = (half * 4 + u) * 4 + sub;
-                const pve_v4 *ss = (const pve_v4 *)__shfl_sync(0xffffffffu, s64, from);
-                dd[u] = (pve_v4 *)__shfl_sync(0xffffffffu, d64, from);
-                if (q < 7 && dd[u] != nullptr) val[u] = ss[q];
-            }
-#pragma unroll
-            for (int u = 0; u < 4; ++u)
-                if (q < 7 && dd[u] != nullptr) dd[u][q] = val[u];
+        for (int u = 0; u < 8; ++u) {
+            pve_v4 *dd = (pve_v4 *)__shfl_sync(0xffffffffu, d64, u * 4 + sub);
+            if (q < 7 && dd != nullptr) dd[q] = val[u];
         }
     }
 #else
@@ -425,6 +468,11 @@ PVE_DEV void pve_step_block(const PveParams &P, const PveState &S, const pve_out
             ((pve_v4 *)hdr)[tid] = ((const pve_v4 *)(S.hdr + b))[tid];
         for (int q = tid; q < M_COUNT; q += NT) misc[q] = 0;
         if (tid < 16) { vl_cnt[tid] = 0; headk[tid] = -1; }
+        if (tid == 32) {        /* row range of this intersection in the dense outputs */
+            const int64_t lo = (int64_t)S.agent_offset[b], hi = (int64_t)S.agent_offset[b + 1];
+            wsum[32] = (hi <= P.out_cap && hi - lo <= AC) ? 1 : 0;
+            wsum[33] = (int32_t)lo;
+        }
     PVE_END_TID
 
     /* ---- L1: lane offsets (every lane of warp 0 sums its own prefix) ----------------------- */
@@ -435,14 +483,10 @@ PVE_DEV void pve_step_block(const PveParams &P, const PveState &S, const pve_out
             lane_off[tid] = o;
             if (tid == PVE_NLANE) misc[M_V] = o;
         }
-        if (tid == 32) {
-            misc[M_IDSEQ0] = hdr->id_seq;
-            const int64_t lo = (int64_t)S.agent_offset[b], hi = (int64_t)S.agent_offset[b + 1];
-            misc[M_OUTOK] = (hi <= P.out_cap && hi - lo <= AC) ? 1 : 0;
-        }
+        if (tid == 32) { misc[M_IDSEQ0] = hdr->id_seq; misc[M_OUTOK] = wsum[32]; }
     PVE_END_TID
     const int V = misc[M_V];
-    const int64_t obase = (int64_t)S.agent_offset[b];
+    const int64_t obase = (int64_t)wsum[33];
     /* this intersection's block of the dense observation output (null: rows are not emitted) */
     pve_v4 *const oblk = (O.obs != nullptr && misc[M_OUTOK]) ? (pve_v4 *)O.obs + obase * (PVE_OBS_H * PVE_OBS_W / 4)
                                                              : nullptr;
@@ -511,18 +555,10 @@ PVE_DEV void pve_step_block(const PveParams &P, const PveState &S, const pve_out
             }
             fbits[k] = (uint8_t)f;
         }
-    PVE_END_TID
+    PVE_END_TID_NOSYNC
 
-    /* ---- B2: resolve the chain front to back, one lane per thread ------------------------- */
-    PVE_FOR_TID(tid)
-        if (tid < PVE_NLANE) {
-            int s = 0;
-            for (int k = lane_off[tid]; k < lane_off[tid + 1]; ++k) {
-                s = (fbits[k] >> s) & 1;
-                ssel[k] = (uint8_t)s;
-            }
-        }
-    PVE_END_TID
+    /* ---- B2: resolve the chain (scan of boolean functions; one internal barrier) ------------ */
+    pve_resolve_chain<NT>(fbits, ssel, V, wsum + 16);
 
     /* ---- C: commit kinematics -------------------------------------------------------------- */
     PVE_FOR_TID(tid)
@@ -542,7 +578,7 @@ PVE_DEV void pve_step_block(const PveParams &P, const PveState &S, const pve_out
             const uint32_t fl = (pk >> 24) & (PVE_F_CONTROL | PVE_F_FINISH);     /* TIS:1506-1507 */
             spk[k] = (pk & 0x00FF0000u) | step | (fl << 24);
         }
-    PVE_END_TID
+    PVE_END_TID_NOSYNC
 
     /* ---- agent numbering: controlled at step() time == gets outputs this tick ------------- */
     const int A = pve_block_excl_scan<NT>(ctl0, acnt, V, wsum);
@@ -970,16 +1006,16 @@ PVE_DEV void pve_step_block(const PveParams &P, const PveState &S, const pve_out
             if (O.env_removed) O.env_removed[b] = misc[M_NREM];
             /* per-intersection running statistics (end-of-rollout reduction, MAIN:407-415) */
             double *st = S.stats + (size_t)b * PVE_NSTAT;
-            st[PVE_STAT_AGENT] += (double)A;
-            st[PVE_STAT_VEH] += (double)V;
-            st[PVE_STAT_COLL] += (double)misc[M_COLLAG];
-            st[PVE_STAT_LOCK] += (double)misc[M_LOCK];
-            st[PVE_STAT_JERK] += dsum[2];
-            st[PVE_STAT_RSUM] += dsum[0];
-            st[PVE_STAT_RSQ] += dsum[1];
-            st[PVE_STAT_REMOVED] += (double)misc[M_NREM];
-            st[PVE_STAT_STEPS] += 1.0;
-            st[PVE_STAT_Q5U] += (double)misc[M_Q5U];
+            PVE_RED_ADD(&st[PVE_STAT_AGENT], (double)A);
+            PVE_RED_ADD(&st[PVE_STAT_VEH], (double)V);
+            PVE_RED_ADD(&st[PVE_STAT_COLL], (double)misc[M_COLLAG]);
+            PVE_RED_ADD(&st[PVE_STAT_LOCK], (double)misc[M_LOCK]);
+            PVE_RED_ADD(&st[PVE_STAT_JERK], dsum[2]);
+            PVE_RED_ADD(&st[PVE_STAT_RSUM], dsum[0]);
+            PVE_RED_ADD(&st[PVE_STAT_RSQ], dsum[1]);
+            PVE_RED_ADD(&st[PVE_STAT_REMOVED], (double)misc[M_NREM]);
+            PVE_RED_ADD(&st[PVE_STAT_STEPS], 1.0);
+            PVE_RED_ADD(&st[PVE_STAT_Q5U], (double)misc[M_Q5U]);
         }
         if (out_ok) {
             for (int g = tid; g < A; g += NT) {
@@ -995,7 +1031,7 @@ PVE_DEV void pve_step_block(const PveParams &P, const PveState &S, const pve_out
                 if (O.jerk_sum) O.jerk_sum[obase + g] = (float)sjs[k];
             }
         }
-    PVE_END_TID
+    PVE_END_TID_NOSYNC
 
     /* ---- N: observation rows and stored rows leave the SM ----------------------------------- */
     {
@@ -1007,7 +1043,7 @@ PVE_DEV void pve_step_block(const PveParams &P, const PveState &S, const pve_out
     }
     PVE_FOR_TID(tid)
         (void)tid;
-    PVE_END_TID
+    PVE_END_TID_NOSYNC
 #if defined(PVE_PHASE_TIMING) && defined(__CUDACC__)
     if (threadIdx.x == 0 && S.stats) {      /* debug build: overwrite this intersection's stats rows with stamps */
         long long *dbg = (long long *)S.dbg + (size_t)b * 48;
