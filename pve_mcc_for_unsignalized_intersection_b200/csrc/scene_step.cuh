@@ -169,31 +169,6 @@ static_assert(M_COUNT <= 56, "misc block");
 #define PVE_SRC_PREV 0x8000u
 #define PVE_ROW_BYTES (PVE_OBS_W * 4)
 
-/* 112-byte row, shared memory -> global memory, through the TMA engine (SASS: UBLKCP).  Used for
- * the ~2 rows per agent whose source is the agent's own row (its observation row 0 and its stored
- * row for the next tick): issued early, they drain in the background.  (Moving ALL ~8 rows per
- * agent this way was measured: ~360 tiny bulk operations per intersection saturate the copy
- * engine.)  The writer of the row must call pve_fence_async_smem() first; every thread calls
- * pve_bulk_drain() before the CTA exits. */
-PVE_DEV void pve_bulk_row_store(void *dst_global, const void *src_smem) {
-#ifdef __CUDACC__
-    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
-                 :: "l"(dst_global), "r"((uint32_t)__cvta_generic_to_shared(src_smem)), "n"(PVE_ROW_BYTES) : "memory");
-#else
-    memcpy(dst_global, src_smem, PVE_ROW_BYTES);
-#endif
-}
-PVE_DEV void pve_fence_async_smem() {
-#ifdef __CUDACC__
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-#endif
-}
-PVE_DEV void pve_bulk_drain() {
-#ifdef __CUDACC__
-    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-#endif
-}
 PVE_DEV void pve_prefetch_l2(const void *p) {
 #ifdef __CUDACC__
     asm volatile("prefetch.global.L2 [%0];" :: "l"(p));
@@ -329,11 +304,11 @@ PVE_DEV void pve_warp0_sums(const float *x, const double *y, int n, double *out3
 }
 
 /* ---------------------------------------------------------------------------------------------
- * Row mover: rows 1..6 of the 7 x 28 observation of every agent (row 0 and the stored row of the
- * next tick are the agent's own row and leave through the TMA engine, see pve_bulk_row_store).
- * Item it < 6A  : observation row 1 + (it % 6) of agent (it / 6) = that neighbour's stored row (Q3):
- *                 this tick's row if the neighbour was processed earlier (shared memory), else last
- *                 tick's row (state buffer in HBM/L2), or zeros.
+ * Row mover: the 7 x 28 observation of every agent and the stored row 0 of every surviving agent.
+ * Item it < 7A  : observation row (it % 7) of agent (it / 7); row 0 is the agent's own row, row q+1
+ *                 is neighbour q's stored row (Q3): this tick's row if that neighbour was processed
+ *                 earlier (shared memory), else last tick's row (state buffer in HBM/L2), or zeros.
+ * Item 7A + g   : row 0 of agent g -> next tick's state buffer at the agent's compacted slot.
  * Device: every lane decodes one item (source and destination address); the warp then moves four
  * rows per step, 8 lanes per 112-byte row (7 active, 16 bytes each), with the addresses handed
  * around by shuffles; the source is a generic pointer, so shared and global rows take the same
@@ -353,18 +328,29 @@ struct PveRowJob {
 
 PVE_DEV void pve_row_decode(const PveRowJob &J, int it, const pve_v4 **src, pve_v4 **dst) {
     *src = nullptr; *dst = nullptr;
-    if (it < J.A * 6 && J.oblk) {
-        const int g = it / 6, rw = it - g * 6 + 1;
-        const uint32_t code = (uint32_t)J.srcc[g * 8 + rw];
-        const int idx = (int)(code & 0x7FFFu);
-        *src = (const pve_v4 *)(((code & PVE_SRC_PREV) ? J.rows_prev : J.rows_smem) + (size_t)idx * PVE_OBS_W);
-        *dst = J.oblk + (size_t)(g * 7 + rw) * 7;
+    const int n_obs = J.A * 7;
+    if (it < n_obs) {
+        if (J.oblk) {
+            const int g = it / 7, rw = it - g * 7;
+            const uint32_t code = rw ? (uint32_t)J.srcc[g * 8 + rw] : (uint32_t)g;
+            const int idx = (int)(code & 0x7FFFu);
+            *src = (const pve_v4 *)(((code & PVE_SRC_PREV) ? J.rows_prev : J.rows_smem) + (size_t)idx * PVE_OBS_W);
+            *dst = J.oblk + (size_t)it * 7;
+        }
+    } else if (it < n_obs + J.A) {
+        const int g = it - n_obs;
+        const int k = J.vidx[g];
+        if (!J.del[k]) {
+            const int np = (int)J.surv[k] + J.spref[J.lane_of[k]];
+            *src = (const pve_v4 *)(J.rows_smem + (size_t)g * PVE_OBS_W);
+            *dst = (pve_v4 *)(J.rows_next + (size_t)np * PVE_OBS_W);
+        }
     }
 }
 
 template <int NT>
 PVE_DEV void pve_move_rows(const PveRowJob &J) {
-    const int n_items = J.A * 6;
+    const int n_items = J.A * 8;
 #ifdef __CUDACC__
     const int tid = (int)threadIdx.x, lane = tid & 31, q = lane & 7, sub = lane >> 3;
     for (int chunk = (tid >> 5) * 32; chunk < n_items; chunk += NT) {
@@ -698,57 +684,79 @@ PVE_DEV void pve_step_block(const PveParams &P, const PveState &S, const pve_out
             /* vir_header / vir_dis, TIS:1349-1354 */
             if (r == 0) { hdra[g] = -1; virdis[g] = 100.0; }
             else { hdra[g] = (int16_t)acnt[sidx[base + r - 1]]; virdis[g] = pe - spos[base + r - 1]; }
-            /* Six nearest by |delta|, ties to the lower list index (stable sort, TIS:1389): a two-pointer
-             * walk outwards from the ego, entries below win ties against entries above.  Two entries
-             * BELOW the ego with exactly equal |delta| would have to come out farther-first; that
-             * case is detected and redone with the run-aware walk. */
+            /* Six nearest by |delta|, ties to the lower list index (stable sort, TIS:1389).  Only the six
+             * entries below and the six above the ego can qualify.  Instead of walking outwards (a
+             * serial chain of dependent loads) every candidate computes its position in the stable
+             * order by counting the candidates that precede it: below-side entries have lower list
+             * indices, so on equal |delta| they win against above-side ones, and among themselves the
+             * farther one (lower index) wins. */
             pve_v4 *const orow = (pve_v4 *)(row0 + (size_t)g * PVE_OBS_W);
             orow[0] = pve_pack4((float)pe, (float)sv[k], (float)sa[k], (float)d);        /* TIS:1336 */
             nn0[g] = 0xFFFFu;
             vd0s[g] = 0.0;
+            const double INF = 1.0e300;
+            double dl[PVE_NNBR], dh[PVE_NNBR];
+#pragma unroll
+            for (int i = 0; i < PVE_NNBR; ++i) {
+                const int xl = r - 1 - i, xh = r + 1 + i;
+                dl[i] = (xl >= 0) ? fabs(spos[base + (xl >= 0 ? xl : 0)] - pe) : INF;
+                dh[i] = (xh < n) ? fabs(spos[base + (xh < n ? xh : 0)] - pe) : INF;
+            }
             int ncand = 0;
-            for (int pass = 0; pass < 2; ++pass) {
+            /* a run of equal |delta| that continues below the window puts farther (lower-index) entries
+             * first: resolve that rare case with the reference's own outward walk */
+            const bool edge_tie = (r - 1 - PVE_NNBR >= 0) && dl[PVE_NNBR - 1] != INF &&
+                                  fabs(spos[base + (r - 1 - PVE_NNBR >= 0 ? r - 1 - PVE_NNBR : 0)] - pe) == dl[PVE_NNBR - 1];
+            if (edge_tie) {
                 int lo = r - 1, hi = r + 1, run_cur = 0, run_end = -1;
                 double run_d = 0;
-                const double INF = 1.0e300;
-                double dlo = lo >= 0 ? fabs(spos[base + (lo >= 0 ? lo : 0)] - pe) : INF;
-                double dhi = hi < n ? fabs(spos[base + (hi < n ? hi : 0)] - pe) : INF;
-                bool tie = false;
-                ncand = 0;
                 for (int q = 0; q < PVE_NNBR; ++q) {
-                    int pick = -1;
-                    if (pass == 0) {
-                        if (lo >= 0 && dlo <= dhi) {
-                            pick = lo--;
-                            const double nd = lo >= 0 ? fabs(spos[base + (lo >= 0 ? lo : 0)] - pe) : INF;
-                            tie = tie || (nd == dlo);
-                            dlo = nd;
-                        } else if (hi < n) {
-                            pick = hi++;
-                            dhi = hi < n ? fabs(spos[base + (hi < n ? hi : 0)] - pe) : INF;
-                        }
-                    } else {                                                     /* run-aware reference walk */
-                        if (run_cur > run_end && lo >= 0) {
-                            run_end = lo; run_d = fabs(spos[base + lo] - pe);
-                            int x = lo;
-                            while (x - 1 >= 0 && fabs(spos[base + x - 1] - pe) == run_d) --x;
-                            run_cur = x; lo = x - 1;
-                        }
-                        const bool has_lo = run_cur <= run_end, has_hi = hi < n;
-                        if (has_lo && (!has_hi || run_d <= fabs(spos[base + hi] - pe))) pick = run_cur++;
-                        else if (has_hi) pick = hi++;
+                    if (run_cur > run_end && lo >= 0) {
+                        run_end = lo; run_d = fabs(spos[base + lo] - pe);
+                        int x = lo;
+                        while (x - 1 >= 0 && fabs(spos[base + x - 1] - pe) == run_d) --x;
+                        run_cur = x; lo = x - 1;
                     }
+                    const bool has_lo = run_cur <= run_end, has_hi = hi < n;
+                    int pick = -1;
+                    if (has_lo && (!has_hi || run_d <= fabs(spos[base + hi] - pe))) pick = run_cur++;
+                    else if (has_hi) pick = hi++;
                     if (pick >= 0) {
                         const int kn = sidx[base + pick];
                         const double vd = spos[base + pick];
-                        orow[q + 1] = pve_pack4((float)vd, (float)sv[kn], (float)sa[kn], (float)lane_of[kn]);   /* TIS:1330 */
-                        /* Q3: neighbour already processed this tick -> its new row, else last tick's */
+                        orow[q + 1] = pve_pack4((float)vd, (float)sv[kn], (float)sa[kn], (float)lane_of[kn]);
                         srcc[g * 8 + q + 1] = (kn < k) ? (uint16_t)acnt[kn] : (uint16_t)(PVE_SRC_PREV | kn);
                         if (q == 0) { nn0[g] = (uint16_t)kn; vd0s[g] = vd; }
                         ++ncand;
                     }
                 }
-                if (!tie) break;
+            } else
+#pragma unroll
+            for (int side = 0; side < 2; ++side) {
+#pragma unroll
+                for (int i = 0; i < PVE_NNBR; ++i) {
+                    const int x = side ? r + 1 + i : r - 1 - i;
+                    const bool ok = side ? (x < n) : (x >= 0);
+                    const double di = side ? dh[i] : dl[i];
+                    int rk = side ? i : 0;
+#pragma unroll
+                    for (int j = 0; j < PVE_NNBR; ++j) {
+                        if (side) rk += (dl[j] <= di) ? 1 : 0;
+                        else {
+                            if (j != i) rk += (dl[j] < di || (dl[j] == di && j > i)) ? 1 : 0;
+                            rk += (dh[j] < di) ? 1 : 0;
+                        }
+                    }
+                    ncand += ok ? 1 : 0;
+                    if (ok && rk < PVE_NNBR) {
+                        const int kn = sidx[base + x];
+                        const double vd = spos[base + x];
+                        orow[rk + 1] = pve_pack4((float)vd, (float)sv[kn], (float)sa[kn], (float)lane_of[kn]);   /* TIS:1330 */
+                        /* Q3: neighbour already processed this tick -> its new row, else last tick's */
+                        srcc[g * 8 + rk + 1] = (kn < k) ? (uint16_t)acnt[kn] : (uint16_t)(PVE_SRC_PREV | kn);
+                        if (rk == 0) { nn0[g] = (uint16_t)kn; vd0s[g] = vd; }
+                    }
+                }
             }
 #pragma unroll
             for (int q = 0; q < PVE_NNBR; ++q)
@@ -756,9 +764,6 @@ PVE_DEV void pve_step_block(const PveParams &P, const PveState &S, const pve_out
                     orow[q + 1] = pve_pack4(0.f, 0.f, 0.f, 0.f);                 /* TIS:1334 */
                     srcc[g * 8 + q + 1] = (uint16_t)AC;                          /* the zero row */
                 }
-            /* the finished row is this agent's observation row 0: hand it to the copy engine now */
-            pve_fence_async_smem();
-            if (oblk) pve_bulk_row_store(oblk + (size_t)g * 49, orow);
         }
         if (tid < PVE_OBS_W / 4) ((pve_v4 *)(row0 + (size_t)AC * PVE_OBS_W))[tid] = pve_pack4(0.f, 0.f, 0.f, 0.f);
     PVE_END_TID
@@ -974,14 +979,6 @@ PVE_DEV void pve_step_block(const PveParams &P, const PveState &S, const pve_out
                             | ((uint32_t)(slocka[k] + 1) << 27);
                 S.meta[o] = mt;
             }
-        /* stored row 0 of every surviving agent -> next tick's neighbour rows / actor input */
-        for (int g = tid; g < A; g += NT) {
-            const int k = vidx[g];
-            if (!del[k]) {
-                const int np = (int)surv[k] + misc[M_SPREF0 + lane_of[k]];
-                pve_bulk_row_store(row0_next + (size_t)np * PVE_OBS_W, row0 + (size_t)g * PVE_OBS_W);
-            }
-        }
         if (tid < PVE_NLANE && misc[M_SPAWN0 + tid]) {                           /* TIS:395-427 */
             const int i = tid;
             const int np = (int)surv[lane_off[i + 1]] + misc[M_SPREF0 + i];
@@ -1046,7 +1043,6 @@ PVE_DEV void pve_step_block(const PveParams &P, const PveState &S, const pve_out
     }
     PVE_FOR_TID(tid)
         (void)tid;
-        pve_bulk_drain();           /* the copy engine has finished reading this CTA's shared memory */
     PVE_END_TID_NOSYNC
 #if defined(PVE_PHASE_TIMING) && defined(__CUDACC__)
     if (threadIdx.x == 0 && S.stats) {      /* debug build: overwrite this intersection's stats rows with stamps */
