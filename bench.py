@@ -271,6 +271,15 @@ def graft_arm(args, rank, world, local_rank):
         peak = float(peaks.get("hbm_gbs", 6650.0))
         peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6.65 TB/s"
         # per-GPU achieved bandwidth of the step kernel: this rank's algorithmic bytes / its kernel time
+        # DRAM bytes per launch of the step kernel from the newest committed ncu capture (same workload)
+        traffic = None
+        try:
+            import glob
+            caps = sorted(glob.glob(os.path.join(ROOT, "profiles", "*step_kernel*_full.json")))
+            if caps and args.envs == ENVS_PER_GPU and args.workload == "poisson":
+                traffic = json.load(open(caps[-1]))["derived"]["dram_traffic_bytes_per_launch"]
+        except Exception:
+            traffic = None
         alg_bytes = BYTES_PER_VEH * dV + BYTES_PER_AGENT * dA
         my_kern_ms = float(sum(kern_ms))
         achieved = alg_bytes / (my_kern_ms * 1e-3) / 1e9
@@ -284,7 +293,7 @@ def graft_arm(args, rank, world, local_rank):
                        "agents_per_env_step": dA / (K * B), "vehicles_per_env_step": dV / (K * B),
                        "env_steps_per_s": world * B * K / (total_ms * 1e-3)},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                         "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                          "kernel": "pve_step_kernel", "kernel_ms_per_launch": my_kern_ms / K,
                          "scan_ms_per_launch": float(sum(scan_ms)) / K,
                          "algorithmic_bytes_per_launch": alg_bytes / K},
