@@ -46,6 +46,15 @@
 #define PVE_END_TID } __syncthreads();
 #define PVE_END_TID_NOSYNC }      /* the next phase reads nothing this one wrote */
 #endif
+/* After phase G1 the CTA splits: threads [0, NS) ("team") finish the tick with named barrier 1,
+ * threads [NS, NT) move the observation rows concurrently and exit.  NS == NT: no split. */
+#ifdef PVE_PHASE_TIMING
+#define PVE_TEAM_STAMP if (threadIdx.x == 0 && pve_nstamp < 48) pve_stamp[pve_nstamp++] = clock64();
+#else
+#define PVE_TEAM_STAMP
+#endif
+#define PVE_FOR_TEAM(tid) { const int tid = (int)threadIdx.x;
+#define PVE_END_TEAM } pve_team_sync<NS, NT>(); PVE_TEAM_STAMP
 #define PVE_ATOMIC_ADD(ptr, val) atomicAdd((ptr), (val))
 #define PVE_RED_ADD(ptr, val) atomicAdd((ptr), (val))   /* result unused: a RED, nothing to wait for */
 #define PVE_RESTRICT __restrict__
@@ -55,6 +64,8 @@
 #define PVE_FOR_TID(tid) for (int tid = 0; tid < NT; ++tid) {
 #define PVE_END_TID }
 #define PVE_END_TID_NOSYNC }
+#define PVE_FOR_TEAM(tid) for (int tid = 0; tid < NS; ++tid) {
+#define PVE_END_TEAM }
 static inline int pve_emul_atomic_add(int *p, int v) { int o = *p; *p = o + v; return o; }
 #define PVE_ATOMIC_ADD(ptr, val) pve_emul_atomic_add((ptr), (val))
 #define PVE_RED_ADD(ptr, val) (*(ptr) += (val))
@@ -208,7 +219,14 @@ PVE_DEV pve_v4 pve_ld_l2(const pve_v4 *p) { return *p; }
  * also returned to every thread.  This is the stream-compaction index used for agent numbering and
  * for vehicle removal.  NO trailing barrier: thread t may read the out[k] it wrote itself
  * (k = t, t + NT, ...) right away; the caller's next phase boundary publishes the rest. */
-template <int NT>
+#ifdef __CUDACC__
+template <int NTH, int NTOT>
+PVE_DEV void pve_team_sync() {
+    if (NTH == NTOT) __syncthreads();
+    else asm volatile("bar.sync 1, %0;" :: "n"(NTH) : "memory");
+}
+#endif
+template <int NT, int NTOT = NT>
 PVE_DEV int pve_block_excl_scan(const uint8_t *flag, uint16_t *out, int n, int32_t *wsum) {
 #ifdef __CUDACC__
     const int tid = (int)threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -221,7 +239,7 @@ PVE_DEV int pve_block_excl_scan(const uint8_t *flag, uint16_t *out, int n, int32
         const int wp = __popc(bal & ((1u << lane) - 1u));
         int32_t *ws = wsum + ((base / NT) & 1) * NW;      /* double-buffered: one barrier per chunk */
         if (lane == 0) ws[warp] = __popc(bal);
-        __syncthreads();
+        pve_team_sync<NT, NTOT>();
         int woff = 0, tot = 0;
 #pragma unroll
         for (int w = 0; w < NW; ++w) { const int c = ws[w]; woff += (w < warp) ? c : 0; tot += c; }
@@ -304,79 +322,64 @@ PVE_DEV void pve_warp0_sums(const float *x, const double *y, int n, double *out3
 }
 
 /* ---------------------------------------------------------------------------------------------
- * Row mover: the 7 x 28 observation of every agent and the stored row 0 of every surviving agent.
- * Item it < 7A  : observation row (it % 7) of agent (it / 7); row 0 is the agent's own row, row q+1
- *                 is neighbour q's stored row (Q3): this tick's row if that neighbour was processed
- *                 earlier (shared memory), else last tick's row (state buffer in HBM/L2), or zeros.
- * Item 7A + g   : row 0 of agent g -> next tick's state buffer at the agent's compacted slot.
- * Device: every lane decodes one item (source and destination address); the warp then moves four
- * rows per step, 8 lanes per 112-byte row (7 active, 16 bytes each), with the addresses handed
- * around by shuffles; the source is a generic pointer, so shared and global rows take the same
- * path without divergence, and four loads are in flight per lane.
+ * Row mover: the 7 x 28 observation of every agent.  Row 0 is the agent's own row, row q+1 is
+ * neighbour q's stored row (Q3): this tick's row if that neighbour was processed earlier (shared
+ * memory), else last tick's row (state buffer, prefetched to L2 in phase A), or zeros.
+ * Device: every lane decodes one row (a 32-bit source code); the warp then moves four rows per
+ * step, 8 lanes per 112-byte row (7 active, 16 bytes each), the codes handed around by shuffles,
+ * with eight loads in flight per lane.  It runs on the warps that have no work in the agent phases,
+ * concurrently with them (see the CTA split after phase G1).
  * ------------------------------------------------------------------------------------------- */
 struct PveRowJob {
     int A;
-    const uint16_t *srcc, *vidx, *surv;
-    const uint8_t *del, *lane_of;
-    const int32_t *spref;
+    const uint16_t *srcc;
     const float *rows_smem;       /* [AC + 1][28], row AC = zeros */
     const float *rows_prev;       /* last tick's stored rows of this intersection */
-    float *rows_next;             /* next tick's stored rows of this intersection */
     pve_v4 *oblk;                 /* this intersection's observation block or null */
-    int zero_row;
 };
 
-PVE_DEV void pve_row_decode(const PveRowJob &J, int it, const pve_v4 **src, pve_v4 **dst) {
-    *src = nullptr; *dst = nullptr;
-    const int n_obs = J.A * 7;
-    if (it < n_obs) {
-        if (J.oblk) {
-            const int g = it / 7, rw = it - g * 7;
-            const uint32_t code = rw ? (uint32_t)J.srcc[g * 8 + rw] : (uint32_t)g;
-            const int idx = (int)(code & 0x7FFFu);
-            *src = (const pve_v4 *)(((code & PVE_SRC_PREV) ? J.rows_prev : J.rows_smem) + (size_t)idx * PVE_OBS_W);
-            *dst = J.oblk + (size_t)it * 7;
-        }
-    } else if (it < n_obs + J.A) {
-        const int g = it - n_obs;
-        const int k = J.vidx[g];
-        if (!J.del[k]) {
-            const int np = (int)J.surv[k] + J.spref[J.lane_of[k]];
-            *src = (const pve_v4 *)(J.rows_smem + (size_t)g * PVE_OBS_W);
-            *dst = (pve_v4 *)(J.rows_next + (size_t)np * PVE_OBS_W);
-        }
-    }
+/* item it < 7A: observation row (it % 7) of agent (it / 7).  code: bit 31 = source is last tick's
+ * buffer, low bits = row index there / in the shared-memory row table; 0xFFFFFFFF = nothing to do */
+PVE_DEV uint32_t pve_row_code(const PveRowJob &J, int it) {
+    if (it >= J.A * 7) return 0xFFFFFFFFu;
+    const int g = it / 7, rw = it - g * 7;
+    const uint32_t c = rw ? (uint32_t)J.srcc[g * 8 + rw] : (uint32_t)g;
+    return ((c & PVE_SRC_PREV) ? 0x80000000u : 0u) | (c & 0x7FFFu);
 }
 
 template <int NT>
-PVE_DEV void pve_move_rows(const PveRowJob &J) {
-    const int n_items = J.A * 8;
+PVE_DEV void pve_move_rows(const PveRowJob &J, int first_warp, int n_warps) {
+    if (J.oblk == nullptr) return;
+    const int n_items = J.A * 7;
 #ifdef __CUDACC__
     const int tid = (int)threadIdx.x, lane = tid & 31, q = lane & 7, sub = lane >> 3;
-    for (int chunk = (tid >> 5) * 32; chunk < n_items; chunk += NT) {
-        const pve_v4 *src;
-        pve_v4 *dst;
-        pve_row_decode(J, chunk + lane, &src, &dst);
-        const unsigned long long s64 = (unsigned long long)src, d64 = (unsigned long long)dst;
+    const pve_v4 *PVE_RESTRICT prevq = (const pve_v4 *)J.rows_prev + q;
+    const pve_v4 *rowsq = (const pve_v4 *)J.rows_smem + q;
+    pve_v4 *PVE_RESTRICT dstq = J.oblk + q;
+    for (int chunk = ((tid >> 5) - first_warp) * 32; chunk < n_items; chunk += n_warps * 32) {
+        const uint32_t code = pve_row_code(J, chunk + lane);
         pve_v4 val[8];
 #pragma unroll
         for (int u = 0; u < 8; ++u) {           /* all eight loads of this lane are issued before any store */
-            const int from = u * 4 + sub;
-            const pve_v4 *ss = (const pve_v4 *)__shfl_sync(0xffffffffu, s64, from);
-            if (q < 7 && ss != nullptr) val[u] = ss[q];
+            const uint32_t cu = __shfl_sync(0xffffffffu, code, u * 4 + sub);
+            if (q < 7 && cu != 0xFFFFFFFFu) {
+                if (cu & 0x80000000u) val[u] = prevq[(cu & 0x7FFFu) * 7];
+                else val[u] = rowsq[cu * 7];
+            }
         }
 #pragma unroll
         for (int u = 0; u < 8; ++u) {
-            pve_v4 *dd = (pve_v4 *)__shfl_sync(0xffffffffu, d64, u * 4 + sub);
-            if (q < 7 && dd != nullptr) dd[q] = val[u];
+            const int it = chunk + u * 4 + sub;
+            if (q < 7 && it < n_items) dstq[it * 7] = val[u];
         }
     }
 #else
+    (void)first_warp; (void)n_warps;
     for (int it = 0; it < n_items; ++it) {
-        const pve_v4 *src;
-        pve_v4 *dst;
-        pve_row_decode(J, it, &src, &dst);
-        if (dst) memcpy(dst, src, PVE_OBS_W * sizeof(float));
+        const uint32_t c = pve_row_code(J, it);
+        const float *src = (c & 0x80000000u) ? J.rows_prev + (size_t)(c & 0x7FFFu) * PVE_OBS_W
+                                             : J.rows_smem + (size_t)c * PVE_OBS_W;
+        memcpy(J.oblk + (size_t)it * 7, src, PVE_OBS_W * sizeof(float));
     }
 #endif
 }
@@ -768,10 +771,22 @@ PVE_DEV void pve_step_block(const PveParams &P, const PveState &S, const pve_out
         if (tid < PVE_OBS_W / 4) ((pve_v4 *)(row0 + (size_t)AC * PVE_OBS_W))[tid] = pve_pack4(0.f, 0.f, 0.f, 0.f);
     PVE_END_TID
 
+    /* ---- CTA split: the upper half of the CTA moves the observation rows (everything they need is
+     *      final after G1) while the lower half ("team") finishes the tick ------------------------ */
+    constexpr int NS = (NT >= 128) ? NT / 2 : NT;
+    PveRowJob RJ;
+    RJ.A = A; RJ.srcc = srcc; RJ.rows_smem = row0; RJ.rows_prev = row0_prev_base; RJ.oblk = oblk;
+#ifdef __CUDACC__
+    if (NS < NT && (int)threadIdx.x >= NS) {
+        pve_move_rows<NT>(RJ, NS / 32, (NT - NS) / 32);
+        return;
+    }
+#endif
+
     /* ---- G2: two work items per agent: reward (TIS:293-320), world position (TIS:1250-1290) */
-    PVE_FOR_TID(tid)
+    PVE_FOR_TEAM(tid)
         const int A32 = (A + 31) & ~31;         /* the two item kinds start on warp boundaries */
-        for (int it = tid; it < A32 + A; it += NT) {
+        for (int it = tid; it < A32 + A; it += NS) {
             const bool is_xy = it >= A32;
             const int g = is_xy ? it - A32 : it;
             if (g >= A) continue;
@@ -801,11 +816,11 @@ PVE_DEV void pve_step_block(const PveParams &P, const PveState &S, const pve_out
                 rew[g] = (float)fmin(20.0, fmax(-20.0, r_));                     /* TIS:320 */
             }
         }
-    PVE_END_TID
+    PVE_END_TEAM
 
     /* ---- G3: collision test in world space, TIS:322-334 ------------------------------------ */
-    PVE_FOR_TID(tid)
-        for (int g = tid; g < A; g += NT) {
+    PVE_FOR_TEAM(tid)
+        for (int g = tid; g < A; g += NS) {
             const int k0 = nn0[g];
             if (k0 != 0xFFFF) {
                 const int g0 = acnt[k0];
@@ -817,11 +832,11 @@ PVE_DEV void pve_step_block(const PveParams &P, const PveState &S, const pve_out
                 }
             }
         }
-    PVE_END_TID
+    PVE_END_TEAM
 
     /* ---- H: removal / finish flags for every vehicle, TIS:335-359 ------------------------- */
-    PVE_FOR_TID(tid)
-        for (int k = tid; k < V; k += NT) {
+    PVE_FOR_TEAM(tid)
+        for (int k = tid; k < V; k += NS) {
             const int g = ctl0[k] ? (int)acnt[k] : -1;
             uint32_t pk = spk[k];
             const int prev = (int)((pk >> 16) & 0xFFu);
@@ -854,11 +869,11 @@ PVE_DEV void pve_step_block(const PveParams &P, const PveState &S, const pve_out
             fbits[k] = del[k] ? 0 : 1;                                           /* survivor flag */
             if (!del[k] && (fl & PVE_F_CONTROL)) PVE_ATOMIC_ADD(&misc[M_NCTRL], 1);
         }
-    PVE_END_TID
+    PVE_END_TEAM
 
     /* ---- I: deadlock scan (TIS:365-370 + 1469-1499); final rewards ------------------------- */
-    PVE_FOR_TID(tid)
-        for (int g = tid; g < A; g += NT) {
+    PVE_FOR_TEAM(tid)
+        for (int g = tid; g < A; g += NS) {
             const int k = vidx[g];
             /* reward[-1] overrides in processing order: a later -10 beats the agent's own +5 (Q5) */
             if (q5[g]) rew[g] = -10.f;                                           /* TIS:346 */
@@ -903,16 +918,16 @@ PVE_DEV void pve_step_block(const PveParams &P, const PveState &S, const pve_out
                 slocka[vidx[hdra[first_o]]] = -1;                                /* TIS:1497 */
             }
         }
-    PVE_END_TID
+    PVE_END_TEAM
 
     /* ---- removal by stream compaction (TIS:435-444): survivors keep their order ----------- */
-    pve_block_excl_scan<NT>(fbits, surv, V, wsum);
-    PVE_FOR_TID(tid)
+    pve_block_excl_scan<NS, NT>(fbits, surv, V, wsum);
+    PVE_FOR_TEAM(tid)
         (void)tid;
-    PVE_END_TID
+    PVE_END_TEAM
 
     /* ---- J: arrivals (TIS:378-433) and header update, one thread per lane ------------------ */
-    PVE_FOR_TID(tid)
+    PVE_FOR_TEAM(tid)
         if (tid < PVE_NLANE) {
             const int i = tid;
             const int tick = hdr->tick + 1;                                      /* TIS:223 */
@@ -953,10 +968,10 @@ PVE_DEV void pve_step_block(const PveParams &P, const PveState &S, const pve_out
             hdr->passed_step_total += misc[M_PSTEP];
             if (!misc[M_OUTOK]) PVE_ATOMIC_ADD(&hdr->overflow, 1);    /* output rows do not fit: sticky flag */
         }
-    PVE_END_TID
+    PVE_END_TEAM
 
     /* ---- K: write the state back, compacted ------------------------------------------------ */
-    PVE_FOR_TID(tid)
+    PVE_FOR_TEAM(tid)
         if (tid == 0) hdr->tick += 1;
         if (tid >= 32 && tid < 32 + PVE_NLANE) {
             /* header fields other lanes were still reading in phase J */
@@ -969,7 +984,7 @@ PVE_DEV void pve_step_block(const PveParams &P, const PveState &S, const pve_out
             }
             hdr->lane_n[i] = (uint8_t)misc[M_NEWN0 + i];
         }
-        for (int k = tid; k < V; k += NT)
+        for (int k = tid; k < V; k += NS)
             if (!del[k]) {
                 const size_t o = vbase + (size_t)((int)surv[k] + misc[M_SPREF0 + lane_of[k]]);
                 S.p[o] = sp[k]; S.v[o] = sv[k]; S.a[o] = sa[k]; S.js[o] = sjs[k];
@@ -992,12 +1007,20 @@ PVE_DEV void pve_step_block(const PveParams &P, const PveState &S, const pve_out
             for (int q = 0; q < PVE_OBS_W / 4; ++q) ((pve_v4 *)(row0_next + (size_t)np * PVE_OBS_W))[q] = z;
         }
         /* stored row 0 of every surviving agent -> next tick's neighbour rows / actor input */
-    PVE_END_TID
+        for (int it = tid; it < A * 8; it += NS) {
+            const int g = it >> 3, q = it & 7;
+            const int k = vidx[g];
+            if (q < 7 && !del[k]) {
+                const int np = (int)surv[k] + misc[M_SPREF0 + lane_of[k]];
+                ((pve_v4 *)(row0_next + (size_t)np * PVE_OBS_W))[q] = ((const pve_v4 *)(row0 + (size_t)g * PVE_OBS_W))[q];
+            }
+        }
+    PVE_END_TEAM
 
     /* ---- M: outputs ------------------------------------------------------------------------ */
     pve_warp0_sums<NT>(rew, vd0s, A, dsum);
     const bool out_ok = misc[M_OUTOK] != 0;
-    PVE_FOR_TID(tid)
+    PVE_FOR_TEAM(tid)
         if (tid < PVE_HDR_BYTES / 16) ((pve_v4 *)(S.hdr + b))[tid] = ((const pve_v4 *)hdr)[tid];
         if (tid == 0) {
             S.n_ctrl[b] = hdr->n_ctrl; S.n_veh[b] = hdr->n_veh;
@@ -1018,7 +1041,7 @@ PVE_DEV void pve_step_block(const PveParams &P, const PveState &S, const pve_out
             PVE_RED_ADD(&st[PVE_STAT_Q5U], (double)misc[M_Q5U]);
         }
         if (out_ok) {
-            for (int g = tid; g < A; g += NT) {
+            for (int g = tid; g < A; g += NS) {
                 const int k = vidx[g];
                 if (O.reward) O.reward[obase + g] = rew[g];
                 if (O.ids) {
@@ -1033,17 +1056,12 @@ PVE_DEV void pve_step_block(const PveParams &P, const PveState &S, const pve_out
         }
     PVE_END_TID_NOSYNC
 
-    /* ---- N: observation rows and stored rows leave the SM ----------------------------------- */
-    {
-        PveRowJob J;
-        J.A = A; J.srcc = srcc; J.vidx = vidx; J.surv = surv; J.del = del; J.lane_of = lane_of;
-        J.spref = misc + M_SPREF0; J.rows_smem = row0; J.rows_prev = row0_prev_base; J.rows_next = row0_next;
-        J.oblk = oblk; J.zero_row = AC;
-        pve_move_rows<NT>(J);
-    }
-    PVE_FOR_TID(tid)
-        (void)tid;
-    PVE_END_TID_NOSYNC
+    /* ---- N: observation rows leave the SM (already under way on the upper half when the CTA is split) */
+#ifdef __CUDACC__
+    if (NS == NT) pve_move_rows<NT>(RJ, 0, NT / 32);
+#else
+    pve_move_rows<NT>(RJ, 0, 1);
+#endif
 #if defined(PVE_PHASE_TIMING) && defined(__CUDACC__)
     if (threadIdx.x == 0 && S.stats) {      /* debug build: overwrite this intersection's stats rows with stamps */
         long long *dbg = (long long *)S.dbg + (size_t)b * 48;
