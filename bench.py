@@ -297,7 +297,7 @@ def graft_arm(args, rank, world, local_rank):
                          "kernel": "pve_step_kernel", "kernel_ms_per_launch": my_kern_ms / K,
                          "scan_ms_per_launch": float(sum(scan_ms)) / K,
                          "algorithmic_bytes_per_launch": alg_bytes / K},
-            "gpu_launches": K,          # one kernel per tick (the row-offset scan runs in its last CTA)
+            "gpu_launches": 2 * K,
             "clocks": sampler.result(),
             "stats": {k: float(v) for k, v in zip(
                 ["agent_steps", "vehicle_steps", "env_steps", "spawned", "passed", "passed_step_total",

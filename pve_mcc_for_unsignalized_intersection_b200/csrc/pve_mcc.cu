@@ -334,7 +334,6 @@ static int32_t launch_step(pve_scene *s, const float *actions, const pve_outputs
 #undef X
     free(smem);
     if (!done) return PVE_EINVAL;
-    emul_offset_scan(s->st.n_ctrl, s->st.agent_offset, B);     /* on the device: last CTA of the launch */
 #endif
     s->phase ^= 1;
     return PVE_OK;
@@ -396,7 +395,7 @@ void pve_destroy(pve_scene *s) {
     rt_free(s->st.hdr); rt_free(s->st.p); rt_free(s->st.v); rt_free(s->st.a); rt_free(s->st.js);
     rt_free(s->st.meta); rt_free(s->st.row0[0]); rt_free(s->st.row0[1]);
     rt_free(s->st.n_ctrl); rt_free(s->st.n_veh); rt_free(s->st.stats); rt_free(s->st.agent_offset);
-    rt_free(s->actions_dev); rt_free(s->counters_dev); rt_free(s->st.done);
+    rt_free(s->actions_dev); rt_free(s->counters_dev);
     rt_host_free(s->pinned_i32);
 #ifndef PVE_HOST_EMULATION
     for (int i = 0; i < 3; ++i) if (s->ev[i]) cudaEventDestroy(s->ev[i]);
@@ -470,8 +469,6 @@ int32_t pve_create(const pve_config *cfg, int32_t device, pve_scene **out) {
     RT_CHECK(s, rt_alloc((void **)&s->st.stats, sizeof(double) * (size_t)B * PVE_NSTAT));
     RT_CHECK(s, rt_alloc((void **)&s->st.agent_offset, sizeof(int32_t) * ((size_t)B + 1)));
     RT_CHECK(s, rt_alloc((void **)&s->counters_dev, sizeof(double) * 16));
-    RT_CHECK(s, rt_alloc((void **)&s->st.done, sizeof(unsigned int) * 4));
-    RT_CHECK(s, rt_memset(s->st.done, 0, sizeof(unsigned int) * 4, nullptr));
 #ifdef PVE_PHASE_TIMING
     RT_CHECK(s, rt_alloc((void **)&s->st.dbg, sizeof(long long) * 48 * (size_t)B));
 #endif
@@ -507,6 +504,8 @@ int32_t pve_reset(pve_scene *s, const int32_t *spawn_tick_dev, int32_t K, int32_
         /* the tick that brings the first vehicle(s) in: nothing to step, nothing to emit */
         if (!s->actions_dev) RT_CHECK(s, rt_alloc((void **)&s->actions_dev, sizeof(float) * nv));
         rc = launch_step(s, s->actions_dev, null_outputs(), stream);
+        if (rc != PVE_OK) return rc;
+        rc = launch_scan(s, stream);
     }
     return rc;
 }
@@ -515,13 +514,14 @@ int32_t pve_step(pve_scene *s, const float *actions_dev, const pve_outputs *out_
     if (!s || !actions_dev) return PVE_EINVAL;
     pve_stream_t stream = (pve_stream_t)stream_;
     const pve_outputs O = out_dev ? *out_dev : null_outputs();
-    /* one launch per tick: every CTA copies its row offset to the caller's buffer, and the last CTA
-     * to finish scans the row offsets of the NEXT tick */
+    if (O.agent_offset)
+        RT_CHECK(s, rt_copy(O.agent_offset, s->st.agent_offset, sizeof(int32_t) * ((size_t)s->cfg.n_envs + 1), stream));
     int32_t rc = launch_step(s, actions_dev, O, stream);
     if (rc != PVE_OK) return rc;
     s->next_total = -1;
+    rc = launch_scan(s, stream);          /* row offsets of the NEXT tick */
 #ifndef PVE_HOST_EMULATION
-    if (s->profiling) RT_CHECK(s, cudaEventRecord(s->ev[2], stream));
+    if (rc == PVE_OK && s->profiling) RT_CHECK(s, cudaEventRecord(s->ev[2], stream));
 #endif
     return rc;
 }

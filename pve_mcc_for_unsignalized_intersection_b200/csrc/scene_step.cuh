@@ -97,7 +97,6 @@ struct PveState {
     double *stats;            /* [B][PVE_NSTAT] running per-intersection statistics */
     int32_t *agent_offset;    /* [B+1] rows of this tick (written by the scan kernel) */
     void *dbg;                /* tools/phase_timing.py builds only: [B][48] cycle stamps */
-    unsigned int *done;       /* CTAs finished in this launch: the last one scans the row offsets of the next tick */
 };
 
 enum { PVE_STAT_AGENT = 0, PVE_STAT_VEH, PVE_STAT_COLL, PVE_STAT_LOCK, PVE_STAT_JERK, PVE_STAT_RSUM,
@@ -296,43 +295,6 @@ PVE_DEV void pve_resolve_chain(const uint8_t *fbits, uint8_t *sel, int n, int32_
     (void)ws16;
     uint32_t st = 0;
     for (int k = 0; k < n; ++k) { st = ((uint32_t)fbits[k] >> st) & 1u; sel[k] = (uint8_t)st; }
-#endif
-}
-
-/* Row offsets of the NEXT tick's dense outputs: agent_offset[b] = sum of n_ctrl[0..b).  Run by the
- * team of the LAST CTA to finish (ticket counter), so a tick is a single kernel launch.  NTH threads
- * take contiguous chunks; warp shuffles scan the chunk sums. */
-template <int NTH, int NTOT>
-PVE_DEV void pve_last_cta_offset_scan(const PveState &S, int B, int32_t *wsum) {
-#ifdef __CUDACC__
-    const int tid = (int)threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    constexpr int NW = NTH / 32;
-    if (tid == 0) {
-        __threadfence();                                    /* this CTA's n_ctrl[b] is visible before the ticket */
-        const unsigned int ticket = atomicAdd(S.done, 1u);
-        wsum[34] = (ticket == (unsigned int)(B - 1)) ? 1 : 0;
-    }
-    pve_team_sync<NTH, NTOT>();
-    if (!wsum[34]) return;
-    __threadfence();
-    const int chunk = (B + NTH - 1) / NTH;
-    const int lo = min(B, tid * chunk), hi = min(B, lo + chunk);
-    int sum = 0;
-    for (int i = lo; i < hi; ++i) sum += __ldcg(S.n_ctrl + i);
-    int inc = sum;
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-        const int t = __shfl_up_sync(0xffffffffu, inc, d);
-        if (lane >= d) inc += t;
-    }
-    if (lane == 31) wsum[warp] = inc;
-    pve_team_sync<NTH, NTOT>();
-    int run = inc - sum;
-    for (int w = 0; w < NW; ++w) run += (w < warp) ? wsum[w] : 0;
-    for (int i = lo; i < hi; ++i) { S.agent_offset[i] = run; run += __ldcg(S.n_ctrl + i); }
-    if (tid == NTH - 1) { S.agent_offset[B] = run; *S.done = 0u; }
-#else
-    (void)S; (void)B; (void)wsum;       /* the emulation scans after its loop over the CTAs */
 #endif
 }
 
@@ -1062,10 +1024,6 @@ PVE_DEV void pve_step_block(const PveParams &P, const PveState &S, const pve_out
         if (tid < PVE_HDR_BYTES / 16) ((pve_v4 *)(S.hdr + b))[tid] = ((const pve_v4 *)hdr)[tid];
         if (tid == 0) {
             S.n_ctrl[b] = hdr->n_ctrl; S.n_veh[b] = hdr->n_veh;
-            if (O.agent_offset) {
-                O.agent_offset[b] = (int32_t)obase;
-                if (b == P.B - 1) O.agent_offset[P.B] = S.agent_offset[P.B];
-            }
             if (O.env_collisions) O.env_collisions[b] = misc[M_COLL];
             if (O.env_lock) O.env_lock[b] = misc[M_LOCK];
             if (O.env_removed) O.env_removed[b] = misc[M_NREM];
@@ -1104,7 +1062,6 @@ PVE_DEV void pve_step_block(const PveParams &P, const PveState &S, const pve_out
 #else
     pve_move_rows<NT>(RJ, 0, 1);
 #endif
-    pve_last_cta_offset_scan<NS, NT>(S, P.B, wsum);
 #if defined(PVE_PHASE_TIMING) && defined(__CUDACC__)
     if (threadIdx.x == 0 && S.stats) {      /* debug build: overwrite this intersection's stats rows with stamps */
         long long *dbg = (long long *)S.dbg + (size_t)b * 48;
