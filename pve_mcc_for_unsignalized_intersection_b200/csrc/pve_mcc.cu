@@ -44,10 +44,15 @@ struct pve_scene {
     int threads;
     size_t smem_bytes;
     int phase;
+    int rot;                     /* which of the three group-sum buffers holds this tick's counts */
+    int32_t *gsum;               /* [3][G] */
+    int n_groups;
+    int32_t *n_ctrl_buf[2];      /* ping-pong with `phase` */
     const int32_t *spawn_tick;   /* borrowed */
     float *actions_dev;          /* staging for pve_step_host */
     double *counters_dev;
-    int32_t *pinned_i32;         /* host-visible scratch: [0] next agent total */
+    int32_t *pinned_i32;         /* host-visible scratch */
+    int32_t *pinned_gs;          /* host copy of the group sums (next agent total) */
     int64_t next_total;          /* rows of the next tick if known, else -1 */
     int profiling;               /* record events around the step and scan kernels */
     size_t smem_pad;             /* experiment knob (env PVE_SMEM_PAD): extra dynamic shared memory per CTA */
@@ -109,36 +114,14 @@ pve_step_kernel(const PveParams P, const PveState S, const pve_outputs O, const 
     pve_step_block<NT, VC, AC>(P, S, O, spawn_tick, actions, phase, (int)blockIdx.x, pve_smem);
 }
 
-/* agent_offset[b] = sum of n_ctrl[0..b): rows of the dense per-agent outputs.  One CTA. */
-__global__ void __launch_bounds__(1024)
-pve_offset_scan_kernel(const int32_t *__restrict__ n_ctrl, int32_t *__restrict__ agent_offset, int B) {
-    __shared__ int wsum[32];
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int chunk = (B + 1023) / 1024;
-    const int lo = min(B, tid * chunk), hi = min(B, lo + chunk);
+/* group sums of n_ctrl after reset / set_state (during a rollout the step kernel maintains them) */
+__global__ void pve_gsum_kernel(const int32_t *__restrict__ n_ctrl, int32_t *__restrict__ gs_now,
+                                int32_t *__restrict__ gs_a, int32_t *__restrict__ gs_b, int B, int G) {
+    const int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= G) return;
     int s = 0;
-    for (int b = lo; b < hi; ++b) s += n_ctrl[b];
-    int inc = s;
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-        const int t = __shfl_up_sync(0xffffffffu, inc, d);
-        if (lane >= d) inc += t;
-    }
-    if (lane == 31) wsum[warp] = inc;
-    __syncthreads();
-    if (warp == 0) {
-        int w = wsum[lane];
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            const int t = __shfl_up_sync(0xffffffffu, w, d);
-            if (lane >= d) w += t;
-        }
-        wsum[lane] = w;
-    }
-    __syncthreads();
-    int run = inc - s + (warp > 0 ? wsum[warp - 1] : 0);
-    for (int b = lo; b < hi; ++b) { agent_offset[b] = run; run += n_ctrl[b]; }
-    if (tid == 1023) agent_offset[B] = wsum[31];
+    for (int i = g << PVE_GROUP_SHIFT; i < min(B, (g + 1) << PVE_GROUP_SHIFT); ++i) s += n_ctrl[i];
+    gs_now[g] = s; gs_a[g] = 0; gs_b[g] = 0;
 }
 
 __global__ void pve_reset_kernel(PveState S, const int32_t *__restrict__ spawn_tick, int B, int K, int warmup) {
@@ -209,10 +192,12 @@ pve_stats_kernel(PveState S, int B, double *out) {
 
 #else  /* ------------------------------- host emulation ------------------------------------ */
 
-static void emul_offset_scan(const int32_t *n_ctrl, int32_t *agent_offset, int B) {
-    int run = 0;
-    for (int b = 0; b < B; ++b) { agent_offset[b] = run; run += n_ctrl[b]; }
-    agent_offset[B] = run;
+static void emul_gsum(const int32_t *n_ctrl, int32_t *gs_now, int32_t *gs_a, int32_t *gs_b, int B, int G) {
+    for (int g = 0; g < G; ++g) {
+        int s = 0;
+        for (int i = g << PVE_GROUP_SHIFT; i < B && i < ((g + 1) << PVE_GROUP_SHIFT); ++i) s += n_ctrl[i];
+        gs_now[g] = s; gs_a[g] = 0; gs_b[g] = 0;
+    }
 }
 static void emul_reset(PveState S, const int32_t *spawn_tick, int B, int K, int warmup) {
     for (int b = 0; b < B; ++b) {
@@ -262,13 +247,27 @@ static void emul_stats(PveState S, int B, double *out) {
 /* =============================================================================================
  * launch helpers
  * =========================================================================================== */
-static int32_t launch_scan(pve_scene *s, pve_stream_t stream) {
+static void set_rotation(pve_scene *s) {
+    const int G = s->n_groups;
+    s->st.n_ctrl = s->n_ctrl_buf[s->phase];
+    s->st.n_ctrl_next = s->n_ctrl_buf[s->phase ^ 1];
+    s->st.gs_read = s->gsum + (size_t)(s->rot % 3) * G;
+    s->st.gs_acc = s->gsum + (size_t)((s->rot + 1) % 3) * G;
+    s->st.gs_zero = s->gsum + (size_t)((s->rot + 2) % 3) * G;
+}
+
+/* after reset / set_state: group sums from n_ctrl, rotation restarted */
+static int32_t launch_gsum(pve_scene *s, pve_stream_t stream) {
+    s->rot = 0;
+    set_rotation(s);
+    const int G = s->n_groups;
 #ifndef PVE_HOST_EMULATION
-    pve_offset_scan_kernel<<<1, 1024, 0, stream>>>(s->st.n_ctrl, s->st.agent_offset, s->cfg.n_envs);
+    pve_gsum_kernel<<<(G + 127) / 128, 128, 0, stream>>>(s->st.n_ctrl, s->gsum, s->gsum + G, s->gsum + 2 * (size_t)G,
+                                                          s->cfg.n_envs, G);
     RT_CHECK(s, cudaGetLastError());
 #else
     (void)stream;
-    emul_offset_scan(s->st.n_ctrl, s->st.agent_offset, s->cfg.n_envs);
+    emul_gsum(s->st.n_ctrl, s->gsum, s->gsum + G, s->gsum + 2 * (size_t)G, s->cfg.n_envs, G);
 #endif
     return PVE_OK;
 }
@@ -336,6 +335,8 @@ static int32_t launch_step(pve_scene *s, const float *actions, const pve_outputs
     if (!done) return PVE_EINVAL;
 #endif
     s->phase ^= 1;
+    s->rot = (s->rot + 1) % 3;
+    set_rotation(s);
     return PVE_OK;
 }
 
@@ -394,9 +395,9 @@ void pve_destroy(pve_scene *s) {
     if (!s) return;
     rt_free(s->st.hdr); rt_free(s->st.p); rt_free(s->st.v); rt_free(s->st.a); rt_free(s->st.js);
     rt_free(s->st.meta); rt_free(s->st.row0[0]); rt_free(s->st.row0[1]);
-    rt_free(s->st.n_ctrl); rt_free(s->st.n_veh); rt_free(s->st.stats); rt_free(s->st.agent_offset);
+    rt_free(s->n_ctrl_buf[0]); rt_free(s->n_ctrl_buf[1]); rt_free(s->st.n_veh); rt_free(s->st.stats); rt_free(s->gsum);
     rt_free(s->actions_dev); rt_free(s->counters_dev);
-    rt_host_free(s->pinned_i32);
+    rt_host_free(s->pinned_i32); rt_host_free(s->pinned_gs);
 #ifndef PVE_HOST_EMULATION
     for (int i = 0; i < 3; ++i) if (s->ev[i]) cudaEventDestroy(s->ev[i]);
 #endif
@@ -464,10 +465,14 @@ int32_t pve_create(const pve_config *cfg, int32_t device, pve_scene **out) {
     RT_CHECK(s, rt_alloc((void **)&s->st.meta, sizeof(pve_veh_meta) * nv));
     RT_CHECK(s, rt_alloc((void **)&s->st.row0[0], sizeof(float) * nv * PVE_OBS_W));
     RT_CHECK(s, rt_alloc((void **)&s->st.row0[1], sizeof(float) * nv * PVE_OBS_W));
-    RT_CHECK(s, rt_alloc((void **)&s->st.n_ctrl, sizeof(int32_t) * (size_t)B));
+    RT_CHECK(s, rt_alloc((void **)&s->n_ctrl_buf[0], sizeof(int32_t) * (size_t)B));
+    RT_CHECK(s, rt_alloc((void **)&s->n_ctrl_buf[1], sizeof(int32_t) * (size_t)B));
+    s->st.n_ctrl = s->n_ctrl_buf[0]; s->st.n_ctrl_next = s->n_ctrl_buf[1];
     RT_CHECK(s, rt_alloc((void **)&s->st.n_veh, sizeof(int32_t) * (size_t)B));
     RT_CHECK(s, rt_alloc((void **)&s->st.stats, sizeof(double) * (size_t)B * PVE_NSTAT));
-    RT_CHECK(s, rt_alloc((void **)&s->st.agent_offset, sizeof(int32_t) * ((size_t)B + 1)));
+    s->n_groups = (B + (1 << PVE_GROUP_SHIFT) - 1) >> PVE_GROUP_SHIFT;
+    RT_CHECK(s, rt_alloc((void **)&s->gsum, sizeof(int32_t) * 3 * (size_t)s->n_groups));
+    RT_CHECK(s, rt_host_alloc((void **)&s->pinned_gs, sizeof(int32_t) * (size_t)s->n_groups));
     RT_CHECK(s, rt_alloc((void **)&s->counters_dev, sizeof(double) * 16));
 #ifdef PVE_PHASE_TIMING
     RT_CHECK(s, rt_alloc((void **)&s->st.dbg, sizeof(long long) * 48 * (size_t)B));
@@ -484,6 +489,8 @@ int32_t pve_reset(pve_scene *s, const int32_t *spawn_tick_dev, int32_t K, int32_
     s->spawn_tick = spawn_tick_dev;
     s->prm.K = spawn_tick_dev ? K : 0;
     s->phase = 0;
+    s->rot = 0;
+    set_rotation(s);
     s->next_total = -1;
     RT_CHECK(s, rt_memset(s->st.p, 0, sizeof(double) * nv, stream));
     RT_CHECK(s, rt_memset(s->st.v, 0, sizeof(double) * nv, stream));
@@ -498,14 +505,12 @@ int32_t pve_reset(pve_scene *s, const int32_t *spawn_tick_dev, int32_t K, int32_
 #else
     emul_reset(s->st, s->spawn_tick, B, s->prm.K, warmup);
 #endif
-    int32_t rc = launch_scan(s, stream);
+    int32_t rc = launch_gsum(s, stream);
     if (rc != PVE_OK) return rc;
     if (warmup && spawn_tick_dev && K > 0) {
         /* the tick that brings the first vehicle(s) in: nothing to step, nothing to emit */
         if (!s->actions_dev) RT_CHECK(s, rt_alloc((void **)&s->actions_dev, sizeof(float) * nv));
         rc = launch_step(s, s->actions_dev, null_outputs(), stream);
-        if (rc != PVE_OK) return rc;
-        rc = launch_scan(s, stream);
     }
     return rc;
 }
@@ -514,14 +519,12 @@ int32_t pve_step(pve_scene *s, const float *actions_dev, const pve_outputs *out_
     if (!s || !actions_dev) return PVE_EINVAL;
     pve_stream_t stream = (pve_stream_t)stream_;
     const pve_outputs O = out_dev ? *out_dev : null_outputs();
-    if (O.agent_offset)
-        RT_CHECK(s, rt_copy(O.agent_offset, s->st.agent_offset, sizeof(int32_t) * ((size_t)s->cfg.n_envs + 1), stream));
+    /* one launch per tick: every CTA derives its first output row from the group sums */
     int32_t rc = launch_step(s, actions_dev, O, stream);
     if (rc != PVE_OK) return rc;
     s->next_total = -1;
-    rc = launch_scan(s, stream);          /* row offsets of the NEXT tick */
 #ifndef PVE_HOST_EMULATION
-    if (rc == PVE_OK && s->profiling) RT_CHECK(s, cudaEventRecord(s->ev[2], stream));
+    if (s->profiling) RT_CHECK(s, cudaEventRecord(s->ev[2], stream));
 #endif
     return rc;
 }
@@ -555,9 +558,11 @@ int64_t pve_next_agent_total(pve_scene *s, void *stream_) {
     if (!s) return PVE_EINVAL;
     pve_stream_t stream = (pve_stream_t)stream_;
     if (s->next_total < 0) {
-        RT_CHECK(s, rt_copy(s->pinned_i32, s->st.agent_offset + s->cfg.n_envs, sizeof(int32_t), stream));
+        RT_CHECK(s, rt_copy(s->pinned_gs, s->st.gs_read, sizeof(int32_t) * (size_t)s->n_groups, stream));
         RT_CHECK(s, rt_sync(stream));
-        s->next_total = s->pinned_i32[0];
+        int64_t t = 0;
+        for (int g = 0; g < s->n_groups; ++g) t += s->pinned_gs[g];
+        s->next_total = t;
     }
     return s->next_total;
 }
@@ -596,9 +601,11 @@ int32_t pve_step_host(pve_scene *s, const float *actions_host, const pve_outputs
         D2H(obs, sizeof(float) * PVE_OBS_H * PVE_OBS_W * a);
 #undef D2H
     }
-    RT_CHECK(s, rt_copy(s->pinned_i32, s->st.agent_offset + B, sizeof(int32_t), stream));
+    RT_CHECK(s, rt_copy(s->pinned_gs, s->st.gs_read, sizeof(int32_t) * (size_t)s->n_groups, stream));
     RT_CHECK(s, rt_sync(stream));
-    s->next_total = s->pinned_i32[0];
+    int64_t t = 0;
+    for (int g = 0; g < s->n_groups; ++g) t += s->pinned_gs[g];
+    s->next_total = t;
     return PVE_OK;
 }
 
@@ -621,7 +628,7 @@ int32_t pve_set_state(pve_scene *s, const pve_state_view *in, void *stream_) {
     emul_recount(s->st, s->spawn_tick, B, s->cfg.veh_cap, s->prm.K);
 #endif
     s->next_total = -1;
-    return launch_scan(s, stream);
+    return launch_gsum(s, stream);
 }
 
 int32_t pve_get_state(pve_scene *s, const pve_state_view *out, void *stream_) {

@@ -93,9 +93,15 @@ struct PveState {
     double *p, *v, *a, *js;
     pve_veh_meta *meta;
     float *row0[2];           /* ping-pong: [phase] is read, [phase ^ 1] is written */
-    int32_t *n_ctrl, *n_veh;  /* [B] copies of the header counts for the offset scan */
+    int32_t *n_ctrl, *n_veh;  /* [B] this tick's counts (read by every later CTA of the group) */
+    int32_t *n_ctrl_next;     /* [B] next tick's counts: separate buffer, CTAs finish in any order */
     double *stats;            /* [B][PVE_NSTAT] running per-intersection statistics */
-    int32_t *agent_offset;    /* [B+1] rows of this tick (written by the scan kernel) */
+    /* Row offsets of the dense outputs without a scan kernel: intersections are grouped by 128;
+     * gs_read[g] = agents of group g this tick.  A CTA's first row = sum of the earlier groups + the
+     * earlier members of its own group (n_ctrl, written last tick).  At its end every CTA adds its
+     * next-tick count to gs_acc; gs_zero is cleared for the tick after (three rotating buffers). */
+    const int32_t *gs_read;
+    int32_t *gs_acc, *gs_zero;
     void *dbg;                /* tools/phase_timing.py builds only: [B][48] cycle stamps */
 };
 
@@ -144,8 +150,8 @@ struct PveLayout {
     static constexpr uint32_t VL_BASE = LANE_OFF + 64;           /* int[16] */
     static constexpr uint32_t VL_CNT = VL_BASE + 64;             /* int[16] */
     static constexpr uint32_t MISC = VL_CNT + 64;                /* int[56] */
-    static constexpr uint32_t WSUM = MISC + 224;                 /* int[40] */
-    static constexpr uint32_t ACNT = WSUM + 160;                 /* u16[VC+2] */
+    static constexpr uint32_t WSUM = MISC + 224;                 /* int[48] */
+    static constexpr uint32_t ACNT = WSUM + 192;                 /* u16[VC+2] */
     static constexpr uint32_t SURV = ACNT + a16(2 * (VC + 2));
     static constexpr uint32_t VIDX = SURV + a16(2 * (VC + 2));
     static constexpr uint32_t ARANK = VIDX + 2 * AC;
@@ -295,6 +301,32 @@ PVE_DEV void pve_resolve_chain(const uint8_t *fbits, uint8_t *sel, int n, int32_
     (void)ws16;
     uint32_t st = 0;
     for (int k = 0; k < n; ++k) { st = ((uint32_t)fbits[k] >> st) & 1u; sel[k] = (uint8_t)st; }
+#endif
+}
+
+/* first output row of intersection b (see PveState::gs_read); result returned to every thread */
+#define PVE_GROUP_SHIFT 7
+template <int NT>
+PVE_DEV int pve_first_row(const PveState &S, int b, int32_t *ws) {
+#ifdef __CUDACC__
+    const int tid = (int)threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    int part = 0;
+    for (int i = tid; i < (b >> PVE_GROUP_SHIFT); i += NT) part += S.gs_read[i];
+    for (int i = ((b >> PVE_GROUP_SHIFT) << PVE_GROUP_SHIFT) + tid; i < b; i += NT) part += S.n_ctrl[i];
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) part += __shfl_xor_sync(0xffffffffu, part, d);
+    if (lane == 0) ws[warp] = part;
+    __syncthreads();
+    int tot = 0;
+#pragma unroll
+    for (int w = 0; w < NT / 32; ++w) tot += ws[w];
+    return tot;
+#else
+    (void)ws;
+    int tot = 0;
+    for (int i = 0; i < (b >> PVE_GROUP_SHIFT); ++i) tot += S.gs_read[i];
+    for (int i = ((b >> PVE_GROUP_SHIFT) << PVE_GROUP_SHIFT); i < b; ++i) tot += S.n_ctrl[i];
+    return tot;
 #endif
 }
 
@@ -471,12 +503,9 @@ PVE_DEV void pve_step_block(const PveParams &P, const PveState &S, const pve_out
             ((pve_v4 *)hdr)[tid] = ((const pve_v4 *)(S.hdr + b))[tid];
         for (int q = tid; q < M_COUNT; q += NT) misc[q] = 0;
         if (tid < 16) { vl_cnt[tid] = 0; headk[tid] = -1; }
-        if (tid == 32) {        /* row range of this intersection in the dense outputs */
-            const int64_t lo = (int64_t)S.agent_offset[b], hi = (int64_t)S.agent_offset[b + 1];
-            wsum[32] = (hi <= P.out_cap && hi - lo <= AC) ? 1 : 0;
-            wsum[33] = (int32_t)lo;
-        }
-    PVE_END_TID
+    PVE_END_TID_NOSYNC
+    /* row range of this intersection in the dense outputs (one internal barrier, which also publishes L0) */
+    const int64_t obase = (int64_t)pve_first_row<NT>(S, b, wsum + 34);
 
     /* ---- L1: lane offsets (every lane of warp 0 sums its own prefix) ----------------------- */
     PVE_FOR_TID(tid)
@@ -486,10 +515,12 @@ PVE_DEV void pve_step_block(const PveParams &P, const PveState &S, const pve_out
             lane_off[tid] = o;
             if (tid == PVE_NLANE) misc[M_V] = o;
         }
-        if (tid == 32) { misc[M_IDSEQ0] = hdr->id_seq; misc[M_OUTOK] = wsum[32]; }
+        if (tid == 32) {
+            misc[M_IDSEQ0] = hdr->id_seq;
+            misc[M_OUTOK] = (obase + hdr->n_ctrl <= P.out_cap && hdr->n_ctrl <= AC) ? 1 : 0;
+        }
     PVE_END_TID
     const int V = misc[M_V];
-    const int64_t obase = (int64_t)wsum[33];
     /* this intersection's block of the dense observation output (null: rows are not emitted) */
     pve_v4 *const oblk = (O.obs != nullptr && misc[M_OUTOK]) ? (pve_v4 *)O.obs + obase * (PVE_OBS_H * PVE_OBS_W / 4)
                                                              : nullptr;
@@ -1023,7 +1054,13 @@ PVE_DEV void pve_step_block(const PveParams &P, const PveState &S, const pve_out
     PVE_FOR_TEAM(tid)
         if (tid < PVE_HDR_BYTES / 16) ((pve_v4 *)(S.hdr + b))[tid] = ((const pve_v4 *)hdr)[tid];
         if (tid == 0) {
-            S.n_ctrl[b] = hdr->n_ctrl; S.n_veh[b] = hdr->n_veh;
+            S.n_ctrl_next[b] = hdr->n_ctrl; S.n_veh[b] = hdr->n_veh;
+            PVE_RED_ADD(&S.gs_acc[b >> PVE_GROUP_SHIFT], hdr->n_ctrl);         /* next tick's group sums */
+            if ((b & ((1 << PVE_GROUP_SHIFT) - 1)) == 0) S.gs_zero[b >> PVE_GROUP_SHIFT] = 0;
+            if (O.agent_offset) {
+                O.agent_offset[b] = (int32_t)obase;
+                if (b == P.B - 1) O.agent_offset[P.B] = (int32_t)obase + A;
+            }
             if (O.env_collisions) O.env_collisions[b] = misc[M_COLL];
             if (O.env_lock) O.env_lock[b] = misc[M_LOCK];
             if (O.env_removed) O.env_removed[b] = misc[M_NREM];
