@@ -719,11 +719,13 @@ PVE_DEV void pve_step_block(const PveParams &P, const PveState &S, const pve_out
             if (r == 0) { hdra[g] = -1; virdis[g] = 100.0; }
             else { hdra[g] = (int16_t)acnt[sidx[base + r - 1]]; virdis[g] = pe - spos[base + r - 1]; }
             /* Six nearest by |delta|, ties to the lower list index (stable sort, TIS:1389).  Only the six
-             * entries below and the six above the ego can qualify.  Instead of walking outwards (a
-             * serial chain of dependent loads) every candidate computes its position in the stable
-             * order by counting the candidates that precede it: below-side entries have lower list
-             * indices, so on equal |delta| they win against above-side ones, and among themselves the
-             * farther one (lower index) wins. */
+             * entries below and the six above the ego can qualify, and each side is already ordered by
+             * |delta|.  Instead of walking outwards (a serial chain of dependent loads) the 36
+             * comparisons "above j is strictly nearer than below i" give every candidate its position
+             * in the merged order: below i -> i + #{j nearer}, above j -> j + #{i not farther} (entries
+             * below have lower list indices, so they win ties against entries above).  Two entries
+             * BELOW the ego with exactly equal |delta| would have to come out farther-first; that rare
+             * case is detected and done with the reference's run-aware walk. */
             pve_v4 *const orow = (pve_v4 *)(row0 + (size_t)g * PVE_OBS_W);
             orow[0] = pve_pack4((float)pe, (float)sv[k], (float)sa[k], (float)d);        /* TIS:1336 */
             nn0[g] = 0xFFFFu;
@@ -737,11 +739,11 @@ PVE_DEV void pve_step_block(const PveParams &P, const PveState &S, const pve_out
                 dh[i] = (xh < n) ? fabs(spos[base + (xh < n ? xh : 0)] - pe) : INF;
             }
             int ncand = 0;
-            /* a run of equal |delta| that continues below the window puts farther (lower-index) entries
-             * first: resolve that rare case with the reference's own outward walk */
-            const bool edge_tie = (r - 1 - PVE_NNBR >= 0) && dl[PVE_NNBR - 1] != INF &&
-                                  fabs(spos[base + (r - 1 - PVE_NNBR >= 0 ? r - 1 - PVE_NNBR : 0)] - pe) == dl[PVE_NNBR - 1];
-            if (edge_tie) {
+            bool lo_tie = (r - 1 - PVE_NNBR >= 0) && dl[PVE_NNBR - 1] != INF &&
+                          fabs(spos[base + (r - 1 - PVE_NNBR >= 0 ? r - 1 - PVE_NNBR : 0)] - pe) == dl[PVE_NNBR - 1];
+#pragma unroll
+            for (int i = 0; i + 1 < PVE_NNBR; ++i) lo_tie = lo_tie || (dl[i] == dl[i + 1] && dl[i] != INF);
+            if (lo_tie) {
                 int lo = r - 1, hi = r + 1, run_cur = 0, run_end = -1;
                 double run_d = 0;
                 for (int q = 0; q < PVE_NNBR; ++q) {
@@ -764,33 +766,34 @@ PVE_DEV void pve_step_block(const PveParams &P, const PveState &S, const pve_out
                         ++ncand;
                     }
                 }
-            } else
+            } else {
+                int cl[PVE_NNBR], ch[PVE_NNBR];      /* merged positions */
 #pragma unroll
-            for (int side = 0; side < 2; ++side) {
+                for (int i = 0; i < PVE_NNBR; ++i) { cl[i] = i; ch[i] = i + PVE_NNBR; }
 #pragma unroll
-                for (int i = 0; i < PVE_NNBR; ++i) {
-                    const int x = side ? r + 1 + i : r - 1 - i;
-                    const bool ok = side ? (x < n) : (x >= 0);
-                    const double di = side ? dh[i] : dl[i];
-                    int rk = side ? i : 0;
+                for (int i = 0; i < PVE_NNBR; ++i)
 #pragma unroll
                     for (int j = 0; j < PVE_NNBR; ++j) {
-                        if (side) rk += (dl[j] <= di) ? 1 : 0;
-                        else {
-                            if (j != i) rk += (dl[j] < di || (dl[j] == di && j > i)) ? 1 : 0;
-                            rk += (dh[j] < di) ? 1 : 0;
+                        const int m = (dh[j] < dl[i]) ? 1 : 0;
+                        cl[i] += m; ch[j] -= m;
+                    }
+#pragma unroll
+                for (int side = 0; side < 2; ++side)
+#pragma unroll
+                    for (int i = 0; i < PVE_NNBR; ++i) {
+                        const int x = side ? r + 1 + i : r - 1 - i;
+                        const bool ok = side ? (x < n) : (x >= 0);
+                        const int rk = side ? ch[i] : cl[i];
+                        ncand += ok ? 1 : 0;
+                        if (ok && rk < PVE_NNBR) {
+                            const int kn = sidx[base + x];
+                            const double vd = spos[base + x];
+                            orow[rk + 1] = pve_pack4((float)vd, (float)sv[kn], (float)sa[kn], (float)lane_of[kn]);   /* TIS:1330 */
+                            /* Q3: neighbour already processed this tick -> its new row, else last tick's */
+                            srcc[g * 8 + rk + 1] = (kn < k) ? (uint16_t)acnt[kn] : (uint16_t)(PVE_SRC_PREV | kn);
+                            if (rk == 0) { nn0[g] = (uint16_t)kn; vd0s[g] = vd; }
                         }
                     }
-                    ncand += ok ? 1 : 0;
-                    if (ok && rk < PVE_NNBR) {
-                        const int kn = sidx[base + x];
-                        const double vd = spos[base + x];
-                        orow[rk + 1] = pve_pack4((float)vd, (float)sv[kn], (float)sa[kn], (float)lane_of[kn]);   /* TIS:1330 */
-                        /* Q3: neighbour already processed this tick -> its new row, else last tick's */
-                        srcc[g * 8 + rk + 1] = (kn < k) ? (uint16_t)acnt[kn] : (uint16_t)(PVE_SRC_PREV | kn);
-                        if (rk == 0) { nn0[g] = (uint16_t)kn; vd0s[g] = vd; }
-                    }
-                }
             }
 #pragma unroll
             for (int q = 0; q < PVE_NNBR; ++q)
