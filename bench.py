@@ -37,7 +37,7 @@ ENVS_PER_GPU = 4096
 DENSITY = 1000
 VM = 6
 PRIME_TICKS = 400          # untimed: fill the intersections to steady-state occupancy
-VEH_CAP, AGENT_CAP = 128, 96
+VEH_CAP, AGENT_CAP = 128, int(os.environ.get("PVE_BENCH_AGENT_CAP", "96"))
 BYTES_PER_VEH, BYTES_PER_AGENT = 68, 1028        # SURVEY.md 8(d) / BASELINE.md section 4
 
 

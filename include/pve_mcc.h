@@ -169,7 +169,7 @@ int32_t pve_kernel_ms(pve_scene *s, float *step_ms, float *scan_ms);
 int64_t pve_smem_bytes(const pve_scene *s);
 int32_t pve_threads(const pve_scene *s);
 /* capacities actually in use: the requested ones rounded up to a compiled capacity class
- * (128/96, 192/128, 384/320, 576/416); every [B][veh_cap] array uses pve_veh_cap() as its stride */
+ * (128/80, 128/96, 192/128, 384/320, 576/416); every [B][veh_cap] array uses pve_veh_cap() as its stride */
 int32_t pve_veh_cap(const pve_scene *s);
 int32_t pve_agent_cap(const pve_scene *s);
 int32_t pve_config_bytes(void);

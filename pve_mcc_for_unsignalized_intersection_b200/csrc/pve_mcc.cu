@@ -106,8 +106,11 @@ static void rt_host_free(void *p) { free(p); }
  * =========================================================================================== */
 #ifndef PVE_HOST_EMULATION
 
+/* register budget: as many CTAs per SM as the class's shared memory admits (8 for 128/80, 7 for
+ * 128/96), counted in 128-thread units */
 template <int NT, int VC, int AC>
-__global__ void __launch_bounds__(NT)
+__global__ void __launch_bounds__(NT, (((233472 / (PveLayout<VC, AC>::BYTES + 1024)) < 8 ? (233472 / (PveLayout<VC, AC>::BYTES + 1024)) : 8) * 128) / NT > 0
+                                          ? (((233472 / (PveLayout<VC, AC>::BYTES + 1024)) < 8 ? (233472 / (PveLayout<VC, AC>::BYTES + 1024)) : 8) * 128) / NT : 1)
 pve_step_kernel(const PveParams P, const PveState S, const pve_outputs O, const int32_t *spawn_tick,
                 const float *actions, const int phase) {
     extern __shared__ __align__(16) unsigned char pve_smem[];
@@ -273,7 +276,7 @@ static int32_t launch_gsum(pve_scene *s, pve_stream_t stream) {
 }
 
 /* capacity classes (compile-time shared-memory layouts): veh_cap / agent_cap are rounded up to one */
-#define PVE_CLASSES(X) X(128, 96) X(192, 128) X(384, 320) X(576, 416)
+#define PVE_CLASSES(X) X(128, 80) X(128, 96) X(192, 128) X(384, 320) X(576, 416)
 
 static bool pick_class(int veh_cap, int agent_cap, int *VC, int *AC, size_t *smem) {
 #define X(vc, ac) if (veh_cap <= vc && agent_cap <= ac) { *VC = vc; *AC = ac; *smem = PveLayout<vc, ac>::BYTES; return true; }
