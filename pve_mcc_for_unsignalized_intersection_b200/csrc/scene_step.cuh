@@ -307,12 +307,23 @@ PVE_DEV void pve_resolve_chain(const uint8_t *fbits, uint8_t *sel, int n, int32_
 /* first output row of intersection b (see PveState::gs_read); result returned to every thread */
 #define PVE_GROUP_SHIFT 7
 template <int NT>
-PVE_DEV int pve_first_row(const PveState &S, int b, int32_t *ws) {
+PVE_DEV int pve_first_row_part(const PveState &S, int b) {      /* this thread's share: loads issued early */
 #ifdef __CUDACC__
-    const int tid = (int)threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tid = (int)threadIdx.x;
     int part = 0;
     for (int i = tid; i < (b >> PVE_GROUP_SHIFT); i += NT) part += S.gs_read[i];
     for (int i = ((b >> PVE_GROUP_SHIFT) << PVE_GROUP_SHIFT) + tid; i < b; i += NT) part += S.n_ctrl[i];
+    return part;
+#else
+    (void)S; (void)b;
+    return 0;
+#endif
+}
+template <int NT>
+PVE_DEV int pve_first_row(const PveState &S, int b, int part, int32_t *ws) {
+#ifdef __CUDACC__
+    const int tid = (int)threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    (void)S; (void)b;
 #pragma unroll
     for (int d = 16; d > 0; d >>= 1) part += __shfl_xor_sync(0xffffffffu, part, d);
     if (lane == 0) ws[warp] = part;
@@ -322,7 +333,7 @@ PVE_DEV int pve_first_row(const PveState &S, int b, int32_t *ws) {
     for (int w = 0; w < NT / 32; ++w) tot += ws[w];
     return tot;
 #else
-    (void)ws;
+    (void)ws; (void)part;
     int tot = 0;
     for (int i = 0; i < (b >> PVE_GROUP_SHIFT); ++i) tot += S.gs_read[i];
     for (int i = ((b >> PVE_GROUP_SHIFT) << PVE_GROUP_SHIFT); i < b; ++i) tot += S.n_ctrl[i];
@@ -497,6 +508,8 @@ PVE_DEV void pve_step_block(const PveParams &P, const PveState &S, const pve_out
     if (threadIdx.x == 0) pve_stamp[pve_nstamp++] = clock64();
 #endif
 
+    const int row_part = pve_first_row_part<NT>(S, b);       /* loads in flight while the header arrives */
+
     /* ---- L0: header -> shared -------------------------------------------------------------- */
     PVE_FOR_TID(tid)
         if (tid < PVE_HDR_BYTES / 16)
@@ -505,7 +518,7 @@ PVE_DEV void pve_step_block(const PveParams &P, const PveState &S, const pve_out
         if (tid < 16) { vl_cnt[tid] = 0; headk[tid] = -1; }
     PVE_END_TID_NOSYNC
     /* row range of this intersection in the dense outputs (one internal barrier, which also publishes L0) */
-    const int64_t obase = (int64_t)pve_first_row<NT>(S, b, wsum + 34);
+    const int64_t obase = (int64_t)pve_first_row<NT>(S, b, row_part, wsum + 34);
 
     /* ---- L1: lane offsets (every lane of warp 0 sums its own prefix) ----------------------- */
     PVE_FOR_TID(tid)
@@ -719,13 +732,11 @@ PVE_DEV void pve_step_block(const PveParams &P, const PveState &S, const pve_out
             if (r == 0) { hdra[g] = -1; virdis[g] = 100.0; }
             else { hdra[g] = (int16_t)acnt[sidx[base + r - 1]]; virdis[g] = pe - spos[base + r - 1]; }
             /* Six nearest by |delta|, ties to the lower list index (stable sort, TIS:1389).  Only the six
-             * entries below and the six above the ego can qualify, and each side is already ordered by
-             * |delta|.  Instead of walking outwards (a serial chain of dependent loads) the 36
-             * comparisons "above j is strictly nearer than below i" give every candidate its position
-             * in the merged order: below i -> i + #{j nearer}, above j -> j + #{i not farther} (entries
-             * below have lower list indices, so they win ties against entries above).  Two entries
-             * BELOW the ego with exactly equal |delta| would have to come out farther-first; that rare
-             * case is detected and done with the reference's run-aware walk. */
+             * entries below and the six above the ego can qualify.  Instead of walking outwards (a
+             * serial chain of dependent loads) every candidate computes its position in the stable
+             * order by counting the candidates that precede it: below-side entries have lower list
+             * indices, so on equal |delta| they win against above-side ones, and among themselves the
+             * farther one (lower index) wins. */
             pve_v4 *const orow = (pve_v4 *)(row0 + (size_t)g * PVE_OBS_W);
             orow[0] = pve_pack4((float)pe, (float)sv[k], (float)sa[k], (float)d);        /* TIS:1336 */
             nn0[g] = 0xFFFFu;
@@ -739,11 +750,11 @@ PVE_DEV void pve_step_block(const PveParams &P, const PveState &S, const pve_out
                 dh[i] = (xh < n) ? fabs(spos[base + (xh < n ? xh : 0)] - pe) : INF;
             }
             int ncand = 0;
-            bool lo_tie = (r - 1 - PVE_NNBR >= 0) && dl[PVE_NNBR - 1] != INF &&
-                          fabs(spos[base + (r - 1 - PVE_NNBR >= 0 ? r - 1 - PVE_NNBR : 0)] - pe) == dl[PVE_NNBR - 1];
-#pragma unroll
-            for (int i = 0; i + 1 < PVE_NNBR; ++i) lo_tie = lo_tie || (dl[i] == dl[i + 1] && dl[i] != INF);
-            if (lo_tie) {
+            /* a run of equal |delta| that continues below the window puts farther (lower-index) entries
+             * first: resolve that rare case with the reference's own outward walk */
+            const bool edge_tie = (r - 1 - PVE_NNBR >= 0) && dl[PVE_NNBR - 1] != INF &&
+                                  fabs(spos[base + (r - 1 - PVE_NNBR >= 0 ? r - 1 - PVE_NNBR : 0)] - pe) == dl[PVE_NNBR - 1];
+            if (edge_tie) {
                 int lo = r - 1, hi = r + 1, run_cur = 0, run_end = -1;
                 double run_d = 0;
                 for (int q = 0; q < PVE_NNBR; ++q) {
@@ -766,34 +777,33 @@ PVE_DEV void pve_step_block(const PveParams &P, const PveState &S, const pve_out
                         ++ncand;
                     }
                 }
-            } else {
-                int cl[PVE_NNBR], ch[PVE_NNBR];      /* merged positions */
+            } else
 #pragma unroll
-                for (int i = 0; i < PVE_NNBR; ++i) { cl[i] = i; ch[i] = i + PVE_NNBR; }
+            for (int side = 0; side < 2; ++side) {
 #pragma unroll
-                for (int i = 0; i < PVE_NNBR; ++i)
+                for (int i = 0; i < PVE_NNBR; ++i) {
+                    const int x = side ? r + 1 + i : r - 1 - i;
+                    const bool ok = side ? (x < n) : (x >= 0);
+                    const double di = side ? dh[i] : dl[i];
+                    int rk = side ? i : 0;
 #pragma unroll
                     for (int j = 0; j < PVE_NNBR; ++j) {
-                        const int m = (dh[j] < dl[i]) ? 1 : 0;
-                        cl[i] += m; ch[j] -= m;
-                    }
-#pragma unroll
-                for (int side = 0; side < 2; ++side)
-#pragma unroll
-                    for (int i = 0; i < PVE_NNBR; ++i) {
-                        const int x = side ? r + 1 + i : r - 1 - i;
-                        const bool ok = side ? (x < n) : (x >= 0);
-                        const int rk = side ? ch[i] : cl[i];
-                        ncand += ok ? 1 : 0;
-                        if (ok && rk < PVE_NNBR) {
-                            const int kn = sidx[base + x];
-                            const double vd = spos[base + x];
-                            orow[rk + 1] = pve_pack4((float)vd, (float)sv[kn], (float)sa[kn], (float)lane_of[kn]);   /* TIS:1330 */
-                            /* Q3: neighbour already processed this tick -> its new row, else last tick's */
-                            srcc[g * 8 + rk + 1] = (kn < k) ? (uint16_t)acnt[kn] : (uint16_t)(PVE_SRC_PREV | kn);
-                            if (rk == 0) { nn0[g] = (uint16_t)kn; vd0s[g] = vd; }
+                        if (side) rk += (dl[j] <= di) ? 1 : 0;
+                        else {
+                            if (j != i) rk += (dl[j] < di || (dl[j] == di && j > i)) ? 1 : 0;
+                            rk += (dh[j] < di) ? 1 : 0;
                         }
                     }
+                    ncand += ok ? 1 : 0;
+                    if (ok && rk < PVE_NNBR) {
+                        const int kn = sidx[base + x];
+                        const double vd = spos[base + x];
+                        orow[rk + 1] = pve_pack4((float)vd, (float)sv[kn], (float)sa[kn], (float)lane_of[kn]);   /* TIS:1330 */
+                        /* Q3: neighbour already processed this tick -> its new row, else last tick's */
+                        srcc[g * 8 + rk + 1] = (kn < k) ? (uint16_t)acnt[kn] : (uint16_t)(PVE_SRC_PREV | kn);
+                        if (rk == 0) { nn0[g] = (uint16_t)kn; vd0s[g] = vd; }
+                    }
+                }
             }
 #pragma unroll
             for (int q = 0; q < PVE_NNBR; ++q)
