@@ -821,14 +821,10 @@ PVE_DEV void pve_step_block(const PveParams &P, const PveState &S, const pve_out
     PveRowJob RJ;
     RJ.A = A; RJ.srcc = srcc; RJ.rows_smem = row0; RJ.rows_prev = row0_prev_base; RJ.oblk = oblk;
 #ifdef __CUDACC__
-    const bool mover_half = NS < NT && (int)threadIdx.x >= NS;
-    if (mover_half) {
+    if (NS < NT && (int)threadIdx.x >= NS) {
         pve_move_rows<NT>(RJ, NS / 32, (NT - NS) / 32);
-        asm volatile("bar.sync 2, %0;" :: "n"(NT) : "memory");     /* the team has finished phase J */
+        return;
     }
-    if (!mover_half) {
-#else
-    {
 #endif
 
     /* ---- G2: two work items per agent: reward (TIS:293-320), world position (TIS:1250-1290) */
@@ -1018,23 +1014,21 @@ PVE_DEV void pve_step_block(const PveParams &P, const PveState &S, const pve_out
         }
     PVE_END_TEAM
 
-#ifdef __CUDACC__
-        if (NS < NT) { __threadfence_block(); asm volatile("bar.arrive 2, %0;" :: "n"(NT) : "memory"); }
-#endif
-    }   /* end of the team-only part */
-
-    /* ---- K: write the state back, compacted.  Split CTA: done by the upper half (it has finished the
-     *      observation rows) while the team goes on with the header and the small outputs ---------- */
-#ifdef __CUDACC__
-    const int kw_tid = (NS < NT) ? (int)threadIdx.x - NS : (int)threadIdx.x;
-    constexpr int KW = (NS < NT) ? NT - NS : NT;
-    if (NS == NT || mover_half) {
-        const int tid = kw_tid;
-#else
-    constexpr int KW = NS;
-    for (int tid = 0; tid < KW; ++tid) {
-#endif
-        for (int k = tid; k < V; k += KW)
+    /* ---- K: write the state back, compacted ------------------------------------------------ */
+    PVE_FOR_TEAM(tid)
+        if (tid == 0) hdr->tick += 1;
+        if (tid >= 32 && tid < 32 + PVE_NLANE) {
+            /* header fields other lanes were still reading in phase J */
+            const int i = tid - 32;
+            if (misc[M_SPAWN0 + i]) {
+                const int rec = (int)hdr->veh_rec[i] + 1;                        /* TIS:430 */
+                hdr->veh_rec[i] = (uint16_t)rec;
+                hdr->next_spawn[i] = (rec < P.K) ? spawn_tick[((size_t)b * P.K + rec) * PVE_NLANE + i]
+                                                 : PVE_NEVER;
+            }
+            hdr->lane_n[i] = (uint8_t)misc[M_NEWN0 + i];
+        }
+        for (int k = tid; k < V; k += NS)
             if (!del[k]) {
                 const size_t o = vbase + (size_t)((int)surv[k] + misc[M_SPREF0 + lane_of[k]]);
                 S.p[o] = sp[k]; S.v[o] = sv[k]; S.a[o] = sa[k]; S.js[o] = sjs[k];
@@ -1057,31 +1051,13 @@ PVE_DEV void pve_step_block(const PveParams &P, const PveState &S, const pve_out
             for (int q = 0; q < PVE_OBS_W / 4; ++q) ((pve_v4 *)(row0_next + (size_t)np * PVE_OBS_W))[q] = z;
         }
         /* stored row 0 of every surviving agent -> next tick's neighbour rows / actor input */
-        for (int it = tid; it < A * 8; it += KW) {
+        for (int it = tid; it < A * 8; it += NS) {
             const int g = it >> 3, q = it & 7;
             const int k = vidx[g];
             if (q < 7 && !del[k]) {
                 const int np = (int)surv[k] + misc[M_SPREF0 + lane_of[k]];
                 ((pve_v4 *)(row0_next + (size_t)np * PVE_OBS_W))[q] = ((const pve_v4 *)(row0 + (size_t)g * PVE_OBS_W))[q];
             }
-        }
-    }
-#ifdef __CUDACC__
-    if (mover_half) return;
-#endif
-
-    /* ---- K2: header fields other lanes were still reading in phase J ------------------------- */
-    PVE_FOR_TEAM(tid)
-        if (tid == 0) hdr->tick += 1;
-        if (tid >= 32 && tid < 32 + PVE_NLANE) {
-            const int i = tid - 32;
-            if (misc[M_SPAWN0 + i]) {
-                const int rec = (int)hdr->veh_rec[i] + 1;                        /* TIS:430 */
-                hdr->veh_rec[i] = (uint16_t)rec;
-                hdr->next_spawn[i] = (rec < P.K) ? spawn_tick[((size_t)b * P.K + rec) * PVE_NLANE + i]
-                                                 : PVE_NEVER;
-            }
-            hdr->lane_n[i] = (uint8_t)misc[M_NEWN0 + i];
         }
     PVE_END_TEAM
 
