@@ -315,7 +315,7 @@ def graft_arm(args, rank, world, local_rank):
                          "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                          "kernel": "pve_step_kernel", "kernel_ms_per_launch": my_kern_ms / K,
                          "algorithmic_bytes_per_launch": alg_bytes / K},
-            "gpu_launches": 2 * K,
+            "gpu_launches": K,      # one step kernel per tick inside the timed region of `value`
             "clocks": sampler.result(),
             "stats": {k: float(v) for k, v in zip(
                 ["agent_steps", "vehicle_steps", "env_steps", "spawned", "passed", "passed_step_total",

@@ -20,7 +20,7 @@ benchref)
 sweep)
   for th in 64 128 256; do timeout 600 python bench.py --threads $th --steps 60 --warmup 5 --no-cpu-baseline --no-e2e > $OUT/${TAG}_bench_t$th.json 2>> $OUT/${TAG}_sweep.err; cat $OUT/${TAG}_bench_t$th.json; done ;;
 launches)
-  timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -s 830 -c 40 --csv --log-file $OUT/${TAG}_launches.csv \
+  timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -s 430 -c 40 --csv --log-file $OUT/${TAG}_launches.csv \
       python bench.py --steps 30 --warmup 5 --no-cpu-baseline --no-e2e > $OUT/${TAG}_launches_run.log 2>&1; echo "ncu launches rc=$?"; tail -8 $OUT/${TAG}_launches.csv ;;
 full)
   timeout 1200 ncu --set full --clock-control none --import-source on -k regex:pve_step_kernel -s 415 -c 2 -f -o $OUT/${TAG}_prof \
