@@ -721,15 +721,16 @@ PVE_DEV void pve_step_block(const PveParams &P, const PveState &S, const pve_out
         }
     PVE_END_TID
 
-    /* ---- G1: vir_header, six neighbours, row 0, gather codes.  Two work items per agent (the entries
-     *      below / above it in its virtual lane), placed on different warps ---------------------- */
+    /* ---- G1: per agent: vir_header, six neighbours, row 0, gather codes -------------------- */
     PVE_FOR_TID(tid)
-        const int side = tid / (NT / 2);
-        for (int g = tid - side * (NT / 2); g < A; g += NT / 2) {
+        for (int g = tid; g < A; g += NT) {
             const int k = vidx[g];
             const int d = lane_of[k];
             const int base = vl_base[d], n = vl_cnt[d], r = arank[g];
             const double pe = spos[base + r];
+            /* vir_header / vir_dis, TIS:1349-1354 */
+            if (r == 0) { hdra[g] = -1; virdis[g] = 100.0; }
+            else { hdra[g] = (int16_t)acnt[sidx[base + r - 1]]; virdis[g] = pe - spos[base + r - 1]; }
             /* Six nearest by |delta|, ties to the lower list index (stable sort, TIS:1389).  Only the six
              * entries below and the six above the ego can qualify.  Instead of walking outwards (a
              * serial chain of dependent loads) every candidate computes its position in the stable
@@ -737,59 +738,48 @@ PVE_DEV void pve_step_block(const PveParams &P, const PveState &S, const pve_out
              * indices, so on equal |delta| they win against above-side ones, and among themselves the
              * farther one (lower index) wins. */
             pve_v4 *const orow = (pve_v4 *)(row0 + (size_t)g * PVE_OBS_W);
+            orow[0] = pve_pack4((float)pe, (float)sv[k], (float)sa[k], (float)d);        /* TIS:1336 */
+            nn0[g] = 0xFFFFu;
+            vd0s[g] = 0.0;
             const double INF = 1.0e300;
             double dl[PVE_NNBR], dh[PVE_NNBR];
-            int nlo = 0, nhi = 0;
 #pragma unroll
             for (int i = 0; i < PVE_NNBR; ++i) {
                 const int xl = r - 1 - i, xh = r + 1 + i;
                 dl[i] = (xl >= 0) ? fabs(spos[base + (xl >= 0 ? xl : 0)] - pe) : INF;
                 dh[i] = (xh < n) ? fabs(spos[base + (xh < n ? xh : 0)] - pe) : INF;
-                nlo += (xl >= 0) ? 1 : 0; nhi += (xh < n) ? 1 : 0;
             }
-            const int ncand = nlo + nhi;
+            int ncand = 0;
             /* a run of equal |delta| that continues below the window puts farther (lower-index) entries
-             * first: resolve that rare case with the reference's own outward walk (below-side item) */
+             * first: resolve that rare case with the reference's own outward walk */
             const bool edge_tie = (r - 1 - PVE_NNBR >= 0) && dl[PVE_NNBR - 1] != INF &&
                                   fabs(spos[base + (r - 1 - PVE_NNBR >= 0 ? r - 1 - PVE_NNBR : 0)] - pe) == dl[PVE_NNBR - 1];
-            if (side == 0) {
-                /* vir_header / vir_dis, TIS:1349-1354 */
-                if (r == 0) { hdra[g] = -1; virdis[g] = 100.0; }
-                else { hdra[g] = (int16_t)acnt[sidx[base + r - 1]]; virdis[g] = pe - spos[base + r - 1]; }
-                orow[0] = pve_pack4((float)pe, (float)sv[k], (float)sa[k], (float)d);    /* TIS:1336 */
-                if (ncand == 0) { nn0[g] = 0xFFFFu; vd0s[g] = 0.0; }
-#pragma unroll
-                for (int q = 0; q < PVE_NNBR; ++q)
-                    if (q >= ncand) {
-                        orow[q + 1] = pve_pack4(0.f, 0.f, 0.f, 0.f);             /* TIS:1334 */
-                        srcc[g * 8 + q + 1] = (uint16_t)AC;                      /* the zero row */
-                    }
-            }
             if (edge_tie) {
-                if (side == 0) {
-                    int lo = r - 1, hi = r + 1, run_cur = 0, run_end = -1;
-                    double run_d = 0;
-                    for (int q = 0; q < PVE_NNBR; ++q) {
-                        if (run_cur > run_end && lo >= 0) {
-                            run_end = lo; run_d = fabs(spos[base + lo] - pe);
-                            int x = lo;
-                            while (x - 1 >= 0 && fabs(spos[base + x - 1] - pe) == run_d) --x;
-                            run_cur = x; lo = x - 1;
-                        }
-                        const bool has_lo = run_cur <= run_end, has_hi = hi < n;
-                        int pick = -1;
-                        if (has_lo && (!has_hi || run_d <= fabs(spos[base + hi] - pe))) pick = run_cur++;
-                        else if (has_hi) pick = hi++;
-                        if (pick >= 0) {
-                            const int kn = sidx[base + pick];
-                            const double vd = spos[base + pick];
-                            orow[q + 1] = pve_pack4((float)vd, (float)sv[kn], (float)sa[kn], (float)lane_of[kn]);
-                            srcc[g * 8 + q + 1] = (kn < k) ? (uint16_t)acnt[kn] : (uint16_t)(PVE_SRC_PREV | kn);
-                            if (q == 0) { nn0[g] = (uint16_t)kn; vd0s[g] = vd; }
-                        }
+                int lo = r - 1, hi = r + 1, run_cur = 0, run_end = -1;
+                double run_d = 0;
+                for (int q = 0; q < PVE_NNBR; ++q) {
+                    if (run_cur > run_end && lo >= 0) {
+                        run_end = lo; run_d = fabs(spos[base + lo] - pe);
+                        int x = lo;
+                        while (x - 1 >= 0 && fabs(spos[base + x - 1] - pe) == run_d) --x;
+                        run_cur = x; lo = x - 1;
+                    }
+                    const bool has_lo = run_cur <= run_end, has_hi = hi < n;
+                    int pick = -1;
+                    if (has_lo && (!has_hi || run_d <= fabs(spos[base + hi] - pe))) pick = run_cur++;
+                    else if (has_hi) pick = hi++;
+                    if (pick >= 0) {
+                        const int kn = sidx[base + pick];
+                        const double vd = spos[base + pick];
+                        orow[q + 1] = pve_pack4((float)vd, (float)sv[kn], (float)sa[kn], (float)lane_of[kn]);
+                        srcc[g * 8 + q + 1] = (kn < k) ? (uint16_t)acnt[kn] : (uint16_t)(PVE_SRC_PREV | kn);
+                        if (q == 0) { nn0[g] = (uint16_t)kn; vd0s[g] = vd; }
+                        ++ncand;
                     }
                 }
-            } else {
+            } else
+#pragma unroll
+            for (int side = 0; side < 2; ++side) {
 #pragma unroll
                 for (int i = 0; i < PVE_NNBR; ++i) {
                     const int x = side ? r + 1 + i : r - 1 - i;
@@ -804,6 +794,7 @@ PVE_DEV void pve_step_block(const PveParams &P, const PveState &S, const pve_out
                             rk += (dh[j] < di) ? 1 : 0;
                         }
                     }
+                    ncand += ok ? 1 : 0;
                     if (ok && rk < PVE_NNBR) {
                         const int kn = sidx[base + x];
                         const double vd = spos[base + x];
@@ -814,6 +805,12 @@ PVE_DEV void pve_step_block(const PveParams &P, const PveState &S, const pve_out
                     }
                 }
             }
+#pragma unroll
+            for (int q = 0; q < PVE_NNBR; ++q)
+                if (q >= ncand) {
+                    orow[q + 1] = pve_pack4(0.f, 0.f, 0.f, 0.f);                 /* TIS:1334 */
+                    srcc[g * 8 + q + 1] = (uint16_t)AC;                          /* the zero row */
+                }
         }
         if (tid < PVE_OBS_W / 4) ((pve_v4 *)(row0 + (size_t)AC * PVE_OBS_W))[tid] = pve_pack4(0.f, 0.f, 0.f, 0.f);
     PVE_END_TID
