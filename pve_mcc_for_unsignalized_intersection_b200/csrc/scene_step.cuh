@@ -368,10 +368,8 @@ PVE_DEV void pve_warp0_sums(const float *x, const double *y, int n, double *out3
  * Row mover: the 7 x 28 observation of every agent.  Row 0 is the agent's own row, row q+1 is
  * neighbour q's stored row (Q3): this tick's row if that neighbour was processed earlier (shared
  * memory), else last tick's row (state buffer, prefetched to L2 in phase A), or zeros.
- * Device: every lane decodes one row (a 32-bit source code); the warp then moves four rows per
- * step, 8 lanes per 112-byte row (7 active, 16 bytes each), the codes handed around by shuffles,
- * with eight loads in flight per lane.  It runs on the warps that have no work in the agent phases,
- * concurrently with them (see the CTA split after phase G1).
+ * It runs on the warps that have no work in the agent phases, concurrently with them (see the CTA
+ * split after phase G1).
  * ------------------------------------------------------------------------------------------- */
 struct PveRowJob {
     int A;
@@ -379,6 +377,7 @@ struct PveRowJob {
     const float *rows_smem;       /* [AC + 1][28], row AC = zeros */
     const float *rows_prev;       /* last tick's stored rows of this intersection */
     pve_v4 *oblk;                 /* this intersection's observation block or null */
+    int zero_row;                 /* index of the all-zero row of rows_smem */
 };
 
 /* item it < 7A: observation row (it % 7) of agent (it / 7).  code: bit 31 = source is last tick's
@@ -395,26 +394,36 @@ PVE_DEV void pve_move_rows(const PveRowJob &J, int first_warp, int n_warps) {
     if (J.oblk == nullptr) return;
     const int n_items = J.A * 7;
 #ifdef __CUDACC__
-    const int tid = (int)threadIdx.x, lane = tid & 31, q = lane & 7, sub = lane >> 3;
+    /* 8 lanes per 112-byte row (7 active, one 16-byte piece each), 4 rows per warp and step.  A lane
+     * group walks its rows with incremental (agent, row) indices (no division, no shuffles); the row's
+     * source is read from shared memory unless its code says "last tick's buffer", in which case a
+     * predicated global load overrides it; four rows are in flight per lane. */
+    const int tid = (int)threadIdx.x, lane = tid & 31, q = lane & 7;
+    if (q == 7) return;
     const pve_v4 *PVE_RESTRICT prevq = (const pve_v4 *)J.rows_prev + q;
     const pve_v4 *rowsq = (const pve_v4 *)J.rows_smem + q;
     pve_v4 *PVE_RESTRICT dstq = J.oblk + q;
-    for (int chunk = ((tid >> 5) - first_warp) * 32; chunk < n_items; chunk += n_warps * 32) {
-        const uint32_t code = pve_row_code(J, chunk + lane);
-        pve_v4 val[8];
+    const int stride = 4 * n_warps;                       /* rows per step of the mover warps */
+    const int dg = stride / 7, dr = stride - dg * 7;
+    int it = ((tid >> 5) - first_warp) * 4 + (lane >> 3);
+    int g = it / 7, rw = it - g * 7;
+    const int zero7 = J.zero_row * 7;
+    for (; it < n_items; it += 4 * stride) {
+        pve_v4 val[4];
 #pragma unroll
-        for (int u = 0; u < 8; ++u) {           /* all eight loads of this lane are issued before any store */
-            const uint32_t cu = __shfl_sync(0xffffffffu, code, u * 4 + sub);
-            if (q < 7 && cu != 0xFFFFFFFFu) {
-                if (cu & 0x80000000u) val[u] = prevq[(cu & 0x7FFFu) * 7];
-                else val[u] = rowsq[cu * 7];
-            }
+        for (int u = 0; u < 4; ++u) {
+            const bool valid = it + u * stride < n_items;
+            const uint32_t code = valid ? (rw ? (uint32_t)J.srcc[g * 8 + rw] : (uint32_t)g) : (uint32_t)J.zero_row;
+            const bool is_prev = (code & PVE_SRC_PREV) != 0;
+            const int idx7 = (int)(code & 0x7FFFu) * 7;
+            val[u] = rowsq[is_prev ? zero7 : idx7];
+            if (is_prev) val[u] = prevq[idx7];
+            rw += dr; g += dg;
+            if (rw >= 7) { rw -= 7; g += 1; }
         }
 #pragma unroll
-        for (int u = 0; u < 8; ++u) {
-            const int it = chunk + u * 4 + sub;
-            if (q < 7 && it < n_items) dstq[it * 7] = val[u];
-        }
+        for (int u = 0; u < 4; ++u)
+            if (it + u * stride < n_items) dstq[(it + u * stride) * 7] = val[u];
     }
 #else
     (void)first_warp; (void)n_warps;
@@ -819,7 +828,7 @@ PVE_DEV void pve_step_block(const PveParams &P, const PveState &S, const pve_out
      *      final after G1) while the lower half ("team") finishes the tick ------------------------ */
     constexpr int NS = (NT >= 128) ? NT / 2 : NT;
     PveRowJob RJ;
-    RJ.A = A; RJ.srcc = srcc; RJ.rows_smem = row0; RJ.rows_prev = row0_prev_base; RJ.oblk = oblk;
+    RJ.A = A; RJ.srcc = srcc; RJ.rows_smem = row0; RJ.rows_prev = row0_prev_base; RJ.oblk = oblk; RJ.zero_row = AC;
 #ifdef __CUDACC__
     if (NS < NT && (int)threadIdx.x >= NS) {
         pve_move_rows<NT>(RJ, NS / 32, (NT - NS) / 32);
