@@ -103,6 +103,7 @@ struct PveState {
     const int32_t *gs_read;
     int32_t *gs_acc, *gs_zero;
     void *dbg;                /* tools/phase_timing.py builds only: [B][48] cycle stamps */
+    const int32_t *order;     /* CTA index -> intersection, busiest first (refreshed every few ticks), or null */
 };
 
 enum { PVE_STAT_AGENT = 0, PVE_STAT_VEH, PVE_STAT_COLL, PVE_STAT_LOCK, PVE_STAT_JERK, PVE_STAT_RSUM,
