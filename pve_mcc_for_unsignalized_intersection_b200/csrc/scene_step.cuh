@@ -177,8 +177,8 @@ struct PveLayout {
 };
 
 enum { M_V = 0, M_NREM, M_PASSED, M_COLL, M_LOCK, M_NCTRL, M_Q5U, M_PSTEP, M_COLLAG, M_OUTOK, M_IDSEQ0,
-       M_SPAWN0 /* 12 */, M_SPREF0 = M_SPAWN0 + 12 /* 13 */, M_NEWN0 = M_SPREF0 + 13 /* 12 */,
-       M_COUNT = M_NEWN0 + 12 };
+       M_SPAWN0 /* 12 */, M_SPREF0 = M_SPAWN0 + 12 /* 13 */, M_NEXT0 = M_SPREF0 + 13 /* 12 */,
+       M_COUNT = M_NEXT0 + 12 };
 static_assert(M_COUNT <= 56, "misc block");
 
 /* gather codes for observation rows 1..6 (phase M): bit 15 clear -> row `index` of the shared-memory
@@ -923,16 +923,37 @@ PVE_DEV void pve_step_block(const PveParams &P, const PveState &S, const pve_out
             fbits[k] = del[k] ? 0 : 1;                                           /* survivor flag */
             if (!del[k] && (fl & PVE_F_CONTROL)) PVE_ATOMIC_ADD(&misc[M_NCTRL], 1);
         }
+    PVE_END_TID_NOSYNC
+
+    /* ---- removal by stream compaction (TIS:435-444): survivors keep their order.  Every thread scans
+     *      the survivor flags it wrote itself; the scan's barrier also publishes phase H ----------- */
+    pve_block_excl_scan<NS, NT>(fbits, surv, V, wsum);
+    PVE_FOR_TEAM(tid)
+        (void)tid;
     PVE_END_TEAM
 
-    /* ---- I: deadlock scan (TIS:365-370 + 1469-1499); final rewards ------------------------- */
+    /* ---- I: deadlock scan (TIS:365-370 + 1469-1499); final rewards; per-agent outputs ------ */
     PVE_FOR_TEAM(tid)
+#ifndef __CUDACC__
+        if (tid < PVE_NLANE) misc[M_NEXT0 + tid] = hdr->next_spawn[tid];        /* serial stand-in for J's ballot */
+#endif
         for (int g = tid; g < A; g += NS) {
             const int k = vidx[g];
             /* reward[-1] overrides in processing order: a later -10 beats the agent's own +5 (Q5) */
             if (q5[g]) rew[g] = -10.f;                                           /* TIS:346 */
             else if (fin5[g]) rew[g] = 5.f;                                      /* TIS:357 */
             vd0s[g] = fin5[g] ? sjs[k] : 0.0;                                    /* TIS:358 (statistics) */
+            if (misc[M_OUTOK]) {                                                 /* the small per-agent outputs */
+                if (O.reward) O.reward[obase + g] = rew[g];
+                if (O.ids) {
+                    pve_v4 id; id.x = (uint32_t)b; id.y = lane_of[k];
+                    id.z = (uint32_t)(k - lane_off[lane_of[k]]); id.w = (uint32_t)suid[k];
+                    ((pve_v4 *)O.ids)[obase + g] = id;
+                }
+                if (O.cpv) O.cpv[obase + g] = cpv[g];
+                if (O.status) O.status[obase + g] = status[g];
+                if (O.jerk_sum) O.jerk_sum[obase + g] = (float)sjs[k];
+            }
             if (!((spk[k] >> 24) & PVE_F_CONTROL) || del[k]) continue;
             int t = g, len = 0;
 #pragma unroll
@@ -974,70 +995,69 @@ PVE_DEV void pve_step_block(const PveParams &P, const PveState &S, const pve_out
         }
     PVE_END_TEAM
 
-    /* ---- removal by stream compaction (TIS:435-444): survivors keep their order ----------- */
-    pve_block_excl_scan<NS, NT>(fbits, surv, V, wsum);
+    /* ---- J: arrivals (TIS:378-433) and header, one lane of warp 0 per traffic lane -------------- */
     PVE_FOR_TEAM(tid)
-        (void)tid;
-    PVE_END_TEAM
-
-    /* ---- J: arrivals (TIS:378-433) and header update, one thread per lane ------------------ */
-    PVE_FOR_TEAM(tid)
-        if (tid < PVE_NLANE) {
-            const int i = tid;
+        if (tid < 32) {
+            const int i = tid < PVE_NLANE ? tid : 0;
             const int tick = hdr->tick + 1;                                      /* TIS:223 */
-            /* head of the rebuilt virtual lane, read by next tick's step() (Q2) */
-            if (hdr->lane_n[i] > 0) {
-                const int kh = headk[i];
-                if (kh >= 0) {
-                    hdr->head_lane[i] = (int8_t)lane_of[kh];
-                    hdr->head_j[i] = (uint8_t)(kh - lane_off[lane_of[kh]]);
-                } else { hdr->head_lane[i] = -1; hdr->head_j[i] = 0; }
-            }
-            /* arrivals are granted in lane order while there is room (capacity is a sticky error) */
             const int total = surv[V], nctrl = misc[M_NCTRL];
             int room = VC - total;
             room = (AC - nctrl) < room ? (AC - nctrl) : room;
-            int before = 0, want = 0, surv_i = 0;
-            for (int q = 0; q <= i; ++q) {
-                const int sq = (int)surv[lane_off[q + 1]] - (int)surv[lane_off[q]];
-                const int wq = (tick >= hdr->next_spawn[q] && sq < 255) ? 1 : 0;  /* TIS:379 */
-                if (q < i) before += wq; else { want = wq; surv_i = sq; }
+            const int surv_i = (int)surv[lane_off[i + 1]] - (int)surv[lane_off[i]];
+            const int want = (tid < PVE_NLANE && tick >= hdr->next_spawn[i] && surv_i < 255) ? 1 : 0;   /* TIS:379 */
+            /* arrivals are granted in lane order while there is room (capacity is a sticky error) */
+#ifdef __CUDACC__
+            const unsigned wants = __ballot_sync(0xffffffffu, want);
+            const int before = __popc(wants & ((1u << tid) - 1u));
+            const int n_want = __popc(wants);
+#else
+            int before = 0, n_want = 0;
+            for (int q2 = 0; q2 < PVE_NLANE; ++q2) {
+                const int sq = (int)surv[lane_off[q2 + 1]] - (int)surv[lane_off[q2]];
+                const int wq = (tick >= misc[M_NEXT0 + q2] && sq < 255) ? 1 : 0;
+                if (q2 < i) before += wq;
+                n_want += wq;
             }
-            const int sp_i = (want && before < room) ? 1 : 0;
-            const int pref = before < room ? before : (room > 0 ? room : 0);
-            misc[M_SPAWN0 + i] = sp_i;
-            misc[M_SPREF0 + i] = pref;
-            misc[M_NEWN0 + i] = surv_i + sp_i;
-            if (tick >= hdr->next_spawn[i] && !sp_i) PVE_ATOMIC_ADD(&hdr->overflow, 1);
-            if (i == PVE_NLANE - 1) {
-                const int nsp = pref + sp_i;
-                misc[M_SPREF0 + PVE_NLANE] = nsp;
-                hdr->n_veh = total + nsp;
-                hdr->n_ctrl = nctrl + nsp;
-                hdr->id_seq += nsp;                                              /* TIS:433 */
+#endif
+            if (tid < PVE_NLANE) {
+                const int sp_i = (want && before < room) ? 1 : 0;
+                const int pref = before < room ? before : (room > 0 ? room : 0);
+                misc[M_SPAWN0 + i] = sp_i;
+                misc[M_SPREF0 + i] = pref;
+                if (want && !sp_i) PVE_ATOMIC_ADD(&hdr->overflow, 1);
+                /* head of the rebuilt virtual lane, read by next tick's step() (Q2) */
+                if (hdr->lane_n[i] > 0) {
+                    const int kh = headk[i];
+                    if (kh >= 0) {
+                        hdr->head_lane[i] = (int8_t)lane_of[kh];
+                        hdr->head_j[i] = (uint8_t)(kh - lane_off[lane_of[kh]]);
+                    } else { hdr->head_lane[i] = -1; hdr->head_j[i] = 0; }
+                }
+                if (sp_i) {
+                    const int rec = (int)hdr->veh_rec[i] + 1;                    /* TIS:430 */
+                    hdr->veh_rec[i] = (uint16_t)rec;
+                    hdr->next_spawn[i] = (rec < P.K) ? spawn_tick[((size_t)b * P.K + rec) * PVE_NLANE + i]
+                                                     : PVE_NEVER;
+                }
+                hdr->lane_n[i] = (uint8_t)(surv_i + sp_i);
+                if (i == PVE_NLANE - 1) {            /* last in serial order: nobody reads hdr->tick after it */
+                    const int granted = n_want < room ? n_want : (room > 0 ? room : 0);
+                    misc[M_SPREF0 + PVE_NLANE] = granted;
+                    hdr->n_veh = total + granted;
+                    hdr->n_ctrl = nctrl + granted;
+                    hdr->id_seq += granted;                                      /* TIS:433 */
+                    hdr->tick = tick;
+                    hdr->passed_veh += misc[M_PASSED];
+                    hdr->passed_step_total += misc[M_PSTEP];
+                    if (!misc[M_OUTOK]) PVE_ATOMIC_ADD(&hdr->overflow, 1);       /* output rows do not fit */
+                }
             }
-        }
-        if (tid == 32) {
-            hdr->passed_veh += misc[M_PASSED];
-            hdr->passed_step_total += misc[M_PSTEP];
-            if (!misc[M_OUTOK]) PVE_ATOMIC_ADD(&hdr->overflow, 1);    /* output rows do not fit: sticky flag */
         }
     PVE_END_TEAM
 
-    /* ---- K: write the state back, compacted ------------------------------------------------ */
+    /* ---- K: write the state back, compacted; header; statistics ---------------------------------- */
+    pve_warp0_sums<NT>(rew, vd0s, A, dsum);
     PVE_FOR_TEAM(tid)
-        if (tid == 0) hdr->tick += 1;
-        if (tid >= 32 && tid < 32 + PVE_NLANE) {
-            /* header fields other lanes were still reading in phase J */
-            const int i = tid - 32;
-            if (misc[M_SPAWN0 + i]) {
-                const int rec = (int)hdr->veh_rec[i] + 1;                        /* TIS:430 */
-                hdr->veh_rec[i] = (uint16_t)rec;
-                hdr->next_spawn[i] = (rec < P.K) ? spawn_tick[((size_t)b * P.K + rec) * PVE_NLANE + i]
-                                                 : PVE_NEVER;
-            }
-            hdr->lane_n[i] = (uint8_t)misc[M_NEWN0 + i];
-        }
         for (int k = tid; k < V; k += NS)
             if (!del[k]) {
                 const size_t o = vbase + (size_t)((int)surv[k] + misc[M_SPREF0 + lane_of[k]]);
@@ -1069,13 +1089,7 @@ PVE_DEV void pve_step_block(const PveParams &P, const PveState &S, const pve_out
                 ((pve_v4 *)(row0_next + (size_t)np * PVE_OBS_W))[q] = ((const pve_v4 *)(row0 + (size_t)g * PVE_OBS_W))[q];
             }
         }
-    PVE_END_TEAM
-
-    /* ---- M: outputs ------------------------------------------------------------------------ */
-    pve_warp0_sums<NT>(rew, vd0s, A, dsum);
-    const bool out_ok = misc[M_OUTOK] != 0;
-    PVE_FOR_TEAM(tid)
-        if (tid < PVE_HDR_BYTES / 16) ((pve_v4 *)(S.hdr + b))[tid] = ((const pve_v4 *)hdr)[tid];
+        if (tid >= 32 && tid < 32 + PVE_HDR_BYTES / 16) ((pve_v4 *)(S.hdr + b))[tid - 32] = ((const pve_v4 *)hdr)[tid - 32];
         if (tid == 0) {
             S.n_ctrl_next[b] = hdr->n_ctrl; S.n_veh[b] = hdr->n_veh;
             PVE_RED_ADD(&S.gs_acc[b >> PVE_GROUP_SHIFT], hdr->n_ctrl);         /* next tick's group sums */
@@ -1099,20 +1113,6 @@ PVE_DEV void pve_step_block(const PveParams &P, const PveState &S, const pve_out
             PVE_RED_ADD(&st[PVE_STAT_REMOVED], (double)misc[M_NREM]);
             PVE_RED_ADD(&st[PVE_STAT_STEPS], 1.0);
             PVE_RED_ADD(&st[PVE_STAT_Q5U], (double)misc[M_Q5U]);
-        }
-        if (out_ok) {
-            for (int g = tid; g < A; g += NS) {
-                const int k = vidx[g];
-                if (O.reward) O.reward[obase + g] = rew[g];
-                if (O.ids) {
-                    pve_v4 id; id.x = (uint32_t)b; id.y = lane_of[k];
-                    id.z = (uint32_t)(k - lane_off[lane_of[k]]); id.w = (uint32_t)suid[k];
-                    ((pve_v4 *)O.ids)[obase + g] = id;
-                }
-                if (O.cpv) O.cpv[obase + g] = cpv[g];
-                if (O.status) O.status[obase + g] = status[g];
-                if (O.jerk_sum) O.jerk_sum[obase + g] = (float)sjs[k];
-            }
         }
     PVE_END_TID_NOSYNC
 
