@@ -29,6 +29,7 @@
  * contains it.
  */
 #pragma once
+#include <stddef.h>
 #include <math.h>
 #include <stdint.h>
 #include <string.h>
@@ -519,55 +520,64 @@ PVE_DEV void pve_step_block(const PveParams &P, const PveState &S, const pve_out
 #endif
 
     const int row_part = pve_first_row_part<NT>(S, b);       /* loads in flight while the header arrives */
-
-    /* ---- L0: header -> shared -------------------------------------------------------------- */
-    PVE_FOR_TID(tid)
-        if (tid < PVE_HDR_BYTES / 16)
-            ((pve_v4 *)hdr)[tid] = ((const pve_v4 *)(S.hdr + b))[tid];
-        for (int q = tid; q < M_COUNT; q += NT) misc[q] = 0;
-        if (tid < 16) { vl_cnt[tid] = 0; headk[tid] = -1; }
-    PVE_END_TID_NOSYNC
-    /* row range of this intersection in the dense outputs (one internal barrier, which also publishes L0) */
-    const int64_t obase = (int64_t)pve_first_row<NT>(S, b, row_part, wsum + 34);
-
-    /* ---- L1: lane offsets (every lane of warp 0 sums its own prefix) ----------------------- */
-    PVE_FOR_TID(tid)
-        if (tid <= PVE_NLANE) {
-            int o = 0;
-            for (int i = 0; i < tid; ++i) o += hdr->lane_n[i];
-            lane_off[tid] = o;
-            if (tid == PVE_NLANE) misc[M_V] = o;
-        }
-        if (tid == 32) {
-            misc[M_IDSEQ0] = hdr->id_seq;
-            misc[M_OUTOK] = (obase + hdr->n_ctrl <= P.out_cap && hdr->n_ctrl <= AC) ? 1 : 0;
-        }
-    PVE_END_TID
-    const int V = misc[M_V];
-    /* this intersection's block of the dense observation output (null: rows are not emitted) */
-    pve_v4 *const oblk = (O.obs != nullptr && misc[M_OUTOK]) ? (pve_v4 *)O.obs + obase * (PVE_OBS_H * PVE_OBS_W / 4)
-                                                             : nullptr;
-
     const float *const row0_prev_base = (phase ? S.row0[1] : S.row0[0]) + vbase * PVE_OBS_W;
     float *const row0_next = (phase ? S.row0[0] : S.row0[1]) + vbase * PVE_OBS_W;
 
-    /* ---- A: load vehicles, both candidate next states (Q1) --------------------------------- */
+    /* ---- A: header -> shared; load vehicles, both candidate next states (Q1).  Nothing here waits
+     *         for another thread: every thread reads the 36 bytes of lane lengths and virtual-lane
+     *         heads straight from the header in global memory and finds its own (lane, j) in registers,
+     *         while the state of vehicle slot `tid` is already on its way (slots >= V are allocated,
+     *         their content is ignored) ------------------------------------------------------------ */
+    static_assert(offsetof(pve_env_header, lane_n) == 104 && offsetof(pve_env_header, head_lane) == 116
+                  && offsetof(pve_env_header, head_j) == 128 && PVE_NLANE == 12, "lane table bytes");
     PVE_FOR_TID(tid)
-        for (int k = tid; k < V; k += NT) {
-            const double p = S.p[vbase + k], v = S.v[vbase + k], a = S.a[vbase + k];
-            const double js = S.js[vbase + k];
-            const pve_veh_meta mt = S.meta[vbase + k];
-            const double act = (double)actions[vbase + k];
-            int i = 0;
+        const pve_v4 *const gh = (const pve_v4 *)(S.hdr + b);
+        uint32_t lw[12];                                     /* header bytes 96..143 */
+        { const pve_v4 t0 = gh[6], t1 = gh[7], t2 = gh[8];
+          lw[0] = t0.x; lw[1] = t0.y; lw[2] = t0.z; lw[3] = t0.w; lw[4] = t1.x; lw[5] = t1.y; lw[6] = t1.z;
+          lw[7] = t1.w; lw[8] = t2.x; lw[9] = t2.y; lw[10] = t2.z; lw[11] = t2.w; }
+#define PVE_LW_BYTE(off) ((lw[(off) >> 2] >> (((off) & 3) * 8)) & 0xFFu)
+        double p = 0, v = 0, a = 0, js = 0;
+        pve_veh_meta mt; mt.uid = 0; mt.packed = 0;
+        float actf = 0.f;
+        if (tid < VC) {
+            p = S.p[vbase + tid]; v = S.v[vbase + tid]; a = S.a[vbase + tid]; js = S.js[vbase + tid];
+            mt = S.meta[vbase + tid]; actf = actions[vbase + tid];
+        }
+        if (tid < PVE_HDR_BYTES / 16) ((pve_v4 *)hdr)[tid] = gh[tid];
+        for (int q = tid + 1; q < M_COUNT; q += NT) misc[q] = 0;                 /* misc[M_V] is written below */
+        if (tid < 16) { vl_cnt[tid] = 0; headk[tid] = -1; }
+        int V_ = 0;
 #pragma unroll
-            for (int q = 1; q < PVE_NLANE; ++q) i += (k >= lane_off[q]) ? 1 : 0;
-            const int j = k - lane_off[i];
+        for (int q = 0; q < PVE_NLANE; ++q) V_ += (int)PVE_LW_BYTE(8 + q);
+        if (tid == 0) {
+            int o = 0;
+#pragma unroll
+            for (int q = 0; q < PVE_NLANE; ++q) { lane_off[q] = o; o += (int)PVE_LW_BYTE(8 + q); }
+            lane_off[PVE_NLANE] = o;
+            misc[M_V] = o;
+        }
+        for (int k = tid; k < V_; k += NT) {
+            if (k != tid) {
+                p = S.p[vbase + k]; v = S.v[vbase + k]; a = S.a[vbase + k]; js = S.js[vbase + k];
+                mt = S.meta[vbase + k]; actf = actions[vbase + k];
+            }
+            const double act = (double)actf;
+            /* lane of slot k: the last lane whose first slot is <= k; and its virtual-lane head */
+            int i = 0, off_i = 0, o = 0;
+            int hl = (int)(int8_t)PVE_LW_BYTE(20), hj = (int)PVE_LW_BYTE(32);
+#pragma unroll
+            for (int q = 1; q < PVE_NLANE; ++q) {
+                o += (int)PVE_LW_BYTE(8 + q - 1);
+                if (k >= o) { i = q; off_i = o; hl = (int)(int8_t)PVE_LW_BYTE(20 + q); hj = (int)PVE_LW_BYTE(32 + q); }
+            }
+            const int j = k - off_i;
             const uint32_t fl = mt.packed >> 24;
             const bool ctrl = (fl & PVE_F_CONTROL) != 0;
             const int lock_a = (int)((fl >> 3) & 3u) - 1;
             double ta = fmin(P.aM, fmax(P.am, act));                             /* TIS:1502 */
             if ((fl & PVE_F_LOCK) && lock_a != 0 && p > 70.0) ta = a + (double)lock_a;   /* TIS:1503-1505 */
-            const bool forced = (hdr->head_lane[i] == i && (int)hdr->head_j[i] == j)      /* TIS:1517 */
+            const bool forced = (hl == i && hj == j)                             /* TIS:1517 */
                                 || (i % 3 == 2);                                /* TIS:1519 */
             const double ta0 = fmin(P.aM, fmax(P.am, forced ? P.aM : ta));       /* TIS:1521 */
             const double ta1 = forced ? P.aM : P.am;                             /* TIS:1516 */
@@ -581,7 +591,7 @@ PVE_DEV void pve_step_block(const PveParams &P, const PveState &S, const pve_out
             cv0[k] = v0n; cv1[k] = v1n;
             sp[k] = p; sv[k] = v; sa[k] = a; sjs[k] = js;
             suid[k] = mt.uid; spk[k] = mt.packed;
-            if (ctrl) {      /* its stored row will probably be gathered in phase M: start the HBM fetch now */
+            if (ctrl) {      /* its stored row will probably be gathered by the row mover: start the HBM fetch now */
                 const float *r = row0_prev_base + (size_t)k * PVE_OBS_W;
                 pve_prefetch_l2(r); pve_prefetch_l2(r + PVE_OBS_W - 1);
             }
@@ -590,7 +600,11 @@ PVE_DEV void pve_step_block(const PveParams &P, const PveState &S, const pve_out
             del[k] = forced ? 1 : 0;        /* borrowed until phase C */
             slock[k] = 0; slocka[k] = 0;
         }
-    PVE_END_TID
+#undef PVE_LW_BYTE
+    PVE_END_TID_NOSYNC
+    /* row range of this intersection in the dense outputs (one internal barrier, which also publishes A) */
+    const int64_t obase = (int64_t)pve_first_row<NT>(S, b, row_part, wsum + 34);
+    const int V = misc[M_V];
 
     /* ---- B: F_k(s) = "rear-end override fires on k if its leader took candidate s" -------- */
     PVE_FOR_TID(tid)
@@ -638,7 +652,10 @@ PVE_DEV void pve_step_block(const PveParams &P, const PveState &S, const pve_out
     PVE_END_TID_NOSYNC
 
     /* ---- agent numbering: controlled at step() time == gets outputs this tick ------------- */
-    const int A = pve_block_excl_scan<NT>(ctl0, acnt, V, wsum);
+    const int A = pve_block_excl_scan<NT>(ctl0, acnt, V, wsum);           /* == hdr->n_ctrl */
+    /* this intersection's block of the dense outputs (null: rows are not emitted) */
+    const bool out_ok = obase + A <= P.out_cap && A <= AC;
+    pve_v4 *const oblk = (O.obs != nullptr && out_ok) ? (pve_v4 *)O.obs + obase * (PVE_OBS_H * PVE_OBS_W / 4) : nullptr;
 
     /* ---- D: agent tables (each thread uses only the counts it wrote itself) ---------------- */
     PVE_FOR_TID(tid)
@@ -943,7 +960,7 @@ PVE_DEV void pve_step_block(const PveParams &P, const PveState &S, const pve_out
             if (q5[g]) rew[g] = -10.f;                                           /* TIS:346 */
             else if (fin5[g]) rew[g] = 5.f;                                      /* TIS:357 */
             vd0s[g] = fin5[g] ? sjs[k] : 0.0;                                    /* TIS:358 (statistics) */
-            if (misc[M_OUTOK]) {                                                 /* the small per-agent outputs */
+            if (out_ok) {                                                        /* the small per-agent outputs */
                 if (O.reward) O.reward[obase + g] = rew[g];
                 if (O.ids) {
                     pve_v4 id; id.x = (uint32_t)b; id.y = lane_of[k];
@@ -1045,11 +1062,12 @@ PVE_DEV void pve_step_block(const PveParams &P, const PveState &S, const pve_out
                     misc[M_SPREF0 + PVE_NLANE] = granted;
                     hdr->n_veh = total + granted;
                     hdr->n_ctrl = nctrl + granted;
+                    misc[M_IDSEQ0] = hdr->id_seq;
                     hdr->id_seq += granted;                                      /* TIS:433 */
                     hdr->tick = tick;
                     hdr->passed_veh += misc[M_PASSED];
                     hdr->passed_step_total += misc[M_PSTEP];
-                    if (!misc[M_OUTOK]) PVE_ATOMIC_ADD(&hdr->overflow, 1);       /* output rows do not fit */
+                    if (!out_ok) PVE_ATOMIC_ADD(&hdr->overflow, 1);              /* output rows do not fit */
                 }
             }
         }
