@@ -667,57 +667,74 @@ PVE_DEV void pve_step_block(const PveParams &P, const PveState &S, const pve_out
         for (int e = tid; e < (L::EC + 3) / 4; e += NT) ((uint32_t *)edir)[e] = 0xFFFFFFFFu;
     PVE_END_TID
 
-    /* ---- D2: capacity of each virtual lane: own agents + agents of the 4 conflicting lanes - */
+    /* ---- D2: capacity of each virtual lane: own agents + agents of the 4 conflicting lanes; the
+     *          bases are the exclusive prefix over the 12 lanes (lanes of warp 0) -------------- */
     PVE_FOR_TID(tid)
-        if (tid < PVE_NLANE) {
-            const int d = tid;
-            int o = 0;
-            if (hdr->lane_n[d] > 0) {                                            /* TIS:234 */
-                o = (int)acnt[lane_off[d + 1]] - (int)acnt[lane_off[d]];
-                if (d % 3 != 2) {
+        if (tid < 32) {
+#ifdef __CUDACC__
+            const int d0 = tid, d1 = tid + 1;
+#else
+            const int d0 = 0, d1 = (tid == 0) ? PVE_NLANE : 0;                   /* thread 0 walks all lanes */
+            int run = 0;
+#endif
+            for (int d = d0; d < d1; ++d) {
+                int o = 0;
+                if (d < PVE_NLANE && hdr->lane_n[d] > 0) {                       /* TIS:234 */
+                    o = (int)acnt[lane_off[d + 1]] - (int)acnt[lane_off[d]];
+                    if (d % 3 != 2) {
 #pragma unroll
-                    for (int q = 0; q < 4; ++q) {
-                        const int Lq = P.l2l[d][q];
-                        o += (int)acnt[lane_off[Lq + 1]] - (int)acnt[lane_off[Lq]];
+                        for (int q = 0; q < 4; ++q) {
+                            const int Lq = P.l2l[d][q];
+                            o += (int)acnt[lane_off[Lq + 1]] - (int)acnt[lane_off[Lq]];
+                        }
                     }
                 }
+#ifdef __CUDACC__
+                int incl = o;
+#pragma unroll
+                for (int sh = 1; sh < 16; sh <<= 1) {
+                    const int t = __shfl_up_sync(0xffffffffu, incl, sh);
+                    if (tid >= sh) incl += t;
+                }
+                if (d <= PVE_NLANE) vl_base[d] = incl - o;
+#else
+                vl_base[d] = run; run += o;
+                if (d == PVE_NLANE - 1) vl_base[PVE_NLANE] = run;
+#endif
             }
-            wsum[16 + d] = o;
-        }
-    PVE_END_TID
-    PVE_FOR_TID(tid)
-        if (tid <= PVE_NLANE) {
-            int o = 0;
-            for (int d = 0; d < tid; ++d) o += wsum[16 + d];
-            vl_base[tid] = o;
         }
     PVE_END_TID
 
     /* ---- E: virtual-lane membership: each agent offers itself to its own lane and to the four
-     *         lanes it conflicts with --------------------------------------------------------- */
+     *         lanes it conflicts with.  All slot reservations are issued before the first store so
+     *         that their latencies overlap ------------------------------------------------------- */
     PVE_FOR_TID(tid)
         for (int g = tid; g < A; g += NT) {
             const int k = vidx[g];
             const int Lk = lane_of[k];
             const double p = sp[k];
-            {
-                const int e = vl_base[Lk] + PVE_ATOMIC_ADD(&vl_cnt[Lk], 1);     /* TIS:242-249 */
-                epos[e] = p; eidx[e] = (uint16_t)k; edir[e] = (uint8_t)Lk;
-            }
-            if (Lk % 3 != 2) {
+            double pos[4];
+            int dir[4], slot[4];
+            const bool crossing = (Lk % 3 != 2);
 #pragma unroll
-                for (int s = 0; s < 4; ++s) {
-                    const int dd = P.rev_dir[Lk][s], q = P.rev_k[Lk][s];
-                    if (hdr->lane_n[dd] > 0) {                                   /* TIS:234, 259 */
-                        const int mv = dd % 3;
-                        const double delta = (p - P.vd_a1[mv][q]) + P.vd_a2[mv][q];      /* TIS:733-803 */
-                        if (delta > 0) {
-                            const int e = vl_base[dd] + PVE_ATOMIC_ADD(&vl_cnt[dd], 1);
-                            epos[e] = P.vd_b[mv][q] + delta; eidx[e] = (uint16_t)k; edir[e] = (uint8_t)dd;
-                        }
-                    }
-                }
+            for (int s = 0; s < 4; ++s) {
+                const int dd = P.rev_dir[Lk][s], q = P.rev_k[Lk][s];
+                const int mv = dd % 3;
+                const double delta = (p - P.vd_a1[mv][q]) + P.vd_a2[mv][q];      /* TIS:733-803 */
+                pos[s] = P.vd_b[mv][q] + delta;
+                dir[s] = (crossing && hdr->lane_n[dd] > 0 && delta > 0) ? dd : -1;       /* TIS:234, 259 */
             }
+            const int e0 = vl_base[Lk] + PVE_ATOMIC_ADD(&vl_cnt[Lk], 1);         /* TIS:242-249 */
+#pragma unroll
+            for (int s = 0; s < 4; ++s)
+                slot[s] = (dir[s] >= 0) ? PVE_ATOMIC_ADD(&vl_cnt[dir[s]], 1) : 0;
+            epos[e0] = p; eidx[e0] = (uint16_t)k; edir[e0] = (uint8_t)Lk;
+#pragma unroll
+            for (int s = 0; s < 4; ++s)
+                if (dir[s] >= 0) {
+                    const int e = vl_base[dir[s]] + slot[s];
+                    epos[e] = pos[s]; eidx[e] = (uint16_t)k; edir[e] = (uint8_t)dir[s];
+                }
         }
     PVE_END_TID
 
