@@ -182,9 +182,10 @@ enum { M_V = 0, M_NREM, M_PASSED, M_COLL, M_LOCK, M_NCTRL, M_Q5U, M_PSTEP, M_COL
        M_COUNT = M_NEXT0 + 12 };
 static_assert(M_COUNT <= 56, "misc block");
 
-/* gather codes for observation rows 1..6 (phase M): bit 15 clear -> row `index` of the shared-memory
- * row table (this tick's row 0 of agent `index`; index AC is the zero row of an absent neighbour,
- * TIS:1335), bit 15 set -> last tick's stored row of vehicle slot `index`. */
+/* gather codes of the 7 observation rows of an agent: the low 15 bits are the first 16-byte piece of
+ * the source row (7 pieces per row), bit 15 clear -> in the shared-memory row table (this tick's row 0
+ * of an agent; row AC is the zero row of an absent neighbour, TIS:1335), bit 15 set -> in last tick's
+ * stored rows of this intersection (indexed by vehicle slot). */
 #define PVE_SRC_PREV 0x8000u
 #define PVE_ROW_BYTES (PVE_OBS_W * 4)
 
@@ -375,64 +376,49 @@ PVE_DEV void pve_warp0_sums(const float *x, const double *y, int n, double *out3
  * ------------------------------------------------------------------------------------------- */
 struct PveRowJob {
     int A;
-    const uint16_t *srcc;
+    const uint16_t *srcc;         /* [A][7] gather codes, see PVE_SRC_PREV */
     const float *rows_smem;       /* [AC + 1][28], row AC = zeros */
     const float *rows_prev;       /* last tick's stored rows of this intersection */
     pve_v4 *oblk;                 /* this intersection's observation block or null */
     int zero_row;                 /* index of the all-zero row of rows_smem */
 };
 
-/* item it < 7A: observation row (it % 7) of agent (it / 7).  code: bit 31 = source is last tick's
- * buffer, low bits = row index there / in the shared-memory row table; 0xFFFFFFFF = nothing to do */
-PVE_DEV uint32_t pve_row_code(const PveRowJob &J, int it) {
-    if (it >= J.A * 7) return 0xFFFFFFFFu;
-    const int g = it / 7, rw = it - g * 7;
-    const uint32_t c = rw ? (uint32_t)J.srcc[g * 8 + rw] : (uint32_t)g;
-    return ((c & PVE_SRC_PREV) ? 0x80000000u : 0u) | (c & 0x7FFFu);
-}
-
 template <int NT>
 PVE_DEV void pve_move_rows(const PveRowJob &J, int first_warp, int n_warps) {
     if (J.oblk == nullptr) return;
-    const int n_items = J.A * 7;
 #ifdef __CUDACC__
-    /* 8 lanes per 112-byte row (7 active, one 16-byte piece each), 4 rows per warp and step.  A lane
-     * group walks its rows with incremental (agent, row) indices (no division, no shuffles); the row's
-     * source is read from shared memory unless its code says "last tick's buffer", in which case a
-     * predicated global load overrides it; four rows are in flight per lane. */
-    const int tid = (int)threadIdx.x, lane = tid & 31, q = lane & 7;
-    if (q == 7) return;
-    const pve_v4 *PVE_RESTRICT prevq = (const pve_v4 *)J.rows_prev + q;
-    const pve_v4 *rowsq = (const pve_v4 *)J.rows_smem + q;
-    pve_v4 *PVE_RESTRICT dstq = J.oblk + q;
-    const int stride = 4 * n_warps;                       /* rows per step of the mover warps */
-    const int dg = stride / 7, dr = stride - dg * 7;
-    int it = ((tid >> 5) - first_warp) * 4 + (lane >> 3);
-    int g = it / 7, rw = it - g * 7;
-    const int zero7 = J.zero_row * 7;
-    for (; it < n_items; it += 4 * stride) {
+    /* The block of an intersection is contiguous: 49 16-byte pieces per agent.  Lane l of a mover warp
+     * handles piece x = l (mod the movers' width), so a warp stores 512 contiguous bytes per step.
+     * piece x -> row x / 7 -> its gather code -> source piece; the source is read from shared memory
+     * unless the code says "last tick's buffer", in which case a predicated global load overrides it.
+     * Four pieces are in flight per lane. */
+    const int n_v4 = J.A * (PVE_OBS_H * PVE_OBS_W / 4);
+    const int step = 32 * n_warps;
+    const pve_v4 *PVE_RESTRICT prev = (const pve_v4 *)J.rows_prev;
+    const pve_v4 *rows = (const pve_v4 *)J.rows_smem;
+    pve_v4 *PVE_RESTRICT dst = J.oblk;
+    const uint32_t zero7 = (uint32_t)J.zero_row * 7u;
+    for (int x = (int)threadIdx.x - first_warp * 32; x < n_v4; x += 4 * step) {
         pve_v4 val[4];
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
-            const bool valid = it + u * stride < n_items;
-            const uint32_t code = valid ? (rw ? (uint32_t)J.srcc[g * 8 + rw] : (uint32_t)g) : (uint32_t)J.zero_row;
+            const int xu = x + u * step;
+            const uint32_t row = __umulhi((uint32_t)xu, 613566757u);             /* xu / 7 */
+            const uint32_t code = (xu < n_v4) ? (uint32_t)J.srcc[row] : zero7;
             const bool is_prev = (code & PVE_SRC_PREV) != 0;
-            const int idx7 = (int)(code & 0x7FFFu) * 7;
-            val[u] = rowsq[is_prev ? zero7 : idx7];
-            if (is_prev) val[u] = prevq[idx7];
-            rw += dr; g += dg;
-            if (rw >= 7) { rw -= 7; g += 1; }
+            const uint32_t src = (code & 0x7FFFu) + ((uint32_t)xu - row * 7u);
+            val[u] = rows[is_prev ? zero7 : src];
+            if (is_prev) val[u] = prev[src];
         }
 #pragma unroll
         for (int u = 0; u < 4; ++u)
-            if (it + u * stride < n_items) dstq[(it + u * stride) * 7] = val[u];
+            if (x + u * step < n_v4) dst[x + u * step] = val[u];
     }
 #else
     (void)first_warp; (void)n_warps;
-    for (int it = 0; it < n_items; ++it) {
-        const uint32_t c = pve_row_code(J, it);
-        const float *src = (c & 0x80000000u) ? J.rows_prev + (size_t)(c & 0x7FFFu) * PVE_OBS_W
-                                             : J.rows_smem + (size_t)c * PVE_OBS_W;
+    for (int it = 0; it < J.A * PVE_OBS_H; ++it) {
+        const uint32_t c = J.srcc[it];
+        const float *src = ((c & PVE_SRC_PREV) ? J.rows_prev : J.rows_smem) + (size_t)(c & 0x7FFFu) * 4;
         memcpy(J.oblk + (size_t)it * 7, src, PVE_OBS_W * sizeof(float));
     }
 #endif
@@ -783,6 +769,7 @@ PVE_DEV void pve_step_block(const PveParams &P, const PveState &S, const pve_out
              * farther one (lower index) wins. */
             pve_v4 *const orow = (pve_v4 *)(row0 + (size_t)g * PVE_OBS_W);
             orow[0] = pve_pack4((float)pe, (float)sv[k], (float)sa[k], (float)d);        /* TIS:1336 */
+            srcc[g * 7] = (uint16_t)(g * 7);
             nn0[g] = 0xFFFFu;
             vd0s[g] = 0.0;
             const double INF = 1.0e300;
@@ -816,7 +803,7 @@ PVE_DEV void pve_step_block(const PveParams &P, const PveState &S, const pve_out
                         const int kn = sidx[base + pick];
                         const double vd = spos[base + pick];
                         orow[q + 1] = pve_pack4((float)vd, (float)sv[kn], (float)sa[kn], (float)lane_of[kn]);
-                        srcc[g * 8 + q + 1] = (kn < k) ? (uint16_t)acnt[kn] : (uint16_t)(PVE_SRC_PREV | kn);
+                        srcc[g * 7 + q + 1] = (kn < k) ? (uint16_t)(acnt[kn] * 7) : (uint16_t)(PVE_SRC_PREV | (kn * 7));
                         if (q == 0) { nn0[g] = (uint16_t)kn; vd0s[g] = vd; }
                         ++ncand;
                     }
@@ -844,7 +831,7 @@ PVE_DEV void pve_step_block(const PveParams &P, const PveState &S, const pve_out
                         const double vd = spos[base + x];
                         orow[rk + 1] = pve_pack4((float)vd, (float)sv[kn], (float)sa[kn], (float)lane_of[kn]);   /* TIS:1330 */
                         /* Q3: neighbour already processed this tick -> its new row, else last tick's */
-                        srcc[g * 8 + rk + 1] = (kn < k) ? (uint16_t)acnt[kn] : (uint16_t)(PVE_SRC_PREV | kn);
+                        srcc[g * 7 + rk + 1] = (kn < k) ? (uint16_t)(acnt[kn] * 7) : (uint16_t)(PVE_SRC_PREV | (kn * 7));
                         if (rk == 0) { nn0[g] = (uint16_t)kn; vd0s[g] = vd; }
                     }
                 }
@@ -853,7 +840,7 @@ PVE_DEV void pve_step_block(const PveParams &P, const PveState &S, const pve_out
             for (int q = 0; q < PVE_NNBR; ++q)
                 if (q >= ncand) {
                     orow[q + 1] = pve_pack4(0.f, 0.f, 0.f, 0.f);                 /* TIS:1334 */
-                    srcc[g * 8 + q + 1] = (uint16_t)AC;                          /* the zero row */
+                    srcc[g * 7 + q + 1] = (uint16_t)(AC * 7);                    /* the zero row */
                 }
         }
         if (tid < PVE_OBS_W / 4) ((pve_v4 *)(row0 + (size_t)AC * PVE_OBS_W))[tid] = pve_pack4(0.f, 0.f, 0.f, 0.f);
