@@ -459,27 +459,6 @@ PVE_DEV void pve_world_xy(const PveParams &P, double p, int lane, double *x, dou
 }
 
 /* ---------------------------------------------------------------------------------------------
- * TIS:293-320: reward of one agent from its nearest neighbour (virtual distance vd0 of vehicle k0;
- * k0 < 0: none), its own speed and the jerk of this step
- * ------------------------------------------------------------------------------------------- */
-PVE_DEV float pve_reward(const PveParams &P, double p, double v, double jr, int k0, double vd0, double v_k0) {
-    double t_distance = 2, d_distance = 10;
-    if (k0 >= 0) {
-        d_distance = fabs(p - vd0);                                              /* TIS:300 */
-        if (d_distance != 0) t_distance = (p - vd0) / (v - v_k0 + 0.0001);       /* TIS:304 */
-    }
-    double r_ = 0;
-    if (0 < t_distance && t_distance < 4) r_ += 1 / tanh(t_distance * -0.25);    /* TIS:314 */
-    r_ -= jr * jr * (3.0 / 3600.0);                                              /* TIS:316 */
-    if (d_distance < 10) {
-        const double x = d_distance * 0.1, x2 = x * x;
-        r_ += log(x2 * x2 * x + 0.00001);                                        /* TIS:318 */
-    }
-    r_ += (v - P.vm) * (2.0 / P.aspan);                                          /* TIS:319 */
-    return (float)fmin(20.0, fmax(-20.0, r_));                                   /* TIS:320 */
-}
-
-/* ---------------------------------------------------------------------------------------------
  * one tick of intersection b
  * ------------------------------------------------------------------------------------------- */
 template <int NT, int VC, int AC>
@@ -871,34 +850,24 @@ PVE_DEV void pve_step_block(const PveParams &P, const PveState &S, const pve_out
         if (tid < PVE_OBS_W / 4) ((pve_v4 *)(row0 + (size_t)AC * PVE_OBS_W))[tid] = pve_pack4(0.f, 0.f, 0.f, 0.f);
     PVE_END_TID
 
-    /* ---- CTA split: the upper half of the CTA computes the rewards and then moves the observation
-     *      rows (everything they need is final after G1) while the lower half ("team") finishes the
-     *      tick; the team picks the rewards up at barrier 2, before phase I ----------------------- */
+    /* ---- CTA split: the upper half of the CTA moves the observation rows (everything they need is
+     *      final after G1) while the lower half ("team") finishes the tick ------------------------ */
     constexpr int NS = (NT >= 128) ? NT / 2 : NT;
     PveRowJob RJ;
     RJ.A = A; RJ.srcc = srcc; RJ.rows_smem = row0; RJ.rows_prev = row0_prev_base; RJ.oblk = oblk; RJ.zero_row = AC;
 #ifdef __CUDACC__
-    constexpr bool SPLIT = NS < NT;
-    if (SPLIT && (int)threadIdx.x >= NS) {
-        for (int g = (int)threadIdx.x - NS; g < A; g += NT - NS) {
-            const int k = vidx[g], k0 = nn0[g] == 0xFFFFu ? -1 : (int)nn0[g];
-            rew[g] = pve_reward(P, sp[k], sv[k], sjr[k], k0, vd0s[g], sv[k0 < 0 ? k : k0]);
-        }
-        asm volatile("bar.arrive 2, %0;" :: "n"(NT) : "memory");
+    if (NS < NT && (int)threadIdx.x >= NS) {
         pve_move_rows<NT>(RJ, NS / 32, (NT - NS) / 32);
 #ifdef PVE_PHASE_TIMING
         if ((int)threadIdx.x == NS && S.stats) ((long long *)S.dbg)[(size_t)b * 48 + 47] = clock64();
 #endif
         return;
     }
-#else
-    constexpr bool SPLIT = false;
 #endif
 
-    /* ---- G2: world position of every agent (TIS:1250-1290); and the rewards when the CTA is not split:
-     *          then the two item kinds start on warp boundaries --------------------------------- */
+    /* ---- G2: two work items per agent: reward (TIS:293-320), world position (TIS:1250-1290) */
     PVE_FOR_TEAM(tid)
-        const int A32 = SPLIT ? 0 : ((A + 31) & ~31);
+        const int A32 = (A + 31) & ~31;         /* the two item kinds start on warp boundaries */
         for (int it = tid; it < A32 + A; it += NS) {
             const bool is_xy = it >= A32;
             const int g = is_xy ? it - A32 : it;
@@ -909,8 +878,24 @@ PVE_DEV void pve_step_block(const PveParams &P, const PveState &S, const pve_out
                 pve_world_xy(P, sp[k], lane_of[k], &x, &y);
                 xy[2 * g] = x; xy[2 * g + 1] = y;
             } else {
-                const int k0 = nn0[g] == 0xFFFFu ? -1 : (int)nn0[g];
-                rew[g] = pve_reward(P, sp[k], sv[k], sjr[k], k0, vd0s[g], sv[k0 < 0 ? k : k0]);
+                const double p = sp[k], v = sv[k];
+                const int k0 = nn0[g];
+                double t_distance = 2, d_distance = 10;
+                if (k0 != 0xFFFF) {
+                    const double vd0 = vd0s[g];
+                    d_distance = fabs(p - vd0);                                  /* TIS:300 */
+                    if (d_distance != 0) t_distance = (p - vd0) / (v - sv[k0] + 0.0001);  /* TIS:304 */
+                }
+                double r_ = 0;
+                if (0 < t_distance && t_distance < 4) r_ += 1 / tanh(t_distance * -0.25);   /* TIS:314 */
+                const double jr = sjr[k];
+                r_ -= jr * jr * (3.0 / 3600.0);                                  /* TIS:316 */
+                if (d_distance < 10) {
+                    const double x = d_distance * 0.1, x2 = x * x;
+                    r_ += log(x2 * x2 * x + 0.00001);                            /* TIS:318 */
+                }
+                r_ += (v - P.vm) * (2.0 / P.aspan);                              /* TIS:319 */
+                rew[g] = (float)fmin(20.0, fmax(-20.0, r_));                     /* TIS:320 */
             }
         }
     PVE_END_TEAM
@@ -976,9 +961,6 @@ PVE_DEV void pve_step_block(const PveParams &P, const PveState &S, const pve_out
     PVE_END_TEAM
 
     /* ---- I: deadlock scan (TIS:365-370 + 1469-1499); final rewards; per-agent outputs ------ */
-#ifdef __CUDACC__
-    if (SPLIT) asm volatile("bar.sync 2, %0;" :: "n"(NT) : "memory");           /* rewards of the upper half */
-#endif
     PVE_FOR_TEAM(tid)
 #ifndef __CUDACC__
         if (tid < PVE_NLANE) misc[M_NEXT0 + tid] = hdr->next_spawn[tid];        /* serial stand-in for J's ballot */
