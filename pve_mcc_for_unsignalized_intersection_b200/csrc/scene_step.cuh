@@ -309,24 +309,27 @@ PVE_DEV void pve_resolve_chain(const uint8_t *fbits, uint8_t *sel, int n, int32_
 
 /* first output row of intersection b (see PveState::gs_read); result returned to every thread */
 #define PVE_GROUP_SHIFT 7
+struct PveRowPart { int g, n; };
 template <int NT>
-PVE_DEV int pve_first_row_part(const PveState &S, int b) {      /* this thread's share: loads issued early */
+PVE_DEV PveRowPart pve_first_row_part(const PveState &S, int b) {      /* this thread's share: loads issued early, */
+    PveRowPart r; r.g = 0; r.n = 0;                                     /* nothing consumed before pve_first_row    */
 #ifdef __CUDACC__
     const int tid = (int)threadIdx.x;
-    int part = 0;
-    for (int i = tid; i < (b >> PVE_GROUP_SHIFT); i += NT) part += S.gs_read[i];
-    for (int i = ((b >> PVE_GROUP_SHIFT) << PVE_GROUP_SHIFT) + tid; i < b; i += NT) part += S.n_ctrl[i];
-    return part;
+    const int i0 = (b >> PVE_GROUP_SHIFT) << PVE_GROUP_SHIFT;
+    if (tid < (b >> PVE_GROUP_SHIFT)) r.g = S.gs_read[tid];
+    if (i0 + tid < b) r.n = S.n_ctrl[i0 + tid];
 #else
     (void)S; (void)b;
-    return 0;
 #endif
+    return r;
 }
 template <int NT>
-PVE_DEV int pve_first_row(const PveState &S, int b, int part, int32_t *ws) {
+PVE_DEV int pve_first_row(const PveState &S, int b, PveRowPart rp, int32_t *ws) {
 #ifdef __CUDACC__
     const int tid = (int)threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    (void)S; (void)b;
+    int part = rp.g + rp.n;
+    for (int i = tid + NT; i < (b >> PVE_GROUP_SHIFT); i += NT) part += S.gs_read[i];          /* B > 128 * NT only */
+    for (int i = ((b >> PVE_GROUP_SHIFT) << PVE_GROUP_SHIFT) + tid + NT; i < b; i += NT) part += S.n_ctrl[i];
 #pragma unroll
     for (int d = 16; d > 0; d >>= 1) part += __shfl_xor_sync(0xffffffffu, part, d);
     if (lane == 0) ws[warp] = part;
@@ -336,7 +339,7 @@ PVE_DEV int pve_first_row(const PveState &S, int b, int part, int32_t *ws) {
     for (int w = 0; w < NT / 32; ++w) tot += ws[w];
     return tot;
 #else
-    (void)ws; (void)part;
+    (void)ws; (void)rp;
     int tot = 0;
     for (int i = 0; i < (b >> PVE_GROUP_SHIFT); ++i) tot += S.gs_read[i];
     for (int i = ((b >> PVE_GROUP_SHIFT) << PVE_GROUP_SHIFT); i < b; ++i) tot += S.n_ctrl[i];
@@ -509,7 +512,7 @@ PVE_DEV void pve_step_block(const PveParams &P, const PveState &S, const pve_out
     }
 #endif
 
-    const int row_part = pve_first_row_part<NT>(S, b);       /* loads in flight while the header arrives */
+    const PveRowPart row_part = pve_first_row_part<NT>(S, b);       /* loads in flight while the header arrives */
     const float *const row0_prev_base = (phase ? S.row0[1] : S.row0[0]) + vbase * PVE_OBS_W;
     float *const row0_next = (phase ? S.row0[0] : S.row0[1]) + vbase * PVE_OBS_W;
 
