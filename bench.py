@@ -37,11 +37,13 @@ ENVS_PER_GPU = 4096
 DENSITY = 1000
 VM = 6
 PRIME_TICKS = 400          # untimed: fill the intersections to steady-state occupancy
-# Capacity class of the run.  128/80 admits 8 CTAs per SM (128/96: 7).  At this workload the largest
-# agent count seen in 4096 intersections x 800 ticks is 75 (oracle run); should
-# an intersection ever need more, the kernel defers the arrival and counts it in `overflow`, and the
+# Capacity class of the run: 128 vehicle slots / 96 agents per intersection (7 CTAs per SM).  At this
+# workload the largest agent count seen in 4096 intersections x 800 ticks is 75 (oracle run, DESIGN.md
+# section 6).  The tighter 128/80 class (8 CTAs per SM, PVE_BENCH_AGENT_CAP=80) measures ~2% slower: its
+# 64-register budget costs more than the extra resident CTA brings.  Should an intersection ever need
+# more agents than the class holds, the kernel defers the arrival and counts it in `overflow`, and the
 # benchmark then repeats itself with the 128/96 class instead of reporting a flagged run.
-VEH_CAP, AGENT_CAP = 128, int(os.environ.get("PVE_BENCH_AGENT_CAP", "80"))
+VEH_CAP, AGENT_CAP = 128, int(os.environ.get("PVE_BENCH_AGENT_CAP", "96"))
 BYTES_PER_VEH, BYTES_PER_AGENT = 68, 1028        # SURVEY.md 8(d) / BASELINE.md section 4
 
 
