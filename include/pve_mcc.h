@@ -174,6 +174,24 @@ int32_t pve_veh_cap(const pve_scene *s);
 int32_t pve_agent_cap(const pve_scene *s);
 int32_t pve_config_bytes(void);
 
+/* ---- batched actor inference ---------------------------------------------
+ * Replaces agent.action(state=[veh["state"][0]], sess) of main.py:44/404/563 for every controlled
+ * vehicle at once (model_agent_maddpg.py:23-49: LN28 -> Dense64 -> LN -> ReLU -> Dense64 -> LN ->
+ * ReLU -> Dense1 -> 3 tanh, fp32).  `weights_host`: PVE_ACTOR_FLOATS floats in this order:
+ *   LayerNorm gamma[28], beta[28]; dense kernel[28][64], bias[64]; LayerNorm_1 gamma[64], beta[64];
+ *   dense_1 kernel[64][64], bias[64]; LayerNorm_2 gamma[64], beta[64]; dense_2 kernel[64], bias[1]. */
+#define PVE_ACTOR_FLOATS 6393
+typedef struct pve_actor pve_actor;
+int32_t pve_actor_create(const float *weights_host, int32_t n_floats, int32_t device, pve_actor **out);
+void pve_actor_destroy(pve_actor *a);
+/* actions_dev[i] = actor(rows_dev[i][0..27]) for a dense matrix of n_rows observation rows */
+int32_t pve_actor_forward(pve_actor *a, const float *rows_dev, int64_t n_rows, float *actions_dev, void *stream);
+/* the action tensor of the next pve_step: actions_dev[b][k] = actor(stored row 0 of slot k) for the
+ * controlled vehicles of intersection b, 0 elsewhere (main.py:398-404); optional exploration noise
+ * `+ noise_scale * noise_dev[b][k]` (main.py:44; noise_dev may be null) */
+int32_t pve_act(pve_scene *s, pve_actor *a, const float *noise_dev, float noise_scale, float *actions_dev,
+                void *stream);
+
 #ifdef __cplusplus
 }
 #endif

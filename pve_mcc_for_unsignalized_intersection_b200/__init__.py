@@ -6,6 +6,9 @@ Public surface:
                           ``get_state`` / ``set_state`` / ``stats``.
 * ``TrafficInteraction`` -- B = 1 view with the reference's members (``veh_info``, ``step``,
                           ``scene_update``, ``delete_vehicle`` ...) so a main.py-style loop runs unchanged.
+* ``BatchedActor`` / ``ActorWeights`` -- the reference's actor network evaluated for every controlled
+                          vehicle at once (``actor.act(scene)`` -> the next ``scene.step`` input); weights read
+                          from the reference's TF checkpoint without TensorFlow (``checkpoint``).
 * ``SceneConfig``      -- the constructor scalars of the reference scene.
 * ``arrivals``         -- arrival tables: synthetic generator, conversion to integer spawn ticks.
 
@@ -21,6 +24,9 @@ def __getattr__(name):
     if name in ("BatchedScene", "StepOutputs"):
         from . import scene
         return getattr(scene, name)
+    if name in ("BatchedActor", "ActorWeights"):
+        from . import actor
+        return getattr(actor, name)
     if name == "TrafficInteraction":
         from .reference_api import TrafficInteraction
         return TrafficInteraction

@@ -78,6 +78,11 @@ def load_library(path=None):
     lib.pve_stats.argtypes = [vp, vp, vp]
     lib.pve_set_profiling.argtypes = [vp, i32]
     lib.pve_kernel_ms.argtypes = [vp, C.POINTER(C.c_float), C.POINTER(C.c_float)]
+    lib.pve_actor_create.argtypes = [vp, i32, i32, C.POINTER(vp)]
+    lib.pve_actor_destroy.argtypes = [vp]
+    lib.pve_actor_destroy.restype = None
+    lib.pve_actor_forward.argtypes = [vp, vp, i64, vp, vp]
+    lib.pve_act.argtypes = [vp, vp, vp, C.c_float, vp, vp]
     if lib.pve_config_bytes() != C.sizeof(PveConfig):
         raise NativeError("pve_config layout mismatch: library %d bytes, binding %d bytes"
                           % (lib.pve_config_bytes(), C.sizeof(PveConfig)))

@@ -18,6 +18,7 @@
 #include <new>
 
 #include "scene_step.cuh"
+#include "actor.cuh"
 
 #ifndef PVE_HOST_EMULATION
 #include <cuda_runtime.h>
@@ -709,6 +710,80 @@ int32_t pve_stats(pve_scene *s, pve_counters *out_dev, void *stream_) {
 #endif
     RT_CHECK(s, rt_copy(out_dev, s->counters_dev, sizeof(double) * 16, stream));
     return PVE_OK;
+}
+
+/* ---- actor (N1) ---------------------------------------------------------------------------- */
+struct pve_actor {
+    float *w_dev;
+    int device;
+    int blocks;
+};
+
+int32_t pve_actor_create(const float *weights_host, int32_t n_floats, int32_t device, pve_actor **out) {
+    if (!weights_host || !out || n_floats != PVE_ACTOR_FLOATS) return PVE_EINVAL;
+#ifdef PVE_HOST_EMULATION
+    (void)device;
+    return PVE_ESTATE;                       /* device only */
+#else
+    if (cudaSetDevice(device) != cudaSuccess) return PVE_ECUDA;
+    pve_actor *a = (pve_actor *)calloc(1, sizeof(pve_actor));
+    if (!a) return PVE_ENOMEM;
+    a->device = device;
+    int sms = 0;
+    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device) != cudaSuccess || sms <= 0) sms = 148;
+    a->blocks = 2 * sms;                     /* __launch_bounds__(128, 2): one resident wave, warps loop */
+    if (cudaMalloc((void **)&a->w_dev, sizeof(float) * PVE_ACTOR_FLOATS) != cudaSuccess) { free(a); return PVE_ENOMEM; }
+    if (cudaMemcpy(a->w_dev, weights_host, sizeof(float) * PVE_ACTOR_FLOATS, cudaMemcpyHostToDevice) != cudaSuccess) {
+        cudaFree(a->w_dev); free(a); return PVE_ECUDA;
+    }
+    *out = a;
+    return PVE_OK;
+#endif
+}
+
+void pve_actor_destroy(pve_actor *a) {
+    if (!a) return;
+#ifndef PVE_HOST_EMULATION
+    cudaFree(a->w_dev);
+#endif
+    free(a);
+}
+
+int32_t pve_actor_forward(pve_actor *a, const float *rows_dev, int64_t n_rows, float *actions_dev, void *stream_) {
+    if (!a || !rows_dev || !actions_dev || n_rows < 0) return PVE_EINVAL;
+#ifdef PVE_HOST_EMULATION
+    (void)stream_;
+    return PVE_ESTATE;
+#else
+    if (n_rows == 0) return PVE_OK;
+    const int n_env = (int)((n_rows + 31) / 32);             /* groups of 32 rows, one warp each */
+    const int blocks = (n_env + PVA_WARPS - 1) / PVA_WARPS < a->blocks ? (n_env + PVA_WARPS - 1) / PVA_WARPS : a->blocks;
+    pve_actor_kernel<<<blocks, PVA_WARPS * 32, 0, (pve_stream_t)stream_>>>(a->w_dev, rows_dev, nullptr, nullptr, nullptr, 0.f,
+                                                                        actions_dev, n_env, 32, (long long)n_rows);
+    return cudaGetLastError() == cudaSuccess ? PVE_OK : PVE_ECUDA;
+#endif
+}
+
+int32_t pve_act(pve_scene *s, pve_actor *a, const float *noise_dev, float noise_scale, float *actions_dev,
+                void *stream_) {
+    if (!s || !a || !actions_dev) return PVE_EINVAL;
+#ifdef PVE_HOST_EMULATION
+    (void)noise_dev; (void)noise_scale; (void)stream_;
+    snprintf(s->err, sizeof(s->err), "pve_act: the actor kernel exists on the device only");
+    return PVE_ESTATE;
+#else
+    if (a->device != s->device) {
+        snprintf(s->err, sizeof(s->err), "pve_act: actor lives on device %d, scene on %d", a->device, s->device);
+        return PVE_EINVAL;
+    }
+    const int B = s->cfg.n_envs, VCc = s->prm.VC;
+    const int blocks = (B + PVA_WARPS - 1) / PVA_WARPS < a->blocks ? (B + PVA_WARPS - 1) / PVA_WARPS : a->blocks;
+    pve_actor_kernel<<<blocks, PVA_WARPS * 32, 0, (pve_stream_t)stream_>>>(
+        a->w_dev, pve_row0_dev(s), s->st.meta, s->st.n_veh, noise_dev, noise_scale, actions_dev, B, VCc,
+        (long long)B * (long long)VCc);
+    RT_CHECK(s, cudaGetLastError());
+    return PVE_OK;
+#endif
 }
 
 }  /* extern "C" */
