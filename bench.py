@@ -56,7 +56,9 @@ def parse():
     ap.add_argument("--envs", type=int, default=ENVS_PER_GPU, help="intersections per GPU")
     ap.add_argument("--density", type=int, default=DENSITY)
     ap.add_argument("--threads", type=int, default=0, help="CTA size override (64/128/256)")
-    ap.add_argument("--workload", default="poisson", choices=["poisson", "stress"])
+    ap.add_argument("--workload", default="poisson", choices=["poisson", "stress", "rollout"],
+                    help="poisson: BASELINE config 2 (default); stress: config 4; rollout: config 5 = the pretrained "
+                         "actor evaluated on the GPU every tick + the environment step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     return ap.parse_args()
@@ -65,6 +67,10 @@ def parse():
 def workload_name(args):
     if args.workload == "stress":
         return "stress: headway 1.0 s on all 12 lanes, all-brake policy, %d intersections per GPU" % args.envs
+    if args.workload == "rollout":
+        return ("full rollout: %d intersections per GPU, synthetic Poisson arrivals %d veh/h/lane, actions from the "
+                "reference's pretrained actor evaluated on the GPU every tick (tests/golden/actor_agent1.npz), vm=5"
+                % (args.envs, args.density))
     return ("%d intersections per GPU, synthetic Poisson arrivals %d veh/h/lane, actions U(-3,3), vm=%d"
             % (args.envs, args.density, VM))
 
@@ -189,9 +195,15 @@ def graft_arm(args, rank, world, local_rank):
     veh_cap, agent_cap = (384, 320) if stress else (VEH_CAP, AGENT_CAP)
     horizon = (PRIME_TICKS + 3 * (K + W) + 50) * 0.1 + 30.0
     tabs = make_tables(args, B, 1000 + rank, horizon)
-    scene = BatchedScene(B, SceneConfig(vm=5 if stress else VM), veh_cap=veh_cap, agent_cap=agent_cap,
+    rollout = args.workload == "rollout"
+    scene = BatchedScene(B, SceneConfig(vm=5 if (stress or rollout) else VM), veh_cap=veh_cap, agent_cap=agent_cap,
                          device=dev, threads=args.threads)
     scene.reset(tabs, warmup=True)
+    actor = None
+    if rollout:
+        from pve_mcc_for_unsignalized_intersection_b200.actor import ActorWeights, BatchedActor
+        actor = BatchedActor(ActorWeights.from_npz(os.path.join(ROOT, "tests", "golden", "actor_agent1.npz")), device=dev)
+        act_buf = torch.empty(B, veh_cap, dtype=torch.float32, device=dev)
     gen = torch.Generator(device=dev)
     gen.manual_seed(99 + rank)
     if stress:
@@ -200,8 +212,14 @@ def graft_arm(args, rank, world, local_rank):
         pool = [(torch.rand(B, veh_cap, device=dev, generator=gen) * 6.0 - 3.0).contiguous() for _ in range(16)]
     flush = torch.empty(384 * 1024 * 1024, dtype=torch.uint8, device=dev)     # > 126 MB L2
 
+    def actions(t):
+        """The step's input: a pre-generated random tensor, or (rollout) the policy evaluated now."""
+        if actor is not None:
+            return actor.act(scene, out=act_buf)
+        return pool[t % len(pool)]
+
     for t in range(PRIME_TICKS):
-        scene.step(pool[t % len(pool)])
+        scene.step(actions(t))
     torch.cuda.synchronize()
 
     def barrier():
@@ -216,7 +234,7 @@ def graft_arm(args, rank, world, local_rank):
     # around the step kernel (pve_set_profiling -> roofline.achieved).
     for t in range(W):
         flush.fill_(t & 0xFF)
-        scene.step(pool[t % len(pool)])
+        scene.step(actions(t))
     s0 = scene.stats()
     sampler = ClockSampler(local_rank)
     sampler.start()
@@ -226,7 +244,7 @@ def graft_arm(args, rank, world, local_rank):
     for t in range(K):                         # the K timed ticks -> value
         flush.fill_(t & 0xFF)                  # L2 flush between timed iterations (not timed)
         ev[t][0].record()
-        scene.step(pool[t % len(pool)])
+        scene.step(actions(t))
         ev[t][1].record()
     barrier()
     wall1 = time.perf_counter()
@@ -238,10 +256,20 @@ def graft_arm(args, rank, world, local_rank):
     # K more ticks with the library's own events directly around the step kernel -> roofline
     scene.set_profiling(True)
     kern_ms = []
+    actor_ms = []
+    aev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
     for t in range(K):
         flush.fill_(t & 0xFF)
-        scene.step(pool[(K + t) % len(pool)])
+        if actor is not None:                  # the policy kernel of this tick, timed on its own
+            aev[0].record()
+            a = actions(K + t)
+            aev[1].record()
+            scene.step(a)
+        else:
+            scene.step(actions(K + t))
         kern_ms.append(scene.kernel_ms()[0])   # waits for this tick's kernel
+        if actor is not None:
+            actor_ms.append(aev[0].elapsed_time(aev[1]))
     scene.set_profiling(False)
     sampler.stop_flag = True
     s2 = scene.stats()
@@ -251,7 +279,7 @@ def graft_arm(args, rank, world, local_rank):
 
     # ---------------- end-to-end through host buffers ----------------
     e2e = None
-    if not args.no_e2e:
+    if not args.no_e2e and actor is None:
         host = scene.make_host_outputs()
         hact = [p.cpu().pin_memory() for p in pool[:4]]
         for t in range(max(3, W)):
@@ -317,7 +345,8 @@ def graft_arm(args, rank, world, local_rank):
                          "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                          "kernel": "pve_step_kernel", "kernel_ms_per_launch": my_kern_ms / K,
                          "algorithmic_bytes_per_launch": alg_bytes / K},
-            "gpu_launches": K,      # one step kernel per tick inside the timed region of `value`
+            # kernels inside the timed region of `value`: one step kernel per tick (+ one actor kernel in a rollout)
+            "gpu_launches": K * (2 if actor is not None else 1),
             "clocks": sampler.result(),
             "stats": {k: float(v) for k, v in zip(
                 ["agent_steps", "vehicle_steps", "env_steps", "spawned", "passed", "passed_step_total",
@@ -325,12 +354,19 @@ def graft_arm(args, rank, world, local_rank):
                  "removed", "overflow"], counters.tolist())},
             "wall_s_timed_region": wall1 - wall0,
         }
+        if actor is not None:
+            # 2 * (28*64 + 64*64 + 64) multiply-adds per agent; bytes: 112 B row in, 4 B action out, 8 B meta per slot
+            line["actor"] = {"kernel": "pve_actor_kernel", "kernel_ms_per_launch": float(sum(actor_ms)) / K,
+                             "gflop_per_launch": 2 * 5952 * kA / K / 1e9,
+                             "tflops": 2 * 5952 * kA / (float(sum(actor_ms)) * 1e-3) / 1e12,
+                             "note": "fp32 FFMA (the reference's graph is fp32 and ill-conditioned at 1e-4); "
+                                     "timed alone, inside the same ticks as roofline"}
         if e2e:
             line["e2e"] = {"value": e2e_rows / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(e2e["h2d"]),
                            "d2h_bytes_per_step": int(e2e["d2h"]),
                            "note": "pve_step_host: pinned host actions in; reward/ids/cpv/status/jerk_sum/"
                                    "offsets/per-env counters out; observations stay in HBM for the device-side actor"}
-        if world == 1 and not args.no_cpu_baseline:
+        if world == 1 and not args.no_cpu_baseline and actor is None:
             cores = os.cpu_count() or 1
             n_envs = max(64, min(512, 8 * cores))
             r = cpu_port_run(args, n_envs, PRIME_TICKS, 100, 5, cores)
