@@ -7,12 +7,17 @@
  * with tf.contrib.layers.layer_norm (tensorflow 1.12, un-vendored dependency): moments over the
  * feature axis, variance = mean((x - mean)^2), epsilon 1e-12,
  *     inv = rsqrt(var + eps) * gamma;  y = x * inv + (beta - mean * inv).
- * Uncontrolled vehicles get action 0 (main.py:401).  All arithmetic is fp32 like the reference's graph.
+ * Uncontrolled vehicles get action 0 (main.py:401).  All arithmetic is fp32 like the reference's graph; the
+ * network is ill-conditioned at the 1e-4 level (rounding only its inputs to fp32 moves some actions by
+ * 9e-5), so reduced-precision tensor-core formats (tf32 / bf16) are not an option for parity.
  *
- * One warp per intersection at a time.  Each lane owns two of the 64 hidden units and keeps their
- * weight columns in registers (28 + 28 + 64 + 64 values); the activations of a layer are exchanged
- * through a 64-float shared-memory line per warp and read back as broadcast float4s, so the inner
- * loops are FFMA with one LDS.128 per eight FFMAs.  Two agents are in flight per warp for latency.
+ * A CTA walks over its share of the intersections, appends the controlled vehicle slots to a ring in shared
+ * memory (warp ballots) and, whenever 128 are queued, evaluates the network for them as a register-tiled
+ * GEMM chain: thread t owns rows {16 r + t / 8} and the eight hidden units 8 (t % 8) .. +7, i.e. an 8 x 8
+ * accumulator tile; activations (row-major, stride 68 floats) and weights (25 KB, copied once per CTA) are
+ * read from shared memory as float4s, 16 LDS.128 per 256 FFMAs.  The first LayerNorm is computed by the
+ * thread that loads the row, the other two inside the tile (the eight threads of a row are adjacent lanes:
+ * three shuffle steps).  fp32 FFMA on purpose: see the conditioning note above; tensor cores are not used.
  * Device only: there is no host version of this file (the numpy restatement for tests lives in
  * oracle/actor_oracle.py).
  */
@@ -30,131 +35,211 @@ enum { PVA_LN0_G = 0, PVA_LN0_B = 28, PVA_W1 = 56, PVA_B1 = PVA_W1 + 28 * 64, PV
 static_assert(PVA_COUNT == PVE_ACTOR_FLOATS, "actor parameter count");
 
 #ifdef __CUDACC__
-#define PVA_WARPS 4
-#define PVA_ROWS 2            /* agents in flight per warp */
+#define PVA_THREADS 128
+#define PVA_TILE 128          /* vehicles per evaluation round */
+#define PVA_AS 68             /* activation row stride in floats: rows 16 apart fall into different banks */
+#define PVA_RING 1024         /* queued vehicle slots (>= PVA_TILE - 1 + the largest capacity class, 576) */
 #define PVA_EPS 1e-12f
+#define PVA_WPAD ((PVA_COUNT + 3) & ~3)
+#define PVA_SMEM_BYTES ((PVA_WPAD + PVA_TILE * PVA_AS) * 4 + PVA_RING * 4)
 
-__device__ __forceinline__ float pva_warp_sum(float v) {
+/* acc[r][c] = bias[8 cg + c] + sum_k a[16 r + rg][k] * Wm[k][8 cg + c] */
+template <int K>
+__device__ __forceinline__ void pva_gemm_tile(const float *__restrict__ a, const float *__restrict__ Wm,
+                                              const float *__restrict__ bias, float (&acc)[8][8], int rg, int cg) {
+    {
+        const float4 b0 = *reinterpret_cast<const float4 *>(bias + cg * 8), b1 = *reinterpret_cast<const float4 *>(bias + cg * 8 + 4);
 #pragma unroll
-    for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
-    return v;
+        for (int r = 0; r < 8; ++r) {
+            acc[r][0] = b0.x; acc[r][1] = b0.y; acc[r][2] = b0.z; acc[r][3] = b0.w;
+            acc[r][4] = b1.x; acc[r][5] = b1.y; acc[r][6] = b1.z; acc[r][7] = b1.w;
+        }
+    }
+    const float *arow = a + rg * PVA_AS;
+    const float *wcol = Wm + cg * 8;
+#pragma unroll 1
+    for (int k0 = 0; k0 < K; k0 += 4) {
+        float4 av[8];
+#pragma unroll
+        for (int r = 0; r < 8; ++r) av[r] = *reinterpret_cast<const float4 *>(arow + r * 16 * PVA_AS + k0);
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk) {
+            const float4 b0 = *reinterpret_cast<const float4 *>(wcol + (k0 + kk) * 64);
+            const float4 b1 = *reinterpret_cast<const float4 *>(wcol + (k0 + kk) * 64 + 4);
+#pragma unroll
+            for (int r = 0; r < 8; ++r) {
+                const float v = kk == 0 ? av[r].x : kk == 1 ? av[r].y : kk == 2 ? av[r].z : av[r].w;
+                acc[r][0] = fmaf(v, b0.x, acc[r][0]); acc[r][1] = fmaf(v, b0.y, acc[r][1]);
+                acc[r][2] = fmaf(v, b0.z, acc[r][2]); acc[r][3] = fmaf(v, b0.w, acc[r][3]);
+                acc[r][4] = fmaf(v, b1.x, acc[r][4]); acc[r][5] = fmaf(v, b1.y, acc[r][5]);
+                acc[r][6] = fmaf(v, b1.z, acc[r][6]); acc[r][7] = fmaf(v, b1.w, acc[r][7]);
+            }
+        }
+    }
 }
 
-/* rows: [n_slots][28] stored rows (the scene's row0 buffer or any dense matrix); slot s is evaluated when
- * mask says so: meta != null -> control flag of meta[s] and (s mod slots_per_env) < n_veh[env];
- * meta == null -> every slot.  actions[s] = 3 tanh(...) (+ noise_scale * noise[s]) or 0. */
-__global__ void __launch_bounds__(PVA_WARPS * 32, 2)
+/* LayerNorm over the 64 units of every row of the tile (8 per thread, 8 adjacent lanes per row) + ReLU */
+__device__ __forceinline__ void pva_tile_ln_relu(float (&acc)[8][8], const float *__restrict__ gamma,
+                                                 const float *__restrict__ beta, int cg) {
+    float g[8], be[8];
+    {
+        const float4 g0 = *reinterpret_cast<const float4 *>(gamma + cg * 8), g1 = *reinterpret_cast<const float4 *>(gamma + cg * 8 + 4);
+        const float4 e0 = *reinterpret_cast<const float4 *>(beta + cg * 8), e1 = *reinterpret_cast<const float4 *>(beta + cg * 8 + 4);
+        g[0] = g0.x; g[1] = g0.y; g[2] = g0.z; g[3] = g0.w; g[4] = g1.x; g[5] = g1.y; g[6] = g1.z; g[7] = g1.w;
+        be[0] = e0.x; be[1] = e0.y; be[2] = e0.z; be[3] = e0.w; be[4] = e1.x; be[5] = e1.y; be[6] = e1.z; be[7] = e1.w;
+    }
+    float mean[8], rs[8];
+#pragma unroll
+    for (int r = 0; r < 8; ++r) mean[r] = ((acc[r][0] + acc[r][1]) + (acc[r][2] + acc[r][3])) + ((acc[r][4] + acc[r][5]) + (acc[r][6] + acc[r][7]));
+#pragma unroll
+    for (int d = 1; d < 8; d <<= 1)
+#pragma unroll
+        for (int r = 0; r < 8; ++r) mean[r] += __shfl_xor_sync(0xffffffffu, mean[r], d);
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+        mean[r] *= (1.f / 64.f);
+        float q = 0.f;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) { const float dlt = acc[r][c] - mean[r]; q = fmaf(dlt, dlt, q); }
+        rs[r] = q;
+    }
+#pragma unroll
+    for (int d = 1; d < 8; d <<= 1)
+#pragma unroll
+        for (int r = 0; r < 8; ++r) rs[r] += __shfl_xor_sync(0xffffffffu, rs[r], d);
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+        const float inv0 = rsqrtf(rs[r] * (1.f / 64.f) + PVA_EPS);
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+            const float inv = inv0 * g[c];
+            acc[r][c] = fmaxf(acc[r][c] * inv + (be[c] - mean[r] * inv), 0.f);
+        }
+    }
+}
+
+/* rows: [n_slots][28] stored rows (the scene's row0 buffer or any dense matrix), n_slots = n_env * slots_per_env
+ * (the last "intersection" of a dense matrix may be partial: n_slots bounds it).  Slot s is evaluated when
+ * meta == null (every slot), or when its vehicle is live (s mod slots_per_env < n_veh[env]) and controlled
+ * (flag of meta[s]).  actions[s] = 3 tanh(...) (+ noise_scale * noise[s]), or 0 for the other slots. */
+__global__ void __launch_bounds__(PVA_THREADS, 3)
 pve_actor_kernel(const float *__restrict__ W, const float *__restrict__ rows, const pve_veh_meta *__restrict__ meta,
                  const int32_t *__restrict__ n_veh, const float *__restrict__ noise, const float noise_scale,
-                 float *__restrict__ actions, const int n_env, const int slots_per_env, const long long n_slots) {
-    __shared__ __align__(16) float xs[PVA_WARPS][PVA_ROWS][64];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int gw = blockIdx.x * PVA_WARPS + warp, nw = gridDim.x * PVA_WARPS;
+                 float *__restrict__ actions, const int slots_per_env, const int n_env, const long long n_slots) {
+    extern __shared__ __align__(16) unsigned char pva_smem[];
+    float *const w = reinterpret_cast<float *>(pva_smem);                        /* [PVA_WPAD] parameters */
+    float *const a = w + PVA_WPAD;                                               /* [PVA_TILE][PVA_AS] activations */
+    int *const ring = reinterpret_cast<int *>(a + PVA_TILE * PVA_AS);            /* [PVA_RING] queued slots */
+    __shared__ int q_tail;
+    const int tid = threadIdx.x, lane = tid & 31, cg = tid & 7, rg = tid >> 3;
+    for (int i = tid; i < PVA_COUNT; i += PVA_THREADS) w[i] = W[i];
+    if (tid == 0) q_tail = 0;
+    __syncthreads();
 
-    /* this lane's weight columns */
-    float w1a[28], w1b[28], w2a[64], w2b[64];
-#pragma unroll
-    for (int i = 0; i < 28; ++i) { w1a[i] = W[PVA_W1 + i * 64 + lane]; w1b[i] = W[PVA_W1 + i * 64 + lane + 32]; }
-#pragma unroll
-    for (int i = 0; i < 64; ++i) { w2a[i] = W[PVA_W2 + i * 64 + lane]; w2b[i] = W[PVA_W2 + i * 64 + lane + 32]; }
-    const float g0 = lane < 28 ? W[PVA_LN0_G + lane] : 0.f, be0 = lane < 28 ? W[PVA_LN0_B + lane] : 0.f;
-    const float b1a = W[PVA_B1 + lane], b1b = W[PVA_B1 + lane + 32];
-    const float g1a = W[PVA_LN1_G + lane], g1b = W[PVA_LN1_G + lane + 32];
-    const float be1a = W[PVA_LN1_B + lane], be1b = W[PVA_LN1_B + lane + 32];
-    const float b2a = W[PVA_B2 + lane], b2b = W[PVA_B2 + lane + 32];
-    const float g2a = W[PVA_LN2_G + lane], g2b = W[PVA_LN2_G + lane + 32];
-    const float be2a = W[PVA_LN2_B + lane], be2b = W[PVA_LN2_B + lane + 32];
-    const float w3a = W[PVA_W3 + lane], w3b = W[PVA_W3 + lane + 32], b3 = W[PVA_B3];
-
-    for (int env = gw; env < n_env; env += nw) {
-        const size_t base = (size_t)env * (size_t)slots_per_env;
-        const int nv = n_veh ? min(n_veh[env], slots_per_env) : slots_per_env;
-        for (int k0 = 0; k0 < slots_per_env; k0 += 32) {
-            const int k = k0 + lane;
-            bool want = k < nv && (long long)(base + k) < n_slots;
-            if (want && meta) want = ((meta[base + k].packed >> 24) & PVE_F_CONTROL) != 0;
-            if (k < slots_per_env && !want && (long long)(base + k) < n_slots) actions[base + k] = 0.f;   /* main.py:401 */
-            unsigned todo = __ballot_sync(0xffffffffu, want);
-            while (todo) {
-                int kk[PVA_ROWS];
-                float x[PVA_ROWS];
-#pragma unroll
-                for (int r = 0; r < PVA_ROWS; ++r) {
-                    kk[r] = todo ? k0 + __ffs(todo) - 1 : -1;
-                    todo &= todo - 1;
-                    x[r] = (kk[r] >= 0 && lane < 28) ? rows[(base + kk[r]) * PVE_OBS_W + lane] : 0.f;
+    /* contiguous share of the intersections */
+    const int per = (n_env + (int)gridDim.x - 1) / (int)gridDim.x;
+    const int env0 = (int)blockIdx.x * per, env1 = min(n_env, env0 + per);
+    int head = 0;                                /* ring positions are monotonic counters, used modulo PVA_RING */
+    for (int env = env0; env <= env1; ++env) {
+        const bool flush = env == env1;          /* after the last intersection: the partial tile */
+        if (!flush) {
+            /* which slots carry a controlled vehicle (main.py:401-403)? */
+            const long long base = (long long)env * slots_per_env;
+            const int nv = n_veh ? n_veh[env] : slots_per_env;
+            for (int s0 = 0; s0 < slots_per_env; s0 += PVA_THREADS) {
+                const int s = s0 + tid;
+                const long long gs = base + s;
+                bool want = s < slots_per_env && gs < n_slots;
+                if (want && meta) {
+                    want = s < nv && ((meta[gs].packed >> 24) & PVE_F_CONTROL) != 0;
+                    if (!want) actions[gs] = 0.f;
                 }
-                float ha[PVA_ROWS], hb[PVA_ROWS];
-                /* LN(28), NET:27 */
+                const unsigned bal = __ballot_sync(0xffffffffu, want);
+                int at = 0;
+                if (lane == 0 && bal) at = atomicAdd(&q_tail, __popc(bal));
+                at = __shfl_sync(0xffffffffu, at, 0);
+                if (want) ring[(at + __popc(bal & ((1u << lane) - 1u))) & (PVA_RING - 1)] = (int)(gs - (long long)env0 * slots_per_env);
+            }
+            __syncthreads();
+        }
+        const long long cta_base = (long long)env0 * slots_per_env;
+        const int tail = q_tail;
+        __syncthreads();                         /* everybody has read the tail before the next append moves it */
+        while (tail - head >= (flush ? 1 : PVA_TILE)) {
+            const int n_valid = min(PVA_TILE, tail - head);
+            /* first LayerNorm by the thread that loads the row (NET:27) */
+            {
+                float x[28];
+                const bool valid = tid < n_valid;
+                const long long gs = valid ? cta_base + ring[(head + tid) & (PVA_RING - 1)] : 0;
+                const float4 *src = reinterpret_cast<const float4 *>(rows + gs * PVE_OBS_W);
 #pragma unroll
-                for (int r = 0; r < PVA_ROWS; ++r) {
-                    const float mean = pva_warp_sum(x[r]) * (1.f / 28.f);
-                    const float d = lane < 28 ? x[r] - mean : 0.f;
-                    const float var = pva_warp_sum(d * d) * (1.f / 28.f);
-                    const float inv = rsqrtf(var + PVA_EPS) * g0;
-                    xs[warp][r][lane] = x[r] * inv + (be0 - mean * inv);
+                for (int q = 0; q < 7; ++q) {
+                    const float4 v = valid ? src[q] : make_float4(0.f, 0.f, 0.f, 0.f);
+                    x[4 * q] = v.x; x[4 * q + 1] = v.y; x[4 * q + 2] = v.z; x[4 * q + 3] = v.w;
                 }
-                __syncwarp();
-                /* Dense 28 -> 64, NET:28 */
+                float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
 #pragma unroll
-                for (int r = 0; r < PVA_ROWS; ++r) { ha[r] = 0.f; hb[r] = 0.f; }
+                for (int i = 0; i < 28; i += 4) { s0 += x[i]; s1 += x[i + 1]; s2 += x[i + 2]; s3 += x[i + 3]; }
+                const float mean = ((s0 + s1) + (s2 + s3)) * (1.f / 28.f);
+                s0 = s1 = s2 = s3 = 0.f;
 #pragma unroll
-                for (int i = 0; i < 28; i += 4)
-#pragma unroll
-                    for (int r = 0; r < PVA_ROWS; ++r) {
-                        const float4 v = *reinterpret_cast<const float4 *>(&xs[warp][r][i]);
-                        ha[r] = fmaf(v.x, w1a[i], ha[r]); hb[r] = fmaf(v.x, w1b[i], hb[r]);
-                        ha[r] = fmaf(v.y, w1a[i + 1], ha[r]); hb[r] = fmaf(v.y, w1b[i + 1], hb[r]);
-                        ha[r] = fmaf(v.z, w1a[i + 2], ha[r]); hb[r] = fmaf(v.z, w1b[i + 2], hb[r]);
-                        ha[r] = fmaf(v.w, w1a[i + 3], ha[r]); hb[r] = fmaf(v.w, w1b[i + 3], hb[r]);
-                    }
-                __syncwarp();
-                /* LN(64) + ReLU, NET:30-32 */
-#pragma unroll
-                for (int r = 0; r < PVA_ROWS; ++r) {
-                    const float a = ha[r] + b1a, b = hb[r] + b1b;
-                    const float mean = pva_warp_sum(a + b) * (1.f / 64.f);
-                    const float da = a - mean, db = b - mean;
-                    const float var = pva_warp_sum(da * da + db * db) * (1.f / 64.f);
-                    const float rs = rsqrtf(var + PVA_EPS);
-                    const float ia = rs * g1a, ib = rs * g1b;
-                    xs[warp][r][lane] = fmaxf(a * ia + (be1a - mean * ia), 0.f);
-                    xs[warp][r][lane + 32] = fmaxf(b * ib + (be1b - mean * ib), 0.f);
+                for (int i = 0; i < 28; i += 4) {
+                    const float d0 = x[i] - mean, d1 = x[i + 1] - mean, d2 = x[i + 2] - mean, d3 = x[i + 3] - mean;
+                    s0 = fmaf(d0, d0, s0); s1 = fmaf(d1, d1, s1); s2 = fmaf(d2, d2, s2); s3 = fmaf(d3, d3, s3);
                 }
-                __syncwarp();
-                /* Dense 64 -> 64, NET:34 */
+                const float rs = rsqrtf(((s0 + s1) + (s2 + s3)) * (1.f / 28.f) + PVA_EPS);
 #pragma unroll
-                for (int r = 0; r < PVA_ROWS; ++r) { ha[r] = 0.f; hb[r] = 0.f; }
-#pragma unroll
-                for (int i = 0; i < 64; i += 4)
-#pragma unroll
-                    for (int r = 0; r < PVA_ROWS; ++r) {
-                        const float4 v = *reinterpret_cast<const float4 *>(&xs[warp][r][i]);
-                        ha[r] = fmaf(v.x, w2a[i], ha[r]); hb[r] = fmaf(v.x, w2b[i], hb[r]);
-                        ha[r] = fmaf(v.y, w2a[i + 1], ha[r]); hb[r] = fmaf(v.y, w2b[i + 1], hb[r]);
-                        ha[r] = fmaf(v.z, w2a[i + 2], ha[r]); hb[r] = fmaf(v.z, w2b[i + 2], hb[r]);
-                        ha[r] = fmaf(v.w, w2a[i + 3], ha[r]); hb[r] = fmaf(v.w, w2b[i + 3], hb[r]);
-                    }
-                __syncwarp();
-                /* LN(64) + ReLU, Dense 64 -> 1, 3 tanh: NET:36-47 */
-#pragma unroll
-                for (int r = 0; r < PVA_ROWS; ++r) {
-                    const float a = ha[r] + b2a, b = hb[r] + b2b;
-                    const float mean = pva_warp_sum(a + b) * (1.f / 64.f);
-                    const float da = a - mean, db = b - mean;
-                    const float var = pva_warp_sum(da * da + db * db) * (1.f / 64.f);
-                    const float rs = rsqrtf(var + PVA_EPS);
-                    const float ia = rs * g2a, ib = rs * g2b;
-                    const float ra = fmaxf(a * ia + (be2a - mean * ia), 0.f);
-                    const float rb = fmaxf(b * ib + (be2b - mean * ib), 0.f);
-                    const float o = pva_warp_sum(fmaf(ra, w3a, rb * w3b)) + b3;
-                    if (lane == 0 && kk[r] >= 0) {
-                        float act = 3.f * tanhf(o);
-                        if (noise) act += noise_scale * noise[base + kk[r]];     /* main.py:44 */
-                        actions[base + kk[r]] = act;
-                    }
+                for (int i = 0; i < 28; i += 4) {
+                    const float4 g = *reinterpret_cast<const float4 *>(w + PVA_LN0_G + i);
+                    const float4 b = *reinterpret_cast<const float4 *>(w + PVA_LN0_B + i);
+                    const float i0 = rs * g.x, i1 = rs * g.y, i2 = rs * g.z, i3 = rs * g.w;
+                    float4 y;
+                    y.x = x[i] * i0 + (b.x - mean * i0); y.y = x[i + 1] * i1 + (b.y - mean * i1);
+                    y.z = x[i + 2] * i2 + (b.z - mean * i2); y.w = x[i + 3] * i3 + (b.w - mean * i3);
+                    *reinterpret_cast<float4 *>(a + tid * PVA_AS + i) = y;
                 }
             }
+            __syncthreads();
+            float acc[8][8];
+            pva_gemm_tile<28>(a, w + PVA_W1, w + PVA_B1, acc, rg, cg);             /* NET:28 */
+            pva_tile_ln_relu(acc, w + PVA_LN1_G, w + PVA_LN1_B, cg);               /* NET:30-32 */
+            __syncthreads();                                                       /* every thread has read its inputs */
+#pragma unroll
+            for (int r = 0; r < 8; ++r) {
+                float *dst = a + (r * 16 + rg) * PVA_AS + cg * 8;
+                *reinterpret_cast<float4 *>(dst) = make_float4(acc[r][0], acc[r][1], acc[r][2], acc[r][3]);
+                *reinterpret_cast<float4 *>(dst + 4) = make_float4(acc[r][4], acc[r][5], acc[r][6], acc[r][7]);
+            }
+            __syncthreads();
+            pva_gemm_tile<64>(a, w + PVA_W2, w + PVA_B2, acc, rg, cg);             /* NET:34 */
+            pva_tile_ln_relu(acc, w + PVA_LN2_G, w + PVA_LN2_B, cg);               /* NET:36-38 */
+            {   /* Dense 64 -> 1, 3 tanh (NET:40-47) */
+                const float4 u0 = *reinterpret_cast<const float4 *>(w + PVA_W3 + cg * 8);
+                const float4 u1 = *reinterpret_cast<const float4 *>(w + PVA_W3 + cg * 8 + 4);
+                float o[8];
+#pragma unroll
+                for (int r = 0; r < 8; ++r)
+                    o[r] = fmaf(acc[r][0], u0.x, fmaf(acc[r][1], u0.y, fmaf(acc[r][2], u0.z, acc[r][3] * u0.w)))
+                           + fmaf(acc[r][4], u1.x, fmaf(acc[r][5], u1.y, fmaf(acc[r][6], u1.z, acc[r][7] * u1.w)));
+#pragma unroll
+                for (int d = 1; d < 8; d <<= 1)
+#pragma unroll
+                    for (int r = 0; r < 8; ++r) o[r] += __shfl_xor_sync(0xffffffffu, o[r], d);
+                /* lane cg of the row's eight writes row r = cg */
+                const int row = cg * 16 + rg;
+                float mine = o[0];
+#pragma unroll
+                for (int r = 1; r < 8; ++r) mine = cg == r ? o[r] : mine;
+                if (row < n_valid) {
+                    const long long gs = cta_base + ring[(head + row) & (PVA_RING - 1)];
+                    float act = 3.f * tanhf(mine + w[PVA_B3]);
+                    if (noise) act += noise_scale * noise[gs];                     /* main.py:44 */
+                    actions[gs] = act;
+                }
+            }
+            head += n_valid;
+            __syncthreads();                     /* the tile and the ring entries are free again */
         }
     }
 }

@@ -731,7 +731,10 @@ int32_t pve_actor_create(const float *weights_host, int32_t n_floats, int32_t de
     a->device = device;
     int sms = 0;
     if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device) != cudaSuccess || sms <= 0) sms = 148;
-    a->blocks = 2 * sms;                     /* __launch_bounds__(128, 2): one resident wave, warps loop */
+    a->blocks = 3 * sms;                     /* __launch_bounds__(128, 3): one resident wave, CTAs loop over chunks */
+    if (cudaFuncSetAttribute(pve_actor_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PVA_SMEM_BYTES) != cudaSuccess) {
+        free(a); return PVE_ECUDA;
+    }
     if (cudaMalloc((void **)&a->w_dev, sizeof(float) * PVE_ACTOR_FLOATS) != cudaSuccess) { free(a); return PVE_ENOMEM; }
     if (cudaMemcpy(a->w_dev, weights_host, sizeof(float) * PVE_ACTOR_FLOATS, cudaMemcpyHostToDevice) != cudaSuccess) {
         cudaFree(a->w_dev); free(a); return PVE_ECUDA;
@@ -756,10 +759,11 @@ int32_t pve_actor_forward(pve_actor *a, const float *rows_dev, int64_t n_rows, f
     return PVE_ESTATE;
 #else
     if (n_rows == 0) return PVE_OK;
-    const int n_env = (int)((n_rows + 31) / 32);             /* groups of 32 rows, one warp each */
-    const int blocks = (n_env + PVA_WARPS - 1) / PVA_WARPS < a->blocks ? (n_env + PVA_WARPS - 1) / PVA_WARPS : a->blocks;
-    pve_actor_kernel<<<blocks, PVA_WARPS * 32, 0, (pve_stream_t)stream_>>>(a->w_dev, rows_dev, nullptr, nullptr, nullptr, 0.f,
-                                                                        actions_dev, n_env, 32, (long long)n_rows);
+    const long long groups = (n_rows + PVA_TILE - 1) / PVA_TILE;             /* "intersections" of 128 rows */
+    if (groups > 0x7fffffffLL) return PVE_EINVAL;
+    const int blocks = groups < a->blocks ? (int)groups : a->blocks;
+    pve_actor_kernel<<<blocks, PVA_THREADS, PVA_SMEM_BYTES, (pve_stream_t)stream_>>>(
+        a->w_dev, rows_dev, nullptr, nullptr, nullptr, 0.f, actions_dev, PVA_TILE, (int)groups, (long long)n_rows);
     return cudaGetLastError() == cudaSuccess ? PVE_OK : PVE_ECUDA;
 #endif
 }
@@ -777,9 +781,9 @@ int32_t pve_act(pve_scene *s, pve_actor *a, const float *noise_dev, float noise_
         return PVE_EINVAL;
     }
     const int B = s->cfg.n_envs, VCc = s->prm.VC;
-    const int blocks = (B + PVA_WARPS - 1) / PVA_WARPS < a->blocks ? (B + PVA_WARPS - 1) / PVA_WARPS : a->blocks;
-    pve_actor_kernel<<<blocks, PVA_WARPS * 32, 0, (pve_stream_t)stream_>>>(
-        a->w_dev, pve_row0_dev(s), s->st.meta, s->st.n_veh, noise_dev, noise_scale, actions_dev, B, VCc,
+    const int blocks = B < a->blocks ? B : a->blocks;
+    pve_actor_kernel<<<blocks, PVA_THREADS, PVA_SMEM_BYTES, (pve_stream_t)stream_>>>(
+        a->w_dev, pve_row0_dev(s), s->st.meta, s->st.n_veh, noise_dev, noise_scale, actions_dev, VCc, B,
         (long long)B * (long long)VCc);
     RT_CHECK(s, cudaGetLastError());
     return PVE_OK;
