@@ -715,6 +715,7 @@ int32_t pve_stats(pve_scene *s, pve_counters *out_dev, void *stream_) {
 /* ---- actor (N1) ---------------------------------------------------------------------------- */
 struct pve_actor {
     float *w_dev;
+    int *ticket;                 /* [2] work counter + exit counter of the kernel, zero between launches */
     int device;
     int blocks;
 };
@@ -739,6 +740,9 @@ int32_t pve_actor_create(const float *weights_host, int32_t n_floats, int32_t de
     if (cudaMemcpy(a->w_dev, weights_host, sizeof(float) * PVE_ACTOR_FLOATS, cudaMemcpyHostToDevice) != cudaSuccess) {
         cudaFree(a->w_dev); free(a); return PVE_ECUDA;
     }
+    if (cudaMalloc((void **)&a->ticket, 2 * sizeof(int)) != cudaSuccess || cudaMemset(a->ticket, 0, 2 * sizeof(int)) != cudaSuccess) {
+        cudaFree(a->w_dev); free(a); return PVE_ENOMEM;
+    }
     *out = a;
     return PVE_OK;
 #endif
@@ -748,6 +752,7 @@ void pve_actor_destroy(pve_actor *a) {
     if (!a) return;
 #ifndef PVE_HOST_EMULATION
     cudaFree(a->w_dev);
+    cudaFree(a->ticket);
 #endif
     free(a);
 }
@@ -760,10 +765,10 @@ int32_t pve_actor_forward(pve_actor *a, const float *rows_dev, int64_t n_rows, f
 #else
     if (n_rows == 0) return PVE_OK;
     const long long groups = (n_rows + PVA_TILE - 1) / PVA_TILE;             /* "intersections" of 128 rows */
-    if (groups > 0x7fffffffLL) return PVE_EINVAL;
+    if (n_rows > 0x7fffffffLL) return PVE_EINVAL;             /* slot indices are queued as 32-bit */
     const int blocks = groups < a->blocks ? (int)groups : a->blocks;
     pve_actor_kernel<<<blocks, PVA_THREADS, PVA_SMEM_BYTES, (pve_stream_t)stream_>>>(
-        a->w_dev, rows_dev, nullptr, nullptr, nullptr, 0.f, actions_dev, PVA_TILE, (int)groups, (long long)n_rows);
+        a->w_dev, rows_dev, nullptr, nullptr, nullptr, 0.f, actions_dev, PVA_TILE, (int)groups, (long long)n_rows, a->ticket);
     return cudaGetLastError() == cudaSuccess ? PVE_OK : PVE_ECUDA;
 #endif
 }
@@ -784,7 +789,7 @@ int32_t pve_act(pve_scene *s, pve_actor *a, const float *noise_dev, float noise_
     const int blocks = B < a->blocks ? B : a->blocks;
     pve_actor_kernel<<<blocks, PVA_THREADS, PVA_SMEM_BYTES, (pve_stream_t)stream_>>>(
         a->w_dev, pve_row0_dev(s), s->st.meta, s->st.n_veh, noise_dev, noise_scale, actions_dev, VCc, B,
-        (long long)B * (long long)VCc);
+        (long long)B * (long long)VCc, a->ticket);
     RT_CHECK(s, cudaGetLastError());
     return PVE_OK;
 #endif
