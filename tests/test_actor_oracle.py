@@ -67,3 +67,15 @@ def test_checkpoint_reader_against_the_shipped_bundle():
     f = ActorWeights.from_npz(os.path.join(GOLD, "actor_agent1.npz"))
     for n, _ in PARAM_SPECS:
         assert np.array_equal(w.tensors[n], f.tensors[n]), n
+
+
+def test_actor_needs_a_gpu_and_says_so():
+    import torch
+    from pve_mcc_for_unsignalized_intersection_b200 import _native
+    from pve_mcc_for_unsignalized_intersection_b200.actor import BatchedActor
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is visible")
+    with pytest.raises(_native.NativeError):
+        BatchedActor(ActorWeights.random(0))
+    with pytest.raises(_native.NativeError):
+        BatchedActor(ActorWeights.random(0), device="cpu")
