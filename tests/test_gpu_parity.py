@@ -125,3 +125,11 @@ def test_capacity_overflow_is_flagged_not_silent():
     st = scene.get_state()
     assert st["overflow"][0] > 0 and st["n_veh"][0] <= scene.veh_cap and st["n_ctrl"][0] <= scene.agent_cap
     assert scene.stats()["overflow"] > 0
+
+
+def test_config3_teacher_forced_sample_of_a_large_shard():
+    """BASELINE config 3 at reduced size (the full 8 x 8,192 run is tests/config3_check.py under torchrun):
+    a shard of 2,048 intersections free-runs on the GPU; a strided sample is teacher-forced against the oracle."""
+    import config3_check
+    res, _ = config3_check.run_check(2048, ticks=120, sample=32, check_every=20)
+    assert res["checks"] == 7 and res["agent_rows_compared"] > 3000
