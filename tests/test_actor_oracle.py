@@ -79,3 +79,23 @@ def test_actor_needs_a_gpu_and_says_so():
         BatchedActor(ActorWeights.random(0))
     with pytest.raises(_native.NativeError):
         BatchedActor(ActorWeights.random(0), device="cpu")
+
+
+def test_report_line_and_mat_ingest(tmp_path):
+    """Row N4: the batch_test result line (main.py:576-581) and scipy .mat ingest (main.py:388-389)."""
+    import scipy.io as scio
+    from pve_mcc_for_unsignalized_intersection_b200 import evaluate
+    z = np.load(os.path.join(GOLD, "actor_rollout_mat1000.npz"))
+    v, c, p, l = z["outcome"].tolist()
+    line = evaluate.format_report(v, c, p, int(z["trace"][-1, 5]), float(z["jerk_total"]), l)
+    assert line == ("vehicle number 323  collisions occurred number 0 collisions rate 0.0 pT-m 12.2943 s "
+                    "jerks 208.79941400944244 lock_num 548")
+    path = str(tmp_path / "arvTimeNewVeh_new_1000_12.mat")
+    scio.savemat(path, {"arvTimeNewVeh": z["arrive_time"]})
+    arr = evaluate.load_arrivals(path)
+    assert arr.dtype == np.float64 and np.array_equal(arr, z["arrive_time"])
+    stacked = evaluate.stack_tables([arr, arr[:10]])
+    assert stacked.shape == (2,) + arr.shape and np.all(stacked[1, 10:] == 0) and np.array_equal(stacked[0], arr)
+    scio.savemat(path, {"arvTimeNewVeh": np.zeros((5, 4))})
+    with pytest.raises(ValueError):
+        evaluate.load_arrivals(path)

@@ -132,3 +132,22 @@ def test_closed_loop_reproduces_config1_of_the_reference():
     ptm = st["passed_step_total"][0] / (st["passed_veh"][0] + 0.0001) * 0.1         # main.py:525
     assert [int(st["id_seq"][0]), int(coll[0]), int(st["passed_veh"][0]), int(lock[0])] == z["outcome"].tolist()
     assert abs(ptm - float(z["ptm"])) < 1e-9
+
+
+def test_evaluation_report_matches_the_reference_run():
+    """Row N4: evaluate_tables = the reference's test driver (main.py:394-441 / 553-581); tables of different
+    length side by side; the report line equals the one the reference prints for the recorded run."""
+    from pve_mcc_for_unsignalized_intersection_b200 import evaluate
+    z = np.load(os.path.join(GOLD, "actor_rollout_mat1000.npz"))
+    w = ActorWeights.from_npz(os.path.join(GOLD, "actor_agent1.npz"))
+    arr = z["arrive_time"]
+    res = evaluate.evaluate_tables([arr, arr[:20], arr], w, ticks=1000)
+    v, c, p, l = z["outcome"].tolist()
+    for r in (res[0], res[2]):
+        assert [r["vehicles"], r["collisions"], r["passed"], r["lock_total"]] == [v, c, p, l]
+        assert r["passed_step_total"] == int(z["trace"][-1, 5])
+        assert abs(r["jerk_total"] - float(z["jerk_total"])) <= 1e-5 * float(z["jerk_total"])
+        head, tail = r["report"].split(" jerks ")
+        assert head == "vehicle number 323  collisions occurred number 0 collisions rate 0.0 pT-m 12.2943 s"
+        assert tail.endswith(" lock_num 548") and abs(float(tail.split()[0]) - 208.79941400944244) < 2e-3
+    assert res[1]["vehicles"] < v                     # the truncated table runs dry earlier
