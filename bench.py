@@ -364,8 +364,9 @@ def graft_arm(args, rank, world, local_rank):
         if e2e:
             line["e2e"] = {"value": e2e_rows / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(e2e["h2d"]),
                            "d2h_bytes_per_step": int(e2e["d2h"]),
-                           "note": "pve_step_host: pinned host actions in; reward/ids/cpv/status/jerk_sum/"
-                                   "offsets/per-env counters out; observations stay in HBM for the device-side actor"}
+                           "note": "pve_step_host: actions read from and reward/ids/cpv/status/jerk_sum/offsets/"
+                                   "per-env counters written to pinned host memory by the kernel itself, over PCIe, "
+                                   "inside the timed tick; observations stay in HBM for the device-side actor"}
         if world == 1 and not args.no_cpu_baseline and actor is None:
             cores = os.cpu_count() or 1
             n_envs = max(64, min(512, 8 * cores))

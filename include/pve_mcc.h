@@ -143,9 +143,11 @@ int32_t pve_reset(pve_scene *s, const int32_t *spawn_tick_dev, int32_t K, int32_
  * delete_vehicle() (TIS:435).  actions_dev: float [B][veh_cap]. */
 int32_t pve_step(pve_scene *s, const float *actions_dev, const pve_outputs *out_dev, void *stream);
 
-/* Same tick through HOST buffers: copies actions host->device, runs the tick, copies the
- * selected outputs device->host and synchronises.  `copy_mask` bit0: reward/ids/cpv/status/
- * jerk_sum/agent_offset/env_* ; bit1: obs.  `out_host` arrays need `pve_next_agent_total()` rows. */
+/* Same tick through HOST buffers; synchronises.  `copy_mask` bit0: reward/ids/cpv/status/jerk_sum/
+ * agent_offset/env_* ; bit1: obs.  `out_host` arrays need `pve_next_agent_total()` rows.
+ * Pinned host memory (cudaHostAlloc / cudaHostRegister, torch pin_memory()) is used in place: the kernel reads
+ * `actions_host` and writes the bit0 arrays of `out_host` over PCIe while it runs; the bit0 arrays of `out_dev`
+ * are then not written this tick (obs always is).  Pageable buffers are staged through device copies. */
 int32_t pve_step_host(pve_scene *s, const float *actions_host, const pve_outputs *out_dev,
                       const pve_outputs *out_host, int32_t copy_mask, void *stream);
 

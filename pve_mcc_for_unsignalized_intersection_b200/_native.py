@@ -45,7 +45,7 @@ class NativeError(RuntimeError):
 
 def load_library(path=None):
     """Load libpve_mcc.so and declare the prototypes of every symbol in include/pve_mcc.h."""
-    path = path or LIB_PATH
+    path = path or os.environ.get("PVE_MCC_LIBRARY") or LIB_PATH      # the env override is for A/B measurements of builds
     if not os.path.exists(path):
         raise NativeError(
             "CUDA extension %s is missing; build it with `python -c 'import __graft_entry__ as g; g.build()'` "

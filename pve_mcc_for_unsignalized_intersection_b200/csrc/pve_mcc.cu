@@ -59,6 +59,7 @@ struct pve_scene {
     int64_t next_total;          /* rows of the next tick if known, else -1 */
     int profiling;               /* record events around the step and scan kernels */
     size_t smem_pad;             /* experiment knob (env PVE_SMEM_PAD): extra dynamic shared memory per CTA */
+    int host_zerocopy;           /* pve_step_host reads/writes pinned host buffers in place (env PVE_HOST_ZEROCOPY=0: staged copies) */
 #ifndef PVE_HOST_EMULATION
     cudaEvent_t ev[3];
 #endif
@@ -463,6 +464,8 @@ int32_t pve_create(const pve_config *cfg, int32_t device, pve_scene **out) {
     s->cfg.agent_cap = AC;
     s->threads = cfg->threads == 0 ? 128 : cfg->threads;
     if (const char *pad = getenv("PVE_SMEM_PAD")) s->smem_pad = (size_t)atoi(pad);
+    s->host_zerocopy = 1;
+    if (const char *zc = getenv("PVE_HOST_ZEROCOPY")) s->host_zerocopy = atoi(zc) != 0;
     if (s->threads != 64 && s->threads != 128 && s->threads != 256) {
         snprintf(s->err, sizeof s->err, "threads must be 0, 64, 128 or 256");
         return PVE_EINVAL;
@@ -607,6 +610,17 @@ int64_t pve_next_agent_total(pve_scene *s, void *stream_) {
     return s->next_total;
 }
 
+#ifndef PVE_HOST_EMULATION
+/* true if the device can address `p` directly as host memory (cudaHostAlloc / cudaHostRegister: torch's
+ * pin_memory()), which lets the kernel read or write it in place over PCIe */
+static bool is_pinned_host(const void *p) {
+    if (!p) return false;
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return at.type == cudaMemoryTypeHost;
+}
+#endif
+
 int32_t pve_step_host(pve_scene *s, const float *actions_host, const pve_outputs *out_dev,
                       const pve_outputs *out_host, int32_t copy_mask, void *stream_) {
     if (!s || !actions_host || !out_dev) return PVE_EINVAL;
@@ -619,12 +633,38 @@ int32_t pve_step_host(pve_scene *s, const float *actions_host, const pve_outputs
         snprintf(s->err, sizeof s->err, "tick emits %lld rows but out_cap is %lld", (long long)A, (long long)s->cfg.out_cap);
         return PVE_ESTATE;
     }
-    if (!s->actions_dev) RT_CHECK(s, rt_alloc((void **)&s->actions_dev, sizeof(float) * nv));
-    RT_CHECK(s, rt_copy(s->actions_dev, actions_host, sizeof(float) * nv, stream));
-    int32_t rc = pve_step(s, s->actions_dev, out_dev, stream_);
-    if (rc != PVE_OK) return rc;
     const size_t a = (size_t)A;
-    if (out_host && (copy_mask & 1)) {
+    /* Zero-copy path (pinned host buffers, the normal case): the kernel reads the actions and writes the small
+     * per-agent outputs in place over PCIe while it runs, instead of 1 + 9 staged copies around it.  In that
+     * case those arrays of out_dev are NOT written this tick (the observations always are).
+     * PVE_HOST_ZEROCOPY=0 turns it off. */
+    const float *act_for_kernel = nullptr;
+    pve_outputs O = *out_dev;
+    bool mirrored = false;
+#ifndef PVE_HOST_EMULATION
+    if (s->host_zerocopy && is_pinned_host(actions_host)) act_for_kernel = actions_host;
+    if (s->host_zerocopy && out_host && (copy_mask & 1)) {
+        const void *f[9] = {out_host->agent_offset, out_host->reward, out_host->ids, out_host->cpv, out_host->status,
+                            out_host->jerk_sum, out_host->env_collisions, out_host->env_lock, out_host->env_removed};
+        mirrored = true;
+        for (int i = 0; i < 9; ++i) if (!f[i] || !is_pinned_host(f[i])) mirrored = false;
+        if (mirrored) {
+            O.agent_offset = out_host->agent_offset; O.reward = out_host->reward; O.ids = out_host->ids;
+            O.cpv = out_host->cpv; O.status = out_host->status; O.jerk_sum = out_host->jerk_sum;
+            O.env_collisions = out_host->env_collisions; O.env_lock = out_host->env_lock;
+            O.env_removed = out_host->env_removed;
+        }
+    }
+#endif
+    if (!act_for_kernel) {
+        if (!s->actions_dev) RT_CHECK(s, rt_alloc((void **)&s->actions_dev, sizeof(float) * nv));
+        RT_CHECK(s, rt_copy(s->actions_dev, actions_host, sizeof(float) * nv, stream));
+        act_for_kernel = s->actions_dev;
+    }
+    int32_t rc = launch_step(s, act_for_kernel, O, stream);
+    if (rc != PVE_OK) return rc;
+    s->next_total = -1;
+    if (out_host && (copy_mask & 1) && !mirrored) {
 #define D2H(field, bytes) \
         if (out_host->field && out_dev->field) RT_CHECK(s, rt_copy(out_host->field, out_dev->field, (bytes), stream))
         D2H(agent_offset, sizeof(int32_t) * ((size_t)B + 1));

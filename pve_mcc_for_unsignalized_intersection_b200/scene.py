@@ -169,7 +169,9 @@ class BatchedScene:
     def step_host(self, actions_host, host_out, copy_obs=False):
         """One tick through HOST buffers (the end-to-end path): ``actions_host`` is a (pinned) CPU
         float32 ``[B, veh_cap]`` tensor; results land in ``host_out`` (from ``make_host_outputs``).
-        Returns the number of agent rows of this tick."""
+        Returns the number of agent rows of this tick.  With pinned buffers (the default of
+        ``make_host_outputs``) the kernel works on them in place; the small arrays of ``self.out`` (reward, ids,
+        cpv, status, jerk_sum, offsets, per-intersection counters) are then not refreshed, ``self.out.obs`` is."""
         assert actions_host.dtype == torch.float32 and actions_host.is_contiguous()
         assert actions_host.shape == (self.B, self.veh_cap) and actions_host.device.type == "cpu"
         n = int(self.lib.pve_next_agent_total(self._h, self._stream()))

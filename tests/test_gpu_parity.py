@@ -98,7 +98,8 @@ def test_full_size_4096_intersections_vs_oracle():
     assert s["agent_steps"] == total and s["overflow"] == 0
 
 
-def test_step_host_end_to_end_matches_device_outputs():
+def test_step_host_end_to_end_matches_device_outputs(monkeypatch):
+    monkeypatch.setenv("PVE_HOST_ZEROCOPY", "0")          # staged copies: host and device views both written
     B = 64
     tabs = synthetic_arrivals(B, 1000, 30.0, seed=3, rows=24)
     scene = P.make_scene("cuda", B)
@@ -133,3 +134,54 @@ def test_config3_teacher_forced_sample_of_a_large_shard():
     import config3_check
     res, _ = config3_check.run_check(2048, ticks=120, sample=32, check_every=20)
     assert res["checks"] == 7 and res["agent_rows_compared"] > 3000
+
+
+def host_outputs_to_numpy(host, n):
+    g = lambda t: t[:n].numpy() if t.shape[0] != host.agent_offset.shape[0] - 1 else t.numpy()
+    return {"agent_offset": host.agent_offset.numpy(), "obs": host.obs[:n].numpy(), "reward": host.reward[:n].numpy(),
+            "ids": host.ids[:n].numpy(), "cpv": host.cpv[:n].numpy(), "status": host.status[:n].numpy(),
+            "jerk_sum": host.jerk_sum[:n].numpy(), "collisions": host.env_collisions.numpy(),
+            "lock": host.env_lock.numpy(), "n_removed": host.env_removed.numpy()}
+
+
+@pytest.mark.parametrize("zerocopy", ["1", "0"])
+def test_step_host_zero_copy_and_staged_paths_at_scale(zerocopy, monkeypatch):
+    """pve_step_host with pinned host buffers lets the kernel read the actions and write the small outputs in
+    place over PCIe (PVE_HOST_ZEROCOPY=1, default); =0 is the staged-copy path.  Either way the HOST buffers
+    must follow the oracle tick by tick; the device-resident path may be mixed in."""
+    monkeypatch.setenv("PVE_HOST_ZEROCOPY", zerocopy)
+    B = 2304
+    tabs = synthetic_arrivals(B, 1000, 30.0, seed=8, rows=24)
+    scene = P.make_scene("cuda", B, vm=5)
+    orc = P.make_oracle(B, vm=5, veh_cap=scene.veh_cap, n_threads=32)
+    scene.reset(tabs, warmup=True)
+    orc.reset(tabs, warmup=True)
+    host = scene.make_host_outputs()
+    act = torch.zeros(B, scene.veh_cap, dtype=torch.float32).pin_memory()
+    rng = np.random.RandomState(1)
+    for t in range(90):
+        a = P.random_actions(rng, scene.control_mask().cpu().numpy())
+        act.copy_(torch.from_numpy(a))
+        o_ref = orc.step(a)
+        n = scene.step_host(act, host, copy_obs=True)
+        assert n == int(host.agent_offset[-1]) == len(o_ref["reward"])
+        assert torch.equal(host.obs[:n], scene.out.obs[:n].cpu())          # observations always live on the device too
+        if t % 10 == 0 or t > 85:
+            P.compare_outputs(host_outputs_to_numpy(host, n), o_ref, "host step tick %d" % t)
+        if t == 45:                             # the device-resident path in between must not disturb it
+            a = P.random_actions(rng, scene.control_mask().cpu().numpy())
+            o_ref = orc.step(a)
+            P.compare_outputs(P.outputs_to_numpy(scene.step(P.to_device_actions(scene, a))), o_ref, "mixed")
+    # pageable host actions: staged copy of the actions, same results
+    a = P.random_actions(rng, scene.control_mask().cpu().numpy())
+    o_ref = orc.step(a)
+    n = scene.step_host(torch.from_numpy(a), host, copy_obs=True)
+    P.compare_outputs(host_outputs_to_numpy(host, n), o_ref, "pageable actions")
+    # pageable outputs: staged copies
+    host2 = scene.make_host_outputs(pinned=False)
+    a = P.random_actions(rng, scene.control_mask().cpu().numpy())
+    o_ref = orc.step(a)
+    act.copy_(torch.from_numpy(a))
+    n = scene.step_host(act, host2, copy_obs=True)
+    P.compare_outputs(host_outputs_to_numpy(host2, n), o_ref, "pageable outputs")
+    P.compare_states(scene.get_state(), orc.get_state(), "host path final")
