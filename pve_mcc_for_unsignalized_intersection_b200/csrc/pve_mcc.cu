@@ -112,9 +112,18 @@ static void rt_host_free(void *p) { free(p); }
 
 /* register budget: as many CTAs per SM as the class's shared memory admits (8 for 128/80, 7 for
  * 128/96), counted in 128-thread units */
+#ifndef PVE_MAX_RESIDENT
+#define PVE_MAX_RESIDENT 8     /* experiment knob: cap on the CTAs per SM the register budget is sized for */
+#endif
+template <int VC, int AC>
+struct PveResident {
+    static constexpr int BY_SMEM = 233472 / (int)(PveLayout<VC, AC>::BYTES + 1024);
+    static constexpr int CTAS128 = BY_SMEM < PVE_MAX_RESIDENT ? BY_SMEM : PVE_MAX_RESIDENT;     /* in 128-thread units */
+    /* 96-thread CTAs (3 warps): as many as shared memory admits, which leaves up to 85 registers per thread */
+    static constexpr int blocks(int nt) { return nt == 96 ? BY_SMEM : (CTAS128 * 128 / nt > 0 ? CTAS128 * 128 / nt : 1); }
+};
 template <int NT, int VC, int AC>
-__global__ void __launch_bounds__(NT, (((233472 / (PveLayout<VC, AC>::BYTES + 1024)) < 8 ? (233472 / (PveLayout<VC, AC>::BYTES + 1024)) : 8) * 128) / NT > 0
-                                          ? (((233472 / (PveLayout<VC, AC>::BYTES + 1024)) < 8 ? (233472 / (PveLayout<VC, AC>::BYTES + 1024)) : 8) * 128) / NT : 1)
+__global__ void __launch_bounds__(NT, PveResident<VC, AC>::blocks(NT))
 pve_step_kernel(const PveParams P, const PveState S, const pve_outputs O, const int32_t *spawn_tick,
                 const float *actions, const int phase) {
     extern __shared__ __align__(16) unsigned char pve_smem[];
@@ -346,6 +355,7 @@ static int32_t launch_step(pve_scene *s, const float *actions, const pve_outputs
     if (!done && VCc == vc && ACc == ac) {                                                     \
         done = true;                                                                           \
         if (s->threads == 64) RT_CHECK(s, (launch_one<64, vc, ac>(s, actions, O, stream)));    \
+        else if (s->threads == 96) RT_CHECK(s, (launch_one<96, vc, ac>(s, actions, O, stream))); \
         else if (s->threads == 256) RT_CHECK(s, (launch_one<256, vc, ac>(s, actions, O, stream))); \
         else RT_CHECK(s, (launch_one<128, vc, ac>(s, actions, O, stream)));                    \
     }
@@ -465,9 +475,9 @@ int32_t pve_create(const pve_config *cfg, int32_t device, pve_scene **out) {
     s->threads = cfg->threads == 0 ? 128 : cfg->threads;
     if (const char *pad = getenv("PVE_SMEM_PAD")) s->smem_pad = (size_t)atoi(pad);
     s->host_zerocopy = 1;
-    if (const char *zc = getenv("PVE_HOST_ZEROCOPY")) s->host_zerocopy = atoi(zc) != 0;
-    if (s->threads != 64 && s->threads != 128 && s->threads != 256) {
-        snprintf(s->err, sizeof s->err, "threads must be 0, 64, 128 or 256");
+    if (const char *zc = getenv("PVE_HOST_ZEROCOPY")) s->host_zerocopy = atoi(zc);
+    if (s->threads != 64 && s->threads != 96 && s->threads != 128 && s->threads != 256) {
+        snprintf(s->err, sizeof s->err, "threads must be 0, 64, 96, 128 or 256");
         return PVE_EINVAL;
     }
     PveParams &P = s->prm;
@@ -642,7 +652,7 @@ int32_t pve_step_host(pve_scene *s, const float *actions_host, const pve_outputs
     pve_outputs O = *out_dev;
     bool mirrored = false;
 #ifndef PVE_HOST_EMULATION
-    if (s->host_zerocopy && is_pinned_host(actions_host)) act_for_kernel = actions_host;
+    if (s->host_zerocopy == 1 && is_pinned_host(actions_host)) act_for_kernel = actions_host;   /* 2: outputs only */
     if (s->host_zerocopy && out_host && (copy_mask & 1)) {
         const void *f[9] = {out_host->agent_offset, out_host->reward, out_host->ids, out_host->cpv, out_host->status,
                             out_host->jerk_sum, out_host->env_collisions, out_host->env_lock, out_host->env_removed};

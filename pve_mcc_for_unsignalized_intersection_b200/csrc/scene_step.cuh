@@ -855,7 +855,7 @@ PVE_DEV void pve_step_block(const PveParams &P, const PveState &S, const pve_out
 
     /* ---- CTA split: the upper half of the CTA moves the observation rows (everything they need is
      *      final after G1) while the lower half ("team") finishes the tick ------------------------ */
-    constexpr int NS = (NT >= 128) ? NT / 2 : NT;
+    constexpr int NS = (NT >= 128) ? NT / 2 : (NT == 96 ? 64 : NT);      /* 96: two team warps, one mover warp */
     PveRowJob RJ;
     RJ.A = A; RJ.srcc = srcc; RJ.rows_smem = row0; RJ.rows_prev = row0_prev_base; RJ.oblk = oblk; RJ.zero_row = AC;
 #ifdef __CUDACC__

@@ -16,7 +16,7 @@ def test_backend_is_cuda():
     assert torch.cuda.get_device_capability(0)[0] == 10
 
 
-@pytest.mark.parametrize("threads", [64, 128, 256])
+@pytest.mark.parametrize("threads", [64, 96, 128, 256])
 def test_free_running_matches_oracle(threads):
     tabs = np.concatenate([synthetic_arrivals(4, lam, 50.0, seed=lam, rows=40) for lam in (400, 1000, 1200)])
     B = tabs.shape[0]
