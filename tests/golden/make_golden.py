@@ -332,16 +332,31 @@ def crafted(mod):
     print("crafted.npz %.0f KB" % (os.path.getsize(path) / 1024))
 
 
-def main():
+SPECS = {
+    # name: (table factory, ticks, policy, vm, seed) -- every shipped .mat fixture is covered
+    "mat1000_vm5": (lambda: mat_table(1000, 40), 560, "uniform", 5, 11),
+    "mat1200_vm6": (lambda: mat_table(1200, 40), 420, "uniform", 6, 12),
+    "mat200_vm5": (lambda: mat_table(200, 12), 700, "uniform", 5, 13),
+    "stress_brake": (lambda: stress_arrivals(1, 40.0)[0], 330, "brake", 5, 14),
+    "synth1000_accel": (lambda: synthetic_arrivals(1, 1000, 60.0, seed=5)[0], 420, "accel", 5, 15),
+    "synth800_mixed": (lambda: synthetic_arrivals(1, 800, 70.0, seed=6)[0], 520, "mixed", 6, 16),
+    "mat400_vm6": (lambda: mat_table(400, 16), 520, "mixed", 6, 17),
+    "mat600_vm5": (lambda: mat_table(600, 20), 460, "uniform", 5, 18),
+    "mat800_vm6": (lambda: mat_table(800, 28), 440, "uniform", 6, 19),
+    "mat900_vm5": (lambda: mat_table(900, 30), 440, "accel", 5, 20),
+}
+
+
+def main(names):
+    """``python make_golden.py``: everything; ``python make_golden.py name ...``: only those rollouts
+    (``crafted`` = the crafted single-tick cases)."""
     mod = load_reference()
-    rollout(mod, "mat1000_vm5", mat_table(1000, 40), 560, "uniform", vm=5, seed=11)
-    rollout(mod, "mat1200_vm6", mat_table(1200, 40), 420, "uniform", vm=6, seed=12)
-    rollout(mod, "mat200_vm5", mat_table(200, 12), 700, "uniform", vm=5, seed=13)
-    rollout(mod, "stress_brake", stress_arrivals(1, 40.0)[0], 330, "brake", vm=5, seed=14)
-    rollout(mod, "synth1000_accel", synthetic_arrivals(1, 1000, 60.0, seed=5)[0], 420, "accel", vm=5, seed=15)
-    rollout(mod, "synth800_mixed", synthetic_arrivals(1, 800, 70.0, seed=6)[0], 520, "mixed", vm=6, seed=16)
-    crafted(mod)
+    for name, (table, ticks, policy, vm, seed) in SPECS.items():
+        if not names or name in names:
+            rollout(mod, name, table(), ticks, policy, vm=vm, seed=seed)
+    if not names or "crafted" in names:
+        crafted(mod)
 
 
 if __name__ == "__main__":
-    main()
+    main(sys.argv[1:])
