@@ -18,7 +18,7 @@
 #include <new>
 
 #include "scene_step.cuh"
-#include "actor.cuh"
+#include "actor_mma.cuh"
 
 #ifndef PVE_HOST_EMULATION
 #include <cuda_runtime.h>
@@ -764,10 +764,12 @@ int32_t pve_stats(pve_scene *s, pve_counters *out_dev, void *stream_) {
 
 /* ---- actor (N1) ---------------------------------------------------------------------------- */
 struct pve_actor {
-    float *w_dev;
+    float *w_dev;                /* flat fp32 parameters (FFMA kernel) */
+    uint32_t *pw_dev;            /* split bf16 fragments + vectors (tensor-core kernel) */
     int *ticket;                 /* [2] work counter + exit counter of the kernel, zero between launches */
     int device;
-    int blocks;
+    int blocks_ffma, blocks_mma; /* one resident wave of CTAs each */
+    int use_mma;                 /* default 1; env PVE_ACTOR_IMPL=ffma selects the CUDA-core kernel */
 };
 
 int32_t pve_actor_create(const float *weights_host, int32_t n_floats, int32_t device, pve_actor **out) {
@@ -780,18 +782,32 @@ int32_t pve_actor_create(const float *weights_host, int32_t n_floats, int32_t de
     pve_actor *a = (pve_actor *)calloc(1, sizeof(pve_actor));
     if (!a) return PVE_ENOMEM;
     a->device = device;
-    int sms = 0;
+    a->use_mma = 1;
+    if (const char *impl = getenv("PVE_ACTOR_IMPL")) a->use_mma = strcmp(impl, "ffma") != 0;
+    int sms = 0, per_sm = 0;
     if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device) != cudaSuccess || sms <= 0) sms = 148;
-    a->blocks = 3 * sms;                     /* __launch_bounds__(128, 3): one resident wave, CTAs loop over chunks */
-    if (cudaFuncSetAttribute(pve_actor_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PVA_SMEM_BYTES) != cudaSuccess) {
-        free(a); return PVE_ECUDA;
+    bool ok = cudaFuncSetAttribute(pve_actor_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PVA_SMEM_BYTES) == cudaSuccess
+              && cudaFuncSetAttribute(pve_actor_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PVM_SMEM_BYTES) == cudaSuccess;
+    if (ok) {
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pve_actor_kernel, PVA_THREADS, PVA_SMEM_BYTES) != cudaSuccess || per_sm < 1) per_sm = 1;
+        a->blocks_ffma = per_sm * sms;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pve_actor_mma_kernel, PVM_THREADS, PVM_SMEM_BYTES) != cudaSuccess || per_sm < 1) per_sm = 1;
+        a->blocks_mma = per_sm * sms;
     }
-    if (cudaMalloc((void **)&a->w_dev, sizeof(float) * PVE_ACTOR_FLOATS) != cudaSuccess) { free(a); return PVE_ENOMEM; }
-    if (cudaMemcpy(a->w_dev, weights_host, sizeof(float) * PVE_ACTOR_FLOATS, cudaMemcpyHostToDevice) != cudaSuccess) {
-        cudaFree(a->w_dev); free(a); return PVE_ECUDA;
-    }
-    if (cudaMalloc((void **)&a->ticket, 2 * sizeof(int)) != cudaSuccess || cudaMemset(a->ticket, 0, 2 * sizeof(int)) != cudaSuccess) {
-        cudaFree(a->w_dev); free(a); return PVE_ENOMEM;
+    uint32_t *packed = ok ? (uint32_t *)malloc(sizeof(uint32_t) * PVM_WORDS) : nullptr;
+    ok = ok && packed;
+    if (ok) pvm_pack(weights_host, packed);
+    ok = ok && cudaMalloc((void **)&a->w_dev, sizeof(float) * PVE_ACTOR_FLOATS) == cudaSuccess
+            && cudaMalloc((void **)&a->pw_dev, sizeof(uint32_t) * PVM_WORDS) == cudaSuccess
+            && cudaMalloc((void **)&a->ticket, 2 * sizeof(int)) == cudaSuccess
+            && cudaMemcpy(a->w_dev, weights_host, sizeof(float) * PVE_ACTOR_FLOATS, cudaMemcpyHostToDevice) == cudaSuccess
+            && cudaMemcpy(a->pw_dev, packed, sizeof(uint32_t) * PVM_WORDS, cudaMemcpyHostToDevice) == cudaSuccess
+            && cudaMemset(a->ticket, 0, 2 * sizeof(int)) == cudaSuccess;
+    free(packed);
+    if (!ok) {
+        cudaFree(a->w_dev); cudaFree(a->pw_dev); cudaFree(a->ticket); free(a);
+        cudaGetLastError();
+        return PVE_ECUDA;
     }
     *out = a;
     return PVE_OK;
@@ -802,10 +818,28 @@ void pve_actor_destroy(pve_actor *a) {
     if (!a) return;
 #ifndef PVE_HOST_EMULATION
     cudaFree(a->w_dev);
+    cudaFree(a->pw_dev);
     cudaFree(a->ticket);
 #endif
     free(a);
 }
+
+#ifndef PVE_HOST_EMULATION
+static cudaError_t launch_actor(pve_actor *a, const float *rows, const pve_veh_meta *meta, const int32_t *n_veh,
+                                const float *noise, float noise_scale, float *actions, int slots_per_env, int n_env,
+                                long long n_slots, pve_stream_t stream) {
+    if (a->use_mma) {
+        const int blocks = n_env < a->blocks_mma ? n_env : a->blocks_mma;
+        pve_actor_mma_kernel<<<blocks, PVM_THREADS, PVM_SMEM_BYTES, stream>>>(a->pw_dev, rows, meta, n_veh, noise, noise_scale,
+                                                                           actions, slots_per_env, n_env, n_slots, a->ticket);
+    } else {
+        const int blocks = n_env < a->blocks_ffma ? n_env : a->blocks_ffma;
+        pve_actor_kernel<<<blocks, PVA_THREADS, PVA_SMEM_BYTES, stream>>>(a->w_dev, rows, meta, n_veh, noise, noise_scale,
+                                                                       actions, slots_per_env, n_env, n_slots, a->ticket);
+    }
+    return cudaGetLastError();
+}
+#endif
 
 int32_t pve_actor_forward(pve_actor *a, const float *rows_dev, int64_t n_rows, float *actions_dev, void *stream_) {
     if (!a || !rows_dev || !actions_dev || n_rows < 0) return PVE_EINVAL;
@@ -814,12 +848,10 @@ int32_t pve_actor_forward(pve_actor *a, const float *rows_dev, int64_t n_rows, f
     return PVE_ESTATE;
 #else
     if (n_rows == 0) return PVE_OK;
-    const long long groups = (n_rows + PVA_TILE - 1) / PVA_TILE;             /* "intersections" of 128 rows */
     if (n_rows > 0x7fffffffLL) return PVE_EINVAL;             /* slot indices are queued as 32-bit */
-    const int blocks = groups < a->blocks ? (int)groups : a->blocks;
-    pve_actor_kernel<<<blocks, PVA_THREADS, PVA_SMEM_BYTES, (pve_stream_t)stream_>>>(
-        a->w_dev, rows_dev, nullptr, nullptr, nullptr, 0.f, actions_dev, PVA_TILE, (int)groups, (long long)n_rows, a->ticket);
-    return cudaGetLastError() == cudaSuccess ? PVE_OK : PVE_ECUDA;
+    const long long groups = (n_rows + PVA_TILE - 1) / PVA_TILE;             /* "intersections" of 128 rows */
+    return launch_actor(a, rows_dev, nullptr, nullptr, nullptr, 0.f, actions_dev, PVA_TILE, (int)groups, (long long)n_rows,
+                        (pve_stream_t)stream_) == cudaSuccess ? PVE_OK : PVE_ECUDA;
 #endif
 }
 
@@ -836,11 +868,8 @@ int32_t pve_act(pve_scene *s, pve_actor *a, const float *noise_dev, float noise_
         return PVE_EINVAL;
     }
     const int B = s->cfg.n_envs, VCc = s->prm.VC;
-    const int blocks = B < a->blocks ? B : a->blocks;
-    pve_actor_kernel<<<blocks, PVA_THREADS, PVA_SMEM_BYTES, (pve_stream_t)stream_>>>(
-        a->w_dev, pve_row0_dev(s), s->st.meta, s->st.n_veh, noise_dev, noise_scale, actions_dev, VCc, B,
-        (long long)B * (long long)VCc, a->ticket);
-    RT_CHECK(s, cudaGetLastError());
+    RT_CHECK(s, launch_actor(a, pve_row0_dev(s), s->st.meta, s->st.n_veh, noise_dev, noise_scale, actions_dev, VCc, B,
+                             (long long)B * (long long)VCc, (pve_stream_t)stream_));
     return PVE_OK;
 #endif
 }
