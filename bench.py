@@ -359,8 +359,9 @@ def graft_arm(args, rank, world, local_rank):
             line["actor"] = {"kernel": "pve_actor_kernel", "kernel_ms_per_launch": float(sum(actor_ms)) / K,
                              "gflop_per_launch": 2 * 5952 * kA / K / 1e9,
                              "tflops": 2 * 5952 * kA / (float(sum(actor_ms)) * 1e-3) / 1e12,
-                             "note": "fp32 FFMA (the reference's graph is fp32 and ill-conditioned at 1e-4); "
-                                     "timed alone, inside the same ticks as roofline"}
+                             "note": "tensor cores, bf16 x 3 split-precision products (fp32-equivalent: the reference's "
+                                     "graph is fp32 and ill-conditioned at 1e-4); tflops counts the network's fp32 "
+                                     "multiply-adds once; timed alone with a cold L2, inside the same ticks as roofline"}
         if e2e:
             line["e2e"] = {"value": e2e_rows / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(e2e["h2d"]),
                            "d2h_bytes_per_step": int(e2e["d2h"]),

@@ -34,7 +34,14 @@ def check_actions(got, rows32, w, what):
     assert np.all(np.abs(got) <= 3.0)
 
 
-def test_actor_kernel_on_recorded_rows():
+@pytest.fixture(params=["mma", "ffma"])
+def impl(request, monkeypatch):
+    """Both device implementations of the actor: tensor cores (bf16 x 3 split products, default) and fp32 FFMA."""
+    monkeypatch.setenv("PVE_ACTOR_IMPL", request.param)
+    return request.param
+
+
+def test_actor_kernel_on_recorded_rows(impl):
     z = np.load(os.path.join(GOLD, "actor_rollout_mat1000.npz"))
     w = ActorWeights.from_npz(os.path.join(GOLD, "actor_agent1.npz"))
     actor = BatchedActor(w)
@@ -44,7 +51,7 @@ def test_actor_kernel_on_recorded_rows():
 
 
 @pytest.mark.parametrize("n", [1, 31, 32, 33, 1000, 70001])
-def test_actor_kernel_shapes_and_edge_rows(n):
+def test_actor_kernel_shapes_and_edge_rows(n, impl):
     w = ActorWeights.from_npz(os.path.join(GOLD, "actor_agent1.npz"))
     actor = BatchedActor(w)
     rng = np.random.RandomState(n)
@@ -62,7 +69,7 @@ def test_actor_kernel_shapes_and_edge_rows(n):
     check_actions(got, rows, w, "n=%d" % n)
 
 
-def test_random_initialised_actor():
+def test_random_initialised_actor(impl):
     w = ActorWeights.random(5)
     actor = BatchedActor(w)
     rows = (np.random.RandomState(1).randn(500, 28) * 30).astype(np.float32)
@@ -70,7 +77,7 @@ def test_random_initialised_actor():
     check_actions(got, rows, w, "random init")
 
 
-def test_act_on_scene_matches_forward_and_masks():
+def test_act_on_scene_matches_forward_and_masks(impl):
     """pve_act: the policy on the stored row 0 of controlled vehicles, 0 elsewhere (main.py:398-404)."""
     from pve_mcc_for_unsignalized_intersection_b200.arrivals import synthetic_arrivals
     w = ActorWeights.from_npz(os.path.join(GOLD, "actor_agent1.npz"))
