@@ -177,7 +177,7 @@ struct PveLayout {
     static_assert(VC % 16 == 0 && AC % 16 == 0 && AC <= VC && VC <= 1024, "capacity class");
 };
 
-enum { M_V = 0, M_NREM, M_PASSED, M_COLL, M_LOCK, M_NCTRL, M_Q5U, M_PSTEP, M_COLLAG, M_OUTOK, M_IDSEQ0,
+enum { M_V = 0, M_NREM, M_PASSED, M_COLL, M_LOCK, M_NCTRL, M_Q5U, M_PSTEP, M_COLLAG, M_IDSEQ0,
        M_SPAWN0 /* 12 */, M_SPREF0 = M_SPAWN0 + 12 /* 13 */, M_NEXT0 = M_SPREF0 + 13 /* 12 */,
        M_COUNT = M_NEXT0 + 12 };
 static_assert(M_COUNT <= 56, "misc block");
@@ -210,16 +210,6 @@ PVE_DEV uint32_t pve_isneg(double x) {
     uint64_t u; memcpy(&u, &x, sizeof u); return (uint32_t)(u >> 63);
 #endif
 }
-/* read back data this CTA wrote to global memory earlier in the kernel: L2, not L1 */
-#ifdef __CUDACC__
-PVE_DEV pve_v4 pve_ld_l2(const pve_v4 *p) {
-    const uint4 v = __ldcg(reinterpret_cast<const uint4 *>(p));
-    pve_v4 r; r.x = v.x; r.y = v.y; r.z = v.z; r.w = v.w; return r;
-}
-#else
-PVE_DEV pve_v4 pve_ld_l2(const pve_v4 *p) { return *p; }
-#endif
-
 /* ---------------------------------------------------------------------------------------------
  * block collectives.  Device: warp ballot / shuffle + one smem exchange.  Host emulation:
  * sequential loops over the same shared arrays.
