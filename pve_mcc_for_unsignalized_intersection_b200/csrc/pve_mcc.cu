@@ -485,6 +485,7 @@ int32_t pve_create(const pve_config *cfg, int32_t device, pve_scene **out) {
     P.dt = cfg->dt; P.dt2 = cfg->dt2; P.vm = cfg->vm; P.vM = cfg->vM; P.am = cfg->am; P.aM = cfg->aM;
     P.v0 = cfg->v0; P.thr = cfg->collision_thr; P.lane_in = cfg->lane_in; P.remove_p = cfg->remove_p;
     P.lane_cw = cfg->lane_cw; P.abs_am = fabs(cfg->am); P.two_abs_am = 2 * fabs(cfg->am);     /* TIS:1513-1514 */
+    P.r_abs_am = 1.0 / P.abs_am; P.r_two_abs_am = 1.0 / P.two_abs_am;
     P.aspan = (double)(cfg->aM - cfg->am);                                                     /* TIS:319 */
     for (int m = 0; m < 3; ++m) { P.lane_len[m] = cfg->lane_len[m]; P.spawn_p[m] = cfg->lane_in + cfg->lane_len[m]; }  /* TIS:395 */
     memcpy(P.vd_a1, cfg->vd_a1, sizeof P.vd_a1); memcpy(P.vd_a2, cfg->vd_a2, sizeof P.vd_a2);

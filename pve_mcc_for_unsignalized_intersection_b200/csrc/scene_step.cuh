@@ -78,6 +78,7 @@ struct alignas(16) pve_v4 { uint32_t x, y, z, w; };
 /* kernel parameters (by value; lives in the constant bank) */
 struct PveParams {
     double dt, dt2, vm, vM, am, aM, v0, thr, lane_in, remove_p, lane_cw, abs_am, two_abs_am, aspan;
+    double r_abs_am, r_two_abs_am;      /* reciprocals, used only to pre-screen the rear-end test (phase B) */
     double lane_len[3];
     double spawn_p[3];
     double vd_a1[2][4], vd_a2[2][4], vd_b[2][4];
@@ -601,9 +602,16 @@ PVE_DEV void pve_step_block(const PveParams &P, const PveState &S, const pve_out
                     const double vf = s ? cv1[k - 1] : cv0[k - 1];
                     const double pf = s ? cp1[k - 1] : cp0[k - 1];
                     if (vf < v) {
-                        const double d_safe = v * 0.4 + (v * v - vf * vf) / P.two_abs_am
-                                              - (v - vf) * P.vm / P.abs_am;     /* TIS:1512-1514 */
-                        if (p - pf < d_safe) f |= (1 << s);                      /* TIS:1515 */
+                        /* TIS:1512-1515 decide p - pf < d_safe.  The two float64 divisions are only needed when the
+                         * margin is within 1e-9 of zero: a reciprocal-multiply estimate (error < 1e-12 at these
+                         * magnitudes) settles every other case with the same outcome. */
+                        const double gap = p - pf, dv2 = v * v - vf * vf, dvm = (v - vf) * P.vm;
+                        const double est = v * 0.4 + dv2 * P.r_two_abs_am - dvm * P.r_abs_am;
+                        bool fire;
+                        if (gap < est - 1.0e-9) fire = true;
+                        else if (gap > est + 1.0e-9) fire = false;
+                        else fire = gap < v * 0.4 + dv2 / P.two_abs_am - dvm / P.abs_am;
+                        if (fire) f |= (1 << s);
                     }
                 }
             }
