@@ -47,6 +47,9 @@ VEH_CAP, AGENT_CAP = 128, int(os.environ.get("PVE_BENCH_AGENT_CAP", "96"))
 BYTES_PER_VEH, BYTES_PER_AGENT = 68, 1028        # SURVEY.md 8(d) / BASELINE.md section 4
 
 
+TRAIN_GAMMA = 0.8766832904447475          # main.py:227 at epoch 20: tanh(26 / 12) * 0.9
+
+
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -56,9 +59,10 @@ def parse():
     ap.add_argument("--envs", type=int, default=ENVS_PER_GPU, help="intersections per GPU")
     ap.add_argument("--density", type=int, default=DENSITY)
     ap.add_argument("--threads", type=int, default=0, help="CTA size override (64/128/256)")
-    ap.add_argument("--workload", default="poisson", choices=["poisson", "stress", "rollout"],
+    ap.add_argument("--workload", default="poisson", choices=["poisson", "stress", "rollout", "train"],
                     help="poisson: BASELINE config 2 (default); stress: config 4; rollout: config 5 = the pretrained "
-                         "actor evaluated on the GPU every tick + the environment step")
+                         "actor evaluated on the GPU every tick + the environment step; train: rollout + the training "
+                         "loop's n-step return folding and replay writer (main.py:243-266) on the GPU every tick")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     return ap.parse_args()
@@ -67,6 +71,10 @@ def parse():
 def workload_name(args):
     if args.workload == "stress":
         return "stress: headway 1.0 s on all 12 lanes, all-brake policy, %d intersections per GPU" % args.envs
+    if args.workload == "train":
+        return ("training rollout: %d intersections per GPU, synthetic Poisson arrivals %d veh/h/lane, pretrained actor "
+                "+ environment step + n-step folding (seq_max_step 12, target actor on 7 rows per agent, target critic) "
+                "+ replay writer (500 000 records) on the GPU every tick, vm=5" % (args.envs, args.density))
     if args.workload == "rollout":
         return ("full rollout: %d intersections per GPU, synthetic Poisson arrivals %d veh/h/lane, actions from the "
                 "reference's pretrained actor evaluated on the GPU every tick (tests/golden/actor_agent1.npz), vm=5"
@@ -195,7 +203,7 @@ def graft_arm(args, rank, world, local_rank):
     veh_cap, agent_cap = (384, 320) if stress else (VEH_CAP, AGENT_CAP)
     horizon = (PRIME_TICKS + 3 * (K + W) + 50) * 0.1 + 30.0
     tabs = make_tables(args, B, 1000 + rank, horizon)
-    rollout = args.workload == "rollout"
+    rollout = args.workload in ("rollout", "train")
     scene = BatchedScene(B, SceneConfig(vm=5 if (stress or rollout) else VM), veh_cap=veh_cap, agent_cap=agent_cap,
                          device=dev, threads=args.threads)
     scene.reset(tabs, warmup=True)
@@ -204,6 +212,15 @@ def graft_arm(args, rank, world, local_rank):
         from pve_mcc_for_unsignalized_intersection_b200.actor import ActorWeights, BatchedActor
         actor = BatchedActor(ActorWeights.from_npz(os.path.join(ROOT, "tests", "golden", "actor_agent1.npz")), device=dev)
         act_buf = torch.empty(B, veh_cap, dtype=torch.float32, device=dev)
+    folder = None
+    if args.workload == "train":
+        from pve_mcc_for_unsignalized_intersection_b200.nstep import BatchedCritic, CriticWeights, NStepFolder
+        with np.load(os.path.join(ROOT, "tests", "golden", "nstep_nets.npz")) as z:
+            t_actor = BatchedActor(ActorWeights({k[len("actor__"):].replace("__", "/"): z[k] for k in z.files
+                                                 if k.startswith("actor__")}), device=dev)
+            t_critic = BatchedCritic(CriticWeights({k[len("critic__"):].replace("__", "/"): z[k] for k in z.files
+                                                    if k.startswith("critic__")}), device=dev)
+        folder = NStepFolder(scene, t_actor, t_critic, seq_max_step=12, buffer_size=500000)      # main.py:91, 212
     gen = torch.Generator(device=dev)
     gen.manual_seed(99 + rank)
     if stress:
@@ -218,8 +235,15 @@ def graft_arm(args, rank, world, local_rank):
             return actor.act(scene, out=act_buf)
         return pool[t % len(pool)]
 
+    def tick(a):
+        """One tick of the workload: the environment step and, for `train`, main.py:243-266 on its outputs."""
+        out = scene.step(a)
+        if folder is not None:
+            folder.push(out, TRAIN_GAMMA)
+        return out
+
     for t in range(PRIME_TICKS):
-        scene.step(actions(t))
+        tick(actions(t))
     torch.cuda.synchronize()
 
     def barrier():
@@ -234,7 +258,7 @@ def graft_arm(args, rank, world, local_rank):
     # around the step kernel (pve_set_profiling -> roofline.achieved).
     for t in range(W):
         flush.fill_(t & 0xFF)
-        scene.step(actions(t))
+        tick(actions(t))
     s0 = scene.stats()
     sampler = ClockSampler(local_rank)
     sampler.start()
@@ -244,7 +268,7 @@ def graft_arm(args, rank, world, local_rank):
     for t in range(K):                         # the K timed ticks -> value
         flush.fill_(t & 0xFF)                  # L2 flush between timed iterations (not timed)
         ev[t][0].record()
-        scene.step(actions(t))
+        tick(actions(t))
         ev[t][1].record()
     barrier()
     wall1 = time.perf_counter()
@@ -258,18 +282,27 @@ def graft_arm(args, rank, world, local_rank):
     kern_ms = []
     actor_ms = []
     aev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+    fev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+    fold_ms = []
     for t in range(K):
         flush.fill_(t & 0xFF)
         if actor is not None:                  # the policy kernel of this tick, timed on its own
             aev[0].record()
             a = actions(K + t)
             aev[1].record()
-            scene.step(a)
+            out = scene.step(a)
+            if folder is not None:             # the folding of this tick, timed on its own
+                fev[0].record()
+                folder.push(out, TRAIN_GAMMA)
+                fev[1].record()
         else:
             scene.step(actions(K + t))
         kern_ms.append(scene.kernel_ms()[0])   # waits for this tick's kernel
         if actor is not None:
             actor_ms.append(aev[0].elapsed_time(aev[1]))
+        if folder is not None:
+            torch.cuda.synchronize()
+            fold_ms.append(fev[0].elapsed_time(fev[1]))
     scene.set_profiling(False)
     sampler.stop_flag = True
     s2 = scene.stats()
@@ -346,7 +379,8 @@ def graft_arm(args, rank, world, local_rank):
                          "kernel": "pve_step_kernel", "kernel_ms_per_launch": my_kern_ms / K,
                          "algorithmic_bytes_per_launch": alg_bytes / K},
             # kernels inside the timed region of `value`: one step kernel per tick (+ one actor kernel in a rollout)
-            "gpu_launches": K * (2 if actor is not None else 1),
+            # (+ target actor, critic, plan, scan, fold in a training rollout)
+            "gpu_launches": K * ((7 if folder is not None else 2) if actor is not None else 1),
             "clocks": sampler.result(),
             "stats": {k: float(v) for k, v in zip(
                 ["agent_steps", "vehicle_steps", "env_steps", "spawned", "passed", "passed_step_total",
@@ -362,6 +396,17 @@ def graft_arm(args, rank, world, local_rank):
                              "note": "tensor cores, bf16 x 3 split-precision products (fp32-equivalent: the reference's "
                                      "graph is fp32 and ill-conditioned at 1e-4); tflops counts the network's fp32 "
                                      "multiply-adds once; timed alone with a cold L2, inside the same ticks as roofline"}
+        if folder is not None:
+            fc = folder.counters()
+            # per agent row: 784 B observation in + 784 B frame out; per record: 2 x 784 B frames in, 2 x 784 + 36 B out
+            fold_bytes = (1568 * kA + 3172 * kA) / K
+            line["nstep"] = {"kernels": "pve_actor_mma_kernel (7 rows per agent) + pve_critic_kernel + pvn_plan/scan/fold",
+                             "ms_per_push": float(sum(fold_ms)) / K, "seq_max_step": 12, "gamma": TRAIN_GAMMA,
+                             "num_experiences": fc["num_experiences"], "records_last_push": fc["last_added"],
+                             "slot_conflicts": fc["slot_conflicts"], "replay_capacity": folder.capacity,
+                             "fold_algorithmic_bytes_per_push": fold_bytes,
+                             "note": "timed alone with a cold L2 inside the same ticks as roofline; the bootstrap runs "
+                                     "the target actor on all 7 rows of every agent's observation like main.py:253-255"}
         if e2e:
             line["e2e"] = {"value": e2e_rows / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(e2e["h2d"]),
                            "d2h_bytes_per_step": int(e2e["d2h"]),

@@ -194,6 +194,59 @@ int32_t pve_actor_forward(pve_actor *a, const float *rows_dev, int64_t n_rows, f
 int32_t pve_act(pve_scene *s, pve_actor *a, const float *noise_dev, float noise_scale, float *actions_dev,
                 void *stream);
 
+/* device-side row count: like pve_actor_forward for the first min(max_rows, n_rows_dev[0] * mult) rows of a dense
+ * matrix; nothing is read back (used on the 7 rows of every agent's observation: mult = 7, n_rows_dev =
+ * &agent_offset[B]) */
+int32_t pve_actor_forward_n(pve_actor *a, const float *rows_dev, int64_t max_rows, const int32_t *n_rows_dev,
+                            int32_t mult, float *actions_dev, void *stream);
+
+/* ---- n-step return folding + replay writer --------------------------------
+ * Replaces the per-vehicle bookkeeping of the training loop, main.py:243-266, and ReplayBuffer.add with
+ * rand_s=True (replay_buffer.py:45-53), for all intersections of a handle at once.
+ *
+ * Critic = agent_ddpg_target.Q (model_agent_maddpg.py:52-76, 123-125: LN28 -> Dense64 -> LN -> ReLU ->
+ * concat(action, 6 other actions) -> Dense64 -> LN -> ReLU -> Dense1, fp32).  `weights_host`: PVE_CRITIC_FLOATS
+ * floats in this order: LayerNorm gamma[28], beta[28]; dense kernel[28][64], bias[64]; LayerNorm_1 gamma[64],
+ * beta[64]; dense_1 kernel[71][64], bias[64]; LayerNorm_2 gamma[64], beta[64]; dense_2 kernel[64], bias[1]. */
+#define PVE_CRITIC_FLOATS 6841
+typedef struct pve_critic pve_critic;
+int32_t pve_critic_create(const float *weights_host, int32_t n_floats, int32_t device, pve_critic **out);
+void pve_critic_destroy(pve_critic *c);
+/* q_dev[i] = Q(obs_dev[i][0][0..27], act7_dev[i][0..6]) for i < min(max_rows, n_rows_dev[0]) (n_rows_dev may be
+ * null: all max_rows rows).  obs_dev: [max_rows][7][28] observations, only row 0 is read (main.py:257). */
+int32_t pve_critic_forward(pve_critic *c, const float *obs_dev, const float *act7_dev, int64_t max_rows,
+                           const int32_t *n_rows_dev, float *q_dev, void *stream);
+
+/* The replay memory as device arrays: a ring of `capacity` = buffer_size - 1 records (replay_buffer.py:47-53: the
+ * reference's deque never holds buffer_size items).  The k-th record ever added (k from 0) sits at k % capacity;
+ * the deque, oldest first, is records max(0, N - capacity) .. N - 1 with N = num_experiences. */
+typedef struct pve_replay_view {
+    float *state;        /* [capacity][7][28]  seq_data[0][0]  main.py:263 */
+    float *action;       /* [capacity][7]      seq_data[0][1]              */
+    float *reward;       /* [capacity]         r_target        main.py:250-262 */
+    float *next_state;   /* [capacity][7][28]  seq_data[0][3]              */
+    uint8_t *done;       /* [capacity]         always 0        main.py:264 */
+    int64_t capacity;
+} pve_replay_view;
+
+typedef struct pve_nstep pve_nstep;
+/* n_envs intersections; uid_slots (power of two >= 16, about 2 x the vehicle capacity) history slots per
+ * intersection; seq_max_step = args.seq_max_step (main.py:91, <= 14); out_cap = rows of the per-agent output arrays;
+ * buffer_size = ReplayBuffer(buffer_size, ...) (main.py:212), buffer_size - 1 >= out_cap */
+int32_t pve_nstep_create(int32_t n_envs, int32_t uid_slots, int32_t seq_max_step, int64_t out_cap,
+                         int64_t buffer_size, int32_t device, pve_nstep **out);
+void pve_nstep_destroy(pve_nstep *f);
+/* main.py:243-266 for the tick whose outputs are in `out_dev` (agent_offset, ids, status, obs, reward are read).
+ * The bootstrap term uses the two target networks on this tick's observations.  Asynchronous on `stream`. */
+int32_t pve_nstep_push(pve_nstep *f, const pve_outputs *out_dev, double gamma, pve_actor *target_actor,
+                       pve_critic *target_critic, void *stream);
+int32_t pve_nstep_replay(const pve_nstep *f, pve_replay_view *view);
+/* out_host[0] = num_experiences (replay_buffer.py:47), [1] = records added by the last push, [2] = history slots
+ * claimed while another live vehicle owned them (sticky; must stay 0), [3] = pushes so far.  Synchronises `stream`. */
+int32_t pve_nstep_counters(pve_nstep *f, int64_t *out_host, void *stream);
+/* device pointer of the bootstrap values Q' of the last push ([out_cap], valid for its agent rows) */
+const float *pve_nstep_q_dev(const pve_nstep *f);
+
 #ifdef __cplusplus
 }
 #endif

@@ -39,6 +39,10 @@ class PveOutputs(C.Structure):
                  "env_collisions", "env_lock", "env_removed")]
 
 
+class PveReplayView(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in ("state", "action", "reward", "next_state", "done")] + [("capacity", C.c_int64)]
+
+
 class NativeError(RuntimeError):
     pass
 
@@ -83,6 +87,19 @@ def load_library(path=None):
     lib.pve_actor_destroy.restype = None
     lib.pve_actor_forward.argtypes = [vp, vp, i64, vp, vp]
     lib.pve_act.argtypes = [vp, vp, vp, C.c_float, vp, vp]
+    lib.pve_actor_forward_n.argtypes = [vp, vp, i64, vp, i32, vp, vp]
+    lib.pve_critic_create.argtypes = [vp, i32, i32, C.POINTER(vp)]
+    lib.pve_critic_destroy.argtypes = [vp]
+    lib.pve_critic_destroy.restype = None
+    lib.pve_critic_forward.argtypes = [vp, vp, vp, i64, vp, vp, vp]
+    lib.pve_nstep_create.argtypes = [i32, i32, i32, i64, i64, i32, C.POINTER(vp)]
+    lib.pve_nstep_destroy.argtypes = [vp]
+    lib.pve_nstep_destroy.restype = None
+    lib.pve_nstep_push.argtypes = [vp, C.POINTER(PveOutputs), C.c_double, vp, vp, vp]
+    lib.pve_nstep_replay.argtypes = [vp, C.POINTER(PveReplayView)]
+    lib.pve_nstep_counters.argtypes = [vp, C.POINTER(i64), vp]
+    lib.pve_nstep_q_dev.argtypes = [vp]
+    lib.pve_nstep_q_dev.restype = vp
     if lib.pve_config_bytes() != C.sizeof(PveConfig):
         raise NativeError("pve_config layout mismatch: library %d bytes, binding %d bytes"
                           % (lib.pve_config_bytes(), C.sizeof(PveConfig)))

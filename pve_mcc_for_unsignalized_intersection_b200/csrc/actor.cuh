@@ -47,7 +47,7 @@ static_assert(PVA_COUNT == PVE_ACTOR_FLOATS, "actor parameter count");
 /* The eight hidden units of thread column-group cg are {4 cg .. 4 cg + 3} and {32 + 4 cg .. 32 + 4 cg + 3}: the
  * eight groups of a warp then read 128 contiguous bytes of a weight row per LDS.128 (no bank conflicts).
  * acc[r][c] = bias[u(c)] + sum_k a[16 r + rg][k] * Wm[k][u(c)] */
-template <int K, int R>
+template <int K, int R, int AS = PVA_AS>
 __device__ __forceinline__ void pva_gemm_tile(const float *__restrict__ a, const float *__restrict__ Wm,
                                               const float *__restrict__ bias, float (&acc)[R][8], int rg, int cg) {
     {
@@ -58,13 +58,13 @@ __device__ __forceinline__ void pva_gemm_tile(const float *__restrict__ a, const
             acc[r][4] = b1.x; acc[r][5] = b1.y; acc[r][6] = b1.z; acc[r][7] = b1.w;
         }
     }
-    const float *arow = a + rg * PVA_AS;
+    const float *arow = a + rg * AS;
     const float *wcol = Wm + cg * 4;
 #pragma unroll 1
     for (int k0 = 0; k0 < K; k0 += 4) {
         float4 av[R];
 #pragma unroll
-        for (int r = 0; r < R; ++r) av[r] = *reinterpret_cast<const float4 *>(arow + r * 16 * PVA_AS + k0);
+        for (int r = 0; r < R; ++r) av[r] = *reinterpret_cast<const float4 *>(arow + r * 16 * AS + k0);
 #pragma unroll
         for (int kk = 0; kk < 4; ++kk) {
             const float4 b0 = *reinterpret_cast<const float4 *>(wcol + (k0 + kk) * 64);
@@ -210,8 +210,10 @@ __device__ __forceinline__ void pva_round(const float *__restrict__ w, float *__
 __global__ void __launch_bounds__(PVA_THREADS, 3)
 pve_actor_kernel(const float *__restrict__ W, const float *__restrict__ rows, const pve_veh_meta *__restrict__ meta,
                  const int32_t *__restrict__ n_veh, const float *__restrict__ noise, const float noise_scale,
-                 float *__restrict__ actions, const int slots_per_env, const int n_env, const long long n_slots,
-                 int *__restrict__ ticket) {
+                 float *__restrict__ actions, const int slots_per_env, const int n_env, const long long n_slots_max,
+                 int *__restrict__ ticket, const int32_t *__restrict__ limit_dev, const int limit_mult) {
+    /* device-side row count of a dense matrix (pve_actor_forward_n): rows >= limit_dev[0] * limit_mult are skipped */
+    const long long n_slots = limit_dev ? min(n_slots_max, (long long)limit_dev[0] * limit_mult) : n_slots_max;
     extern __shared__ __align__(16) unsigned char pva_smem[];
     float *const w = reinterpret_cast<float *>(pva_smem);                        /* [PVA_WPAD] parameters */
     float *const a = w + PVA_WPAD;                                               /* [PVA_TILE][PVA_AS] activations */

@@ -244,8 +244,10 @@ __device__ __forceinline__ void pvm_warp_round(const uint32_t *__restrict__ pw, 
 __global__ void __launch_bounds__(PVM_THREADS, 2)
 pve_actor_mma_kernel(const uint32_t *__restrict__ PW, const float *__restrict__ rows, const pve_veh_meta *__restrict__ meta,
                      const int32_t *__restrict__ n_veh, const float *__restrict__ noise, const float noise_scale,
-                     float *__restrict__ actions, const int slots_per_env, const int n_env, const long long n_slots,
-                     int *__restrict__ ticket) {
+                     float *__restrict__ actions, const int slots_per_env, const int n_env, const long long n_slots_max,
+                     int *__restrict__ ticket, const int32_t *__restrict__ limit_dev, const int limit_mult) {
+    /* device-side row count of a dense matrix (pve_actor_forward_n): rows >= limit_dev[0] * limit_mult are skipped */
+    const long long n_slots = limit_dev ? min(n_slots_max, (long long)limit_dev[0] * limit_mult) : n_slots_max;
     extern __shared__ __align__(16) unsigned char pvm_smem[];
     uint32_t *const pw = reinterpret_cast<uint32_t *>(pvm_smem);
     float *const a = reinterpret_cast<float *>(pw + PVM_WORDS);

@@ -19,6 +19,7 @@
 
 #include "scene_step.cuh"
 #include "actor_mma.cuh"
+#include "nstep.cuh"
 
 #ifndef PVE_HOST_EMULATION
 #include <cuda_runtime.h>
@@ -828,15 +829,15 @@ void pve_actor_destroy(pve_actor *a) {
 #ifndef PVE_HOST_EMULATION
 static cudaError_t launch_actor(pve_actor *a, const float *rows, const pve_veh_meta *meta, const int32_t *n_veh,
                                 const float *noise, float noise_scale, float *actions, int slots_per_env, int n_env,
-                                long long n_slots, pve_stream_t stream) {
+                                long long n_slots, pve_stream_t stream, const int32_t *limit_dev = nullptr, int limit_mult = 1) {
     if (a->use_mma) {
         const int blocks = n_env < a->blocks_mma ? n_env : a->blocks_mma;
         pve_actor_mma_kernel<<<blocks, PVM_THREADS, PVM_SMEM_BYTES, stream>>>(a->pw_dev, rows, meta, n_veh, noise, noise_scale,
-                                                                           actions, slots_per_env, n_env, n_slots, a->ticket);
+                                                                           actions, slots_per_env, n_env, n_slots, a->ticket, limit_dev, limit_mult);
     } else {
         const int blocks = n_env < a->blocks_ffma ? n_env : a->blocks_ffma;
         pve_actor_kernel<<<blocks, PVA_THREADS, PVA_SMEM_BYTES, stream>>>(a->w_dev, rows, meta, n_veh, noise, noise_scale,
-                                                                       actions, slots_per_env, n_env, n_slots, a->ticket);
+                                                                       actions, slots_per_env, n_env, n_slots, a->ticket, limit_dev, limit_mult);
     }
     return cudaGetLastError();
 }
@@ -874,5 +875,191 @@ int32_t pve_act(pve_scene *s, pve_actor *a, const float *noise_dev, float noise_
     return PVE_OK;
 #endif
 }
+
+int32_t pve_actor_forward_n(pve_actor *a, const float *rows_dev, int64_t max_rows, const int32_t *n_rows_dev,
+                            int32_t mult, float *actions_dev, void *stream_) {
+    if (!a || !rows_dev || !actions_dev || !n_rows_dev || max_rows < 0 || mult < 1) return PVE_EINVAL;
+#ifdef PVE_HOST_EMULATION
+    (void)stream_;
+    return PVE_ESTATE;
+#else
+    if (max_rows == 0) return PVE_OK;
+    if (max_rows > 0x7fffffffLL) return PVE_EINVAL;
+    const long long groups = (max_rows + PVA_TILE - 1) / PVA_TILE;
+    return launch_actor(a, rows_dev, nullptr, nullptr, nullptr, 0.f, actions_dev, PVA_TILE, (int)groups, (long long)max_rows,
+                        (pve_stream_t)stream_, n_rows_dev, mult) == cudaSuccess ? PVE_OK : PVE_ECUDA;
+#endif
+}
+
+/* ---- critic + n-step folding + replay writer (N2) ------------------------------------------ */
+struct pve_critic {
+    float *w_dev;
+    int device, blocks;
+};
+
+int32_t pve_critic_create(const float *weights_host, int32_t n_floats, int32_t device, pve_critic **out) {
+    if (!weights_host || !out || n_floats != PVE_CRITIC_FLOATS) return PVE_EINVAL;
+#ifdef PVE_HOST_EMULATION
+    (void)device;
+    return PVE_ESTATE;                       /* device only */
+#else
+    if (cudaSetDevice(device) != cudaSuccess) return PVE_ECUDA;
+    pve_critic *c = (pve_critic *)calloc(1, sizeof(pve_critic));
+    if (!c) return PVE_ENOMEM;
+    c->device = device;
+    int sms = 0, per_sm = 0;
+    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device) != cudaSuccess || sms <= 0) sms = 148;
+    bool ok = cudaFuncSetAttribute(pve_critic_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PVC_SMEM_BYTES) == cudaSuccess;
+    if (ok && (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pve_critic_kernel, PVC_THREADS, PVC_SMEM_BYTES) != cudaSuccess || per_sm < 1)) per_sm = 1;
+    c->blocks = per_sm * sms;
+    ok = ok && cudaMalloc((void **)&c->w_dev, sizeof(float) * PVE_CRITIC_FLOATS) == cudaSuccess
+            && cudaMemcpy(c->w_dev, weights_host, sizeof(float) * PVE_CRITIC_FLOATS, cudaMemcpyHostToDevice) == cudaSuccess;
+    if (!ok) { cudaFree(c->w_dev); free(c); cudaGetLastError(); return PVE_ECUDA; }
+    *out = c;
+    return PVE_OK;
+#endif
+}
+
+void pve_critic_destroy(pve_critic *c) {
+    if (!c) return;
+#ifndef PVE_HOST_EMULATION
+    cudaFree(c->w_dev);
+#endif
+    free(c);
+}
+
+int32_t pve_critic_forward(pve_critic *c, const float *obs_dev, const float *act7_dev, int64_t max_rows,
+                           const int32_t *n_rows_dev, float *q_dev, void *stream_) {
+    if (!c || !obs_dev || !act7_dev || !q_dev || max_rows < 0) return PVE_EINVAL;
+#ifdef PVE_HOST_EMULATION
+    (void)n_rows_dev; (void)stream_;
+    return PVE_ESTATE;
+#else
+    if (max_rows == 0) return PVE_OK;
+    const long long tiles = (max_rows + PVC_TILE - 1) / PVC_TILE;
+    const int blocks = (int)(tiles < c->blocks ? tiles : c->blocks);
+    pve_critic_kernel<<<blocks, PVC_THREADS, PVC_SMEM_BYTES, (pve_stream_t)stream_>>>(c->w_dev, obs_dev, act7_dev, q_dev,
+                                                                                     (long long)max_rows, n_rows_dev);
+    return cudaGetLastError() == cudaSuccess ? PVE_OK : PVE_ECUDA;
+#endif
+}
+
+struct pve_nstep {
+    PvnTable T;
+    PvnReplay R;
+    float *act7, *q;             /* [out_cap][7], [out_cap] target actions and bootstrap values of the last push */
+    uint32_t *plan;              /* [out_cap] */
+    int32_t *blk_count;          /* [n_blk] */
+    long long *blk_base;         /* [n_blk] */
+    long long *counters;         /* [4] device */
+    long long out_cap, pushes;
+    int n_blk, device, fold_blocks;
+};
+
+void pve_nstep_destroy(pve_nstep *f) {
+    if (!f) return;
+#ifndef PVE_HOST_EMULATION
+    cudaFree(f->T.key); cudaFree(f->T.fill); cudaFree(f->T.rew); cudaFree(f->T.frames);
+    cudaFree(f->R.state); cudaFree(f->R.action); cudaFree(f->R.reward); cudaFree(f->R.next_state); cudaFree(f->R.done);
+    cudaFree(f->act7); cudaFree(f->q); cudaFree(f->plan); cudaFree(f->blk_count); cudaFree(f->blk_base); cudaFree(f->counters);
+#endif
+    free(f);
+}
+
+int32_t pve_nstep_create(int32_t n_envs, int32_t uid_slots, int32_t seq_max_step, int64_t out_cap,
+                         int64_t buffer_size, int32_t device, pve_nstep **out) {
+    if (!out || n_envs < 1 || uid_slots < 16 || (uid_slots & (uid_slots - 1)) != 0 || seq_max_step < 0
+        || seq_max_step + 2 > PVN_MAX_M || out_cap < 1 || buffer_size - 1 < out_cap)
+        return PVE_EINVAL;
+#ifdef PVE_HOST_EMULATION
+    (void)device;
+    return PVE_ESTATE;                       /* device only */
+#else
+    if (cudaSetDevice(device) != cudaSuccess) return PVE_ECUDA;
+    pve_nstep *f = (pve_nstep *)calloc(1, sizeof(pve_nstep));
+    if (!f) return PVE_ENOMEM;
+    f->device = device;
+    f->out_cap = out_cap;
+    f->T.B = n_envs; f->T.U = uid_slots; f->T.S = seq_max_step; f->T.M = seq_max_step + 2;
+    f->R.cap = buffer_size - 1;
+    f->n_blk = (int)((out_cap + PVN_PLAN_THREADS - 1) / PVN_PLAN_THREADS);
+    int sms = 0;
+    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device) != cudaSuccess || sms <= 0) sms = 148;
+    f->fold_blocks = sms * 8;
+    const size_t slots = (size_t)n_envs * uid_slots, cap = (size_t)f->R.cap, oc = (size_t)out_cap;
+    bool ok = cudaMalloc((void **)&f->T.key, slots * 8) == cudaSuccess
+              && cudaMalloc((void **)&f->T.fill, slots * 2) == cudaSuccess
+              && cudaMalloc((void **)&f->T.rew, slots * f->T.M * sizeof(float)) == cudaSuccess
+              && cudaMalloc((void **)&f->T.frames, slots * f->T.M * PVN_OBS * sizeof(float)) == cudaSuccess
+              && cudaMalloc((void **)&f->R.state, cap * PVN_OBS * sizeof(float)) == cudaSuccess
+              && cudaMalloc((void **)&f->R.next_state, cap * PVN_OBS * sizeof(float)) == cudaSuccess
+              && cudaMalloc((void **)&f->R.action, cap * PVE_OBS_H * sizeof(float)) == cudaSuccess
+              && cudaMalloc((void **)&f->R.reward, cap * sizeof(float)) == cudaSuccess
+              && cudaMalloc((void **)&f->R.done, cap) == cudaSuccess
+              && cudaMalloc((void **)&f->act7, oc * PVE_OBS_H * sizeof(float)) == cudaSuccess
+              && cudaMalloc((void **)&f->q, oc * sizeof(float)) == cudaSuccess
+              && cudaMalloc((void **)&f->plan, oc * sizeof(uint32_t)) == cudaSuccess
+              && cudaMalloc((void **)&f->blk_count, (size_t)f->n_blk * sizeof(int32_t)) == cudaSuccess
+              && cudaMalloc((void **)&f->blk_base, (size_t)f->n_blk * sizeof(long long)) == cudaSuccess
+              && cudaMalloc((void **)&f->counters, 4 * sizeof(long long)) == cudaSuccess;
+    ok = ok && cudaMemset(f->T.key, 0xFF, slots * 8) == cudaSuccess && cudaMemset(f->T.fill, 0, slots * 2) == cudaSuccess
+            && cudaMemset(f->counters, 0, 4 * sizeof(long long)) == cudaSuccess
+            && cudaMemset(f->q, 0, oc * sizeof(float)) == cudaSuccess && cudaMemset(f->R.done, 0, cap) == cudaSuccess
+            && cudaMemset(f->R.reward, 0, cap * sizeof(float)) == cudaSuccess;
+    if (!ok) { cudaGetLastError(); pve_nstep_destroy(f); return PVE_ENOMEM; }
+    *out = f;
+    return PVE_OK;
+#endif
+}
+
+int32_t pve_nstep_push(pve_nstep *f, const pve_outputs *O, double gamma, pve_actor *target_actor,
+                       pve_critic *target_critic, void *stream_) {
+    if (!f || !O || !target_actor || !target_critic || !O->agent_offset || !O->ids || !O->status || !O->obs || !O->reward)
+        return PVE_EINVAL;
+#ifdef PVE_HOST_EMULATION
+    (void)gamma; (void)stream_;
+    return PVE_ESTATE;
+#else
+    if (target_actor->device != f->device || target_critic->device != f->device) return PVE_EINVAL;
+    pve_stream_t stream = (pve_stream_t)stream_;
+    const int32_t *n_rows_dev = O->agent_offset + f->T.B;
+    /* mu'(s'[k]) for the 7 rows of every observation, then Q' (main.py:253-260) */
+    int32_t rc = pve_actor_forward_n(target_actor, O->obs, f->out_cap * PVE_OBS_H, n_rows_dev, PVE_OBS_H, f->act7, stream_);
+    if (rc != PVE_OK) return rc;
+    rc = pve_critic_forward(target_critic, O->obs, f->act7, f->out_cap, n_rows_dev, f->q, stream_);
+    if (rc != PVE_OK) return rc;
+    const unsigned stamp = (unsigned)(++f->pushes);
+    pvn_plan_kernel<<<f->n_blk, PVN_PLAN_THREADS, 0, stream>>>(f->T, O->ids, O->status, O->agent_offset, f->out_cap, stamp,
+                                                              f->plan, f->blk_count, f->counters);
+    pvn_scan_kernel<<<1, 1024, 0, stream>>>(f->blk_count, f->blk_base, f->n_blk, f->counters);
+    pvn_fold_kernel<<<f->fold_blocks, 256, 0, stream>>>(f->T, f->R, O->ids, O->status, O->obs, O->reward, f->q, O->agent_offset,
+                                                        f->out_cap, stamp, gamma, f->plan, f->blk_base);
+    return cudaGetLastError() == cudaSuccess ? PVE_OK : PVE_ECUDA;
+#endif
+}
+
+int32_t pve_nstep_replay(const pve_nstep *f, pve_replay_view *view) {
+    if (!f || !view) return PVE_EINVAL;
+    view->state = f->R.state; view->action = f->R.action; view->reward = f->R.reward;
+    view->next_state = f->R.next_state; view->done = f->R.done; view->capacity = f->R.cap;
+    return PVE_OK;
+}
+
+int32_t pve_nstep_counters(pve_nstep *f, int64_t *out_host, void *stream_) {
+    if (!f || !out_host) return PVE_EINVAL;
+#ifdef PVE_HOST_EMULATION
+    (void)stream_;
+    return PVE_ESTATE;
+#else
+    long long tmp[4];
+    if (cudaMemcpyAsync(tmp, f->counters, sizeof(tmp), cudaMemcpyDeviceToHost, (pve_stream_t)stream_) != cudaSuccess
+        || cudaStreamSynchronize((pve_stream_t)stream_) != cudaSuccess)
+        return PVE_ECUDA;
+    out_host[0] = tmp[0]; out_host[1] = tmp[1]; out_host[2] = tmp[2]; out_host[3] = f->pushes;
+    return PVE_OK;
+#endif
+}
+
+const float *pve_nstep_q_dev(const pve_nstep *f) { return f ? f->q : nullptr; }
 
 }  /* extern "C" */
