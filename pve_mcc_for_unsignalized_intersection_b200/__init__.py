@@ -9,6 +9,8 @@ Public surface:
 * ``BatchedActor`` / ``ActorWeights`` -- the reference's actor network evaluated for every controlled
                           vehicle at once (``actor.act(scene)`` -> the next ``scene.step`` input); weights read
                           from the reference's TF checkpoint without TensorFlow (``checkpoint``).
+* ``NStepFolder`` / ``BatchedCritic`` / ``CriticWeights`` -- the training loop's transition buffers, n-step
+                          return folding and replay memory (main.py:243-266, replay_buffer.py:45-53) on the GPU.
 * ``SceneConfig``      -- the constructor scalars of the reference scene.
 * ``arrivals``         -- arrival tables: synthetic generator, conversion to integer spawn ticks.
 
@@ -27,6 +29,9 @@ def __getattr__(name):
     if name in ("BatchedActor", "ActorWeights"):
         from . import actor
         return getattr(actor, name)
+    if name in ("NStepFolder", "BatchedCritic", "CriticWeights"):
+        from . import nstep
+        return getattr(nstep, name)
     if name == "TrafficInteraction":
         from .reference_api import TrafficInteraction
         return TrafficInteraction

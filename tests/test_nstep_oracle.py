@@ -62,3 +62,30 @@ def test_done_uses_the_plain_reward_and_frees_the_vehicle():
     assert abs(out[4][0][3] - (2 + g * (4 + g * (8 + g * 16)))) < 1e-12                # Done: no bootstrap
     assert np.array_equal(out[4][0][1], obs[0, 0]) and np.array_equal(out[4][0][4], obs[1, 0])
     assert (0, 7) not in fold.buffers
+
+
+def test_critic_weight_layout_and_host_errors():
+    import pytest
+    import torch
+    from pve_mcc_for_unsignalized_intersection_b200 import _native
+    from pve_mcc_for_unsignalized_intersection_b200.nstep import (CRITIC_FLOATS, CRITIC_SPECS, BatchedCritic,
+                                                                   CriticWeights)
+    assert CRITIC_SPECS == nstep_oracle.CRITIC_SPECS and CRITIC_FLOATS == 6841
+    _, critic = K.load_nets()
+    w = CriticWeights(critic)
+    flat = w.flat()
+    # order of the flat vector = order of include/pve_mcc.h (PVE_CRITIC_FLOATS)
+    assert np.array_equal(flat[:28], critic["LayerNorm/gamma"])
+    off_w2 = 56 + 28 * 64 + 64 + 128
+    assert np.array_equal(flat[off_w2:off_w2 + 71 * 64].reshape(71, 64), critic["dense_1/kernel"])
+    assert flat[-1] == critic["dense_2/bias"][0]
+    with pytest.raises(ValueError):
+        CriticWeights({n: np.zeros((2,)) for n, _ in CRITIC_SPECS})
+    header = open(__import__("os").path.join(parity.ROOT, "include", "pve_mcc.h")).read()
+    assert "#define PVE_CRITIC_FLOATS 6841" in header
+    if not torch.cuda.is_available():
+        with pytest.raises(_native.NativeError):           # no CPU fallback
+            BatchedCritic(w)
+    # a random critic in the reference's initialisation has the right shapes
+    q = nstep_oracle.critic_forward(CriticWeights.random(1), np.zeros((3, 28)), np.zeros((3, 7)))
+    assert q.shape == (3,)
