@@ -1,3 +1,1 @@
-python -c "import __graft_entry__ as g; g.build()" > gpurun_out/r03b_build.log 2>&1 || { echo BUILD FAILED; tail gpurun_out/r03b_build.log; exit 1; }
-timeout 1200 python -m pytest tests/test_gpu_nstep.py -q > gpurun_out/r03b_nstep.log 2>&1; echo "nstep rc=$?"; tail -40 gpurun_out/r03b_nstep.log
-timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -s 2850 -c 24 --csv --log-file gpurun_out/r03b_train_launches.csv python bench.py --workload train --steps 10 --warmup 5 --no-cpu-baseline --no-e2e > gpurun_out/r03b_train_launches_run.log 2>&1; echo "ncu rc=$?"; tail -26 gpurun_out/r03b_train_launches.csv | cut -c1-400
+nvcc -gencode arch=compute_100a,code=sm_100a -O3 tools/micro/pcie_write_bench.cu -o /tmp/pcie_write_bench && /tmp/pcie_write_bench
