@@ -55,7 +55,7 @@ typedef struct pve_config {
     int32_t n_envs;        /* B: intersections on this GPU                                   */
     int32_t veh_cap;       /* dense vehicle slots per intersection (<= 576; rounded up to a class) */
     int32_t agent_cap;     /* controlled vehicles per intersection (<= veh_cap)               */
-    int32_t threads;       /* CTA size: 0 = default, else 64 / 128 / 256                      */
+    int32_t threads;       /* CTA size: 0 = default (128; 512 for the large classes), else 64/96/128/256/512 */
     int64_t out_cap;       /* rows of the per-agent output arrays the caller will provide     */
     double dt, dt2;        /* deltaT and pow(deltaT, 2)                        TIS:21, 1529   */
     double vm, vM, am, aM, v0;                                             /* TIS:21          */

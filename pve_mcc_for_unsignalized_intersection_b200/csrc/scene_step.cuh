@@ -153,8 +153,8 @@ struct PveLayout {
     static constexpr uint32_t VL_BASE = LANE_OFF + 64;           /* int[16] */
     static constexpr uint32_t VL_CNT = VL_BASE + 64;             /* int[16] */
     static constexpr uint32_t MISC = VL_CNT + 64;                /* int[56] */
-    static constexpr uint32_t WSUM = MISC + 224;                 /* int[48] */
-    static constexpr uint32_t ACNT = WSUM + 192;                 /* u16[VC+2] */
+    static constexpr uint32_t WSUM = MISC + 224;                 /* int[96]: [0,32) scans, [32,64) chain, [64,80) first row; 16 warps */
+    static constexpr uint32_t ACNT = WSUM + 384;                 /* u16[VC+2] */
     static constexpr uint32_t SURV = ACNT + a16(2 * (VC + 2));
     static constexpr uint32_t VIDX = SURV + a16(2 * (VC + 2));
     static constexpr uint32_t ARANK = VIDX + 2 * AC;
@@ -587,7 +587,7 @@ PVE_DEV void pve_step_block(const PveParams &P, const PveState &S, const pve_out
 #undef PVE_LW_BYTE
     PVE_END_TID_NOSYNC
     /* row range of this intersection in the dense outputs (one internal barrier, which also publishes A) */
-    const int64_t obase = (int64_t)pve_first_row<NT>(S, b, row_part, wsum + 34);
+    const int64_t obase = (int64_t)pve_first_row<NT>(S, b, row_part, wsum + 64);
     const int V = misc[M_V];
 
     /* ---- B: F_k(s) = "rear-end override fires on k if its leader took candidate s" -------- */
@@ -620,7 +620,7 @@ PVE_DEV void pve_step_block(const PveParams &P, const PveState &S, const pve_out
     PVE_END_TID_NOSYNC
 
     /* ---- B2: resolve the chain (scan of boolean functions; one internal barrier) ------------ */
-    pve_resolve_chain<NT>(fbits, ssel, V, wsum + 16);
+    pve_resolve_chain<NT>(fbits, ssel, V, wsum + 32);
 
     /* ---- C: commit kinematics -------------------------------------------------------------- */
     PVE_FOR_TID(tid)

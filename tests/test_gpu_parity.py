@@ -16,7 +16,7 @@ def test_backend_is_cuda():
     assert torch.cuda.get_device_capability(0)[0] == 10
 
 
-@pytest.mark.parametrize("threads", [64, 96, 128, 256])
+@pytest.mark.parametrize("threads", [64, 96, 128, 256, 512])
 def test_free_running_matches_oracle(threads):
     tabs = np.concatenate([synthetic_arrivals(4, lam, 50.0, seed=lam, rows=40) for lam in (400, 1000, 1200)])
     B = tabs.shape[0]
@@ -39,8 +39,10 @@ def test_train_setting_vm6_accel():
     E.free_run("cuda", synthetic_arrivals(3, 1000, 40.0, seed=77, rows=32), vm=6, ticks=330, seed=2, policy="accel")
 
 
-def test_stress_occupancy_brake():
-    E.free_run("cuda", stress_arrivals(2, 40.0), vm=5, ticks=300, seed=3, veh_cap=384, agent_cap=320, policy="brake")
+@pytest.mark.parametrize("threads", [0, 128, 256])          # 0 = the class default (512 threads for the large classes)
+def test_stress_occupancy_brake(threads):
+    E.free_run("cuda", stress_arrivals(2, 40.0), vm=5, ticks=300, seed=3, veh_cap=384, agent_cap=320, policy="brake",
+               threads=threads)
 
 
 @pytest.mark.parametrize("name", E.ROLLOUTS)

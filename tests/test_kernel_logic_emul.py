@@ -14,9 +14,9 @@ from pve_mcc_for_unsignalized_intersection_b200.arrivals import stress_arrivals,
 BACKEND = "emul"
 
 
-def free_run(backend, tables, vm, ticks, seed, veh_cap=128, agent_cap=96, policy="uniform"):
+def free_run(backend, tables, vm, ticks, seed, veh_cap=128, agent_cap=96, policy="uniform", threads=0):
     B = tables.shape[0]
-    scene = P.make_scene(backend, B, vm=vm, veh_cap=veh_cap, agent_cap=agent_cap)
+    scene = P.make_scene(backend, B, vm=vm, veh_cap=veh_cap, agent_cap=agent_cap, threads=threads)
     orc = P.make_oracle(B, vm=vm, veh_cap=scene.veh_cap)
     scene.reset(tables, warmup=True)
     orc.reset(tables, warmup=True)
