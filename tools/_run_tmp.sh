@@ -1,4 +1,3 @@
 python -c "import __graft_entry__ as g; g.build()" > /dev/null 2>&1
-timeout 600 python -m pytest tests/test_gpu_parity.py -x -q -k "stress or free_running" 2>&1 | tail -3
-for th in 0 256 512; do python bench.py --workload stress --threads $th --steps 40 --warmup 5 --no-cpu-baseline --no-e2e 2>/dev/null | python -c "import json,sys; d=json.loads(sys.stdin.read()); print('stress threads=$th', d['config']['threads_per_cta'], 'kernel_ms', round(d['roofline']['kernel_ms_per_launch'],5), 'frac', round(d['roofline']['frac'],4), 'value', '%.3e' % d['value'])"; done
-for rep in 1 2; do python bench.py --steps 100 --warmup 5 --no-cpu-baseline --no-e2e 2>/dev/null | python -c "import json,sys; d=json.loads(sys.stdin.read()); print('default', d['config']['threads_per_cta'], 'kernel_ms', round(d['roofline']['kernel_ms_per_launch'],5), 'frac', round(d['roofline']['frac'],4), 'smem', d['config']['smem_per_cta'])"; done
+N=$1
+python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29541 bench.py --gpus $N --workload stress --steps 100 --warmup 5 --no-cpu-baseline > gpurun_out/r03e_bench_stress_${N}gpu.json 2> gpurun_out/r03e_bench_stress_${N}gpu.err; echo "rc=$?"; tail -2 gpurun_out/r03e_bench_stress_${N}gpu.err; cut -c1-200 gpurun_out/r03e_bench_stress_${N}gpu.json
