@@ -240,6 +240,9 @@ void pve_nstep_destroy(pve_nstep *f);
  * The bootstrap term uses the two target networks on this tick's observations.  Asynchronous on `stream`. */
 int32_t pve_nstep_push(pve_nstep *f, const pve_outputs *out_dev, double gamma, pve_actor *target_actor,
                        pve_critic *target_critic, void *stream);
+/* a new episode (main.py:230 builds a new TrafficInteraction every epoch): every vehicle's buffered transitions are
+ * dropped, the replay memory and num_experiences are kept (agent1_memory_seq lives across epochs, main.py:212) */
+int32_t pve_nstep_reset(pve_nstep *f, void *stream);
 int32_t pve_nstep_replay(const pve_nstep *f, pve_replay_view *view);
 /* out_host[0] = num_experiences (replay_buffer.py:47), [1] = records added by the last push, [2] = history slots
  * claimed while another live vehicle owned them (sticky; must stay 0), [3] = pushes so far.  Synchronises `stream`. */

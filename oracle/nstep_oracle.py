@@ -101,6 +101,12 @@ class NStepOracle:
         self.buffers = {}
         self.stored_state = {}
 
+    def reset(self):
+        """A new episode: main.py:230 builds a new scene, so every vehicle record (and its buffer) is gone; the
+        replay memory of main.py:212 lives on."""
+        self.buffers = {}
+        self.stored_state = {}
+
     def push(self, env_of_row, uid, state_next, reward, done, gamma):
         """One tick.  Rows in the order of ``ids`` (intersection, lane, j ascending).  Returns the records added to
         the replay memory this tick as ``(row, state, action, r_target, next_state)``."""

@@ -1045,6 +1045,20 @@ int32_t pve_nstep_push(pve_nstep *f, const pve_outputs *O, double gamma, pve_act
 #endif
 }
 
+int32_t pve_nstep_reset(pve_nstep *f, void *stream_) {
+    if (!f) return PVE_EINVAL;
+#ifdef PVE_HOST_EMULATION
+    (void)stream_;
+    return PVE_ESTATE;
+#else
+    const size_t slots = (size_t)f->T.B * f->T.U;
+    if (cudaMemsetAsync(f->T.key, 0xFF, slots * 8, (pve_stream_t)stream_) != cudaSuccess
+        || cudaMemsetAsync(f->T.fill, 0, slots * 2, (pve_stream_t)stream_) != cudaSuccess)
+        return PVE_ECUDA;
+    return PVE_OK;
+#endif
+}
+
 int32_t pve_nstep_replay(const pve_nstep *f, pve_replay_view *view) {
     if (!f || !view) return PVE_EINVAL;
     view->state = f->R.state; view->action = f->R.action; view->reward = f->R.reward;

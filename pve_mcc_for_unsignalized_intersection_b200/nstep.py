@@ -178,6 +178,13 @@ class NStepFolder:
         if rc != 0:
             raise N.NativeError("pve_nstep_push failed with %d" % rc)
 
+    def reset(self):
+        """A new episode (main.py:230: a new ``TrafficInteraction`` per epoch): the vehicles' buffered transitions are
+        dropped; the replay memory stays (``agent1_memory_seq`` is created once, main.py:212)."""
+        rc = self.lib.pve_nstep_reset(self._h, self._stream())
+        if rc != 0:
+            raise N.NativeError("pve_nstep_reset failed with %d" % rc)
+
     def counters(self):
         """``num_experiences`` (replay_buffer.py:47), records added by the last push, history-slot conflicts (must
         be 0), pushes.  Synchronises."""

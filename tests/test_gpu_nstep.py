@@ -202,3 +202,34 @@ def test_folder_rejects_bad_arguments():
         NStepFolder(scene, actor, critic, uid_slots=100)
     with pytest.raises(N.NativeError):
         NStepFolder(scene, actor, critic, buffer_size=scene.out_cap)       # deque of buffer_size - 1 < one tick
+
+
+def test_new_episode_keeps_the_memory_and_drops_the_buffers():
+    """Two episodes back to back on the same tables: uids repeat, so without ``reset`` the second episode would
+    continue the first one's histories."""
+    aw, cw = nets()
+    B, S = 6, 5
+    tabs = synthetic_arrivals(B, 1000, 30.0, seed=21)
+    scene = P.make_scene("cuda", B, vm=6)
+    folder = NStepFolder(scene, BatchedActor(aw), BatchedCritic(cw), S, buffer_size=100000)
+    orc = nstep_oracle.NStepOracle(aw, cw, S, buffer_size=100000)
+    acts = torch.zeros(B, scene.veh_cap, device="cuda")
+    n_prev = 0
+    for episode in range(2):
+        scene.reset(tabs, warmup=True)
+        folder.reset()
+        orc.reset()
+        for t in range(70):
+            out = scene.step(acts)
+            folder.push(out, 0.7)
+            o = P.outputs_to_numpy(out)
+            added = orc.push(o["ids"][:, 0], o["ids"][:, 3], o["obs"], o["reward"], (o["status"] & 1) != 0, 0.7)
+            c = folder.counters()
+            assert c["num_experiences"] == n_prev + len(added), (episode, t)
+            rec = new_records(folder, n_prev, c["num_experiences"])
+            for i, (row, state, action, target, nxt) in enumerate(added):
+                assert np.array_equal(rec["state"][i], state.astype(np.float32)), (episode, t, i)
+                assert np.array_equal(rec["next_state"][i], nxt.astype(np.float32)), (episode, t, i)
+                assert abs(rec["reward"][i] - target) <= T_RTOL * abs(target) + T_ATOL
+            n_prev = c["num_experiences"]
+    assert n_prev > 1000 and folder.counters()["slot_conflicts"] == 0
