@@ -220,7 +220,7 @@ def graft_arm(args, rank, world, local_rank):
     tabs = make_tables(args, B, 1000 + rank, horizon)
     rollout = args.workload in ("rollout", "train")
     scene = BatchedScene(B, SceneConfig(vm=5 if (stress or rollout) else VM), veh_cap=veh_cap, agent_cap=agent_cap,
-                         device=dev, threads=args.threads)
+                         device=dev, threads=args.threads, neighbour_sources=args.workload == "train")
     scene.reset(tabs, warmup=True)
     actor = None
     if rollout:
@@ -394,8 +394,9 @@ def graft_arm(args, rank, world, local_rank):
                          "kernel": "pve_step_kernel", "kernel_ms_per_launch": my_kern_ms / K,
                          "algorithmic_bytes_per_launch": alg_bytes / K},
             # kernels inside the timed region of `value`: one step kernel per tick (+ one actor kernel in a rollout)
-            # (+ target actor, critic, plan, scan, fold in a training rollout)
-            "gpu_launches": K * ((7 if folder is not None else 2) if actor is not None else 1),
+            # (+ target actor on this tick's rows / last tick's referenced rows / the zero row, mark, gather, critic, plan,
+            # scan, fold in a training rollout)
+            "gpu_launches": K * ((11 if folder is not None else 2) if actor is not None else 1),
             "clocks": sampler.result(),
             "stats": {k: float(v) for k, v in zip(
                 ["agent_steps", "vehicle_steps", "env_steps", "spawned", "passed", "passed_step_total",
@@ -415,13 +416,15 @@ def graft_arm(args, rank, world, local_rank):
             fc = folder.counters()
             # per agent row: 784 B observation in + 784 B frame out; per record: 2 x 784 B frames in, 2 x 784 + 36 B out
             fold_bytes = (1568 * kA + 3172 * kA) / K
-            line["nstep"] = {"kernels": "pve_actor_mma_kernel (7 rows per agent) + pve_critic_kernel + pvn_plan/scan/fold",
+            line["nstep"] = {"kernels": "pve_actor_mma_kernel x 3 (distinct rows: this tick's agents, last tick's referenced rows, "
+                                        "the zero row) + pvn_mark/gather + pve_critic_kernel + pvn_plan/scan/fold",
                              "ms_per_push": float(sum(fold_ms)) / K, "seq_max_step": 12, "gamma": TRAIN_GAMMA,
                              "num_experiences": fc["num_experiences"], "records_last_push": fc["last_added"],
                              "slot_conflicts": fc["slot_conflicts"], "replay_capacity": folder.capacity,
                              "fold_algorithmic_bytes_per_push": fold_bytes,
-                             "note": "timed alone with a cold L2 inside the same ticks as roofline; the bootstrap runs "
-                                     "the target actor on all 7 rows of every agent's observation like main.py:253-255"}
+                             "note": "timed alone with a cold L2 inside the same ticks as roofline; the bootstrap needs the "
+                                     "target actor on all 7 rows of every agent's observation (main.py:253-255): it is "
+                                     "evaluated once per distinct row and gathered through pve_outputs.nbr_src"}
         if e2e:
             line["e2e"] = {"value": e2e_rows / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(e2e["h2d"]),
                            "d2h_bytes_per_step": int(e2e["d2h"]),

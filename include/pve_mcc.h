@@ -116,6 +116,12 @@ typedef struct pve_outputs {
     int32_t *env_collisions;/* [B]  `collisions`                                 TIS:337      */
     int32_t *env_lock;      /* [B]  `lock`                                       TIS:365-370  */
     int32_t *env_removed;   /* [B]  len(delete_veh)                              TIS:348      */
+    /* optional (may be null): [out_cap][8] where each of the 7 observation rows of an agent was copied from
+     * (get_state copies whole stored rows, TIS:1330-1334, Q3): -1 = the all-zero row; 0 .. 0x3FFF = row 0 of agent
+     * g' of the same intersection THIS tick (output row agent_offset[b] + g'; entry 0 is the agent itself);
+     * 0x4000 | k = the row stored LAST tick for vehicle slot k of the same intersection (slot order before this
+     * tick's removals).  Entry 7 is padding (-1).  Lets a consumer evaluate a network once per distinct row. */
+    int16_t *nbr_src;
 } pve_outputs;
 
 /* End-of-rollout statistics (MAIN:407-415, 566-581), summed over the handle's intersections.
@@ -240,6 +246,12 @@ void pve_nstep_destroy(pve_nstep *f);
  * The bootstrap term uses the two target networks on this tick's observations.  Asynchronous on `stream`. */
 int32_t pve_nstep_push(pve_nstep *f, const pve_outputs *out_dev, double gamma, pve_actor *target_actor,
                        pve_critic *target_critic, void *stream);
+/* The same tick with the scene at hand and out_dev->nbr_src filled in by the step: the target actor is evaluated once
+ * per distinct row (this tick's agent rows + the referenced rows stored last tick + the zero row) instead of on all
+ * 7 rows of every observation, and the 7 actions are gathered through nbr_src.  Results are identical (the network
+ * sees the same row contents).  Must be called before the scene's next step (last tick's rows are still in place). */
+int32_t pve_nstep_push_scene(pve_nstep *f, pve_scene *s, const pve_outputs *out_dev, double gamma,
+                             pve_actor *target_actor, pve_critic *target_critic, void *stream);
 /* a new episode (main.py:230 builds a new TrafficInteraction every epoch): every vehicle's buffered transitions are
  * dropped, the replay memory and num_experiences are kept (agent1_memory_seq lives across epochs, main.py:212) */
 int32_t pve_nstep_reset(pve_nstep *f, void *stream);

@@ -36,7 +36,7 @@ class PveStateView(C.Structure):
 class PveOutputs(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in
                 ("agent_offset", "obs", "reward", "ids", "cpv", "status", "jerk_sum",
-                 "env_collisions", "env_lock", "env_removed")]
+                 "env_collisions", "env_lock", "env_removed", "nbr_src")]
 
 
 class PveReplayView(C.Structure):
@@ -96,6 +96,7 @@ def load_library(path=None):
     lib.pve_nstep_destroy.argtypes = [vp]
     lib.pve_nstep_destroy.restype = None
     lib.pve_nstep_push.argtypes = [vp, C.POINTER(PveOutputs), C.c_double, vp, vp, vp]
+    lib.pve_nstep_push_scene.argtypes = [vp, vp, C.POINTER(PveOutputs), C.c_double, vp, vp, vp]
     lib.pve_nstep_reset.argtypes = [vp, vp]
     lib.pve_nstep_replay.argtypes = [vp, C.POINTER(PveReplayView)]
     lib.pve_nstep_counters.argtypes = [vp, C.POINTER(i64), vp]

@@ -245,7 +245,8 @@ __global__ void __launch_bounds__(PVM_THREADS, 2)
 pve_actor_mma_kernel(const uint32_t *__restrict__ PW, const float *__restrict__ rows, const pve_veh_meta *__restrict__ meta,
                      const int32_t *__restrict__ n_veh, const float *__restrict__ noise, const float noise_scale,
                      float *__restrict__ actions, const int slots_per_env, const int n_env, const long long n_slots_max,
-                     int *__restrict__ ticket, const int32_t *__restrict__ limit_dev, const int limit_mult) {
+                     int *__restrict__ ticket, const int32_t *__restrict__ limit_dev, const int limit_mult,
+                 const uint8_t *__restrict__ mask, const int slot_step) {
     /* device-side row count of a dense matrix (pve_actor_forward_n): rows >= limit_dev[0] * limit_mult are skipped */
     const long long n_slots = limit_dev ? min(n_slots_max, (long long)limit_dev[0] * limit_mult) : n_slots_max;
     extern __shared__ __align__(16) unsigned char pvm_smem[];
@@ -274,6 +275,8 @@ pve_actor_mma_kernel(const uint32_t *__restrict__ PW, const float *__restrict__ 
                 const int s = s0 + tid;
                 const long long gs = base + s;
                 bool want = s < total && gs < n_slots;
+                if (want && slot_step > 1) want = (gs % slot_step) == 0;      /* every slot_step-th row of a dense matrix */
+                if (want && mask) want = mask[gs] != 0;                      /* only the marked rows */
                 if (want && meta) {
                     const int e = s / slots_per_env;
                     want = (s - e * slots_per_env) < n_veh[envb + e] && ((meta[gs].packed >> 24) & PVE_F_CONTROL) != 0;

@@ -185,6 +185,38 @@ pve_critic_kernel(const float *__restrict__ W, const float *__restrict__ obs, co
     }
 }
 
+/* ---- bootstrap actions once per distinct row (pve_nstep_push_scene) ---------------------------------------------
+ * nbr_src (pve_outputs) names the source of every observation row.  mark: which rows stored last tick are referenced at
+ * all; gather: act7[r][k] = mu'(source of row k), k = 1..6 (k = 0 was evaluated in place on this tick's agent rows). */
+__global__ void __launch_bounds__(256)
+pvn_mark_kernel(const int16_t *__restrict__ nbr_src, const int32_t *__restrict__ ids, const int32_t *__restrict__ agent_offset,
+                const int B, const long long out_cap, const int VC, uint8_t *__restrict__ need) {
+    const long long n_rows = min((long long)agent_offset[B], out_cap);
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long r = i >> 3;
+    const int k = (int)(i & 7);
+    if (r >= n_rows || k == 0 || k >= PVE_OBS_H) return;
+    const int v = nbr_src[r * 8 + k];
+    if (v >= 0 && (v & 0x4000)) need[(size_t)ids[r * 4] * VC + (v & 0x3FFF)] = 1;
+}
+__global__ void __launch_bounds__(256)
+pvn_gather_kernel(const int16_t *__restrict__ nbr_src, const int32_t *__restrict__ ids, const int32_t *__restrict__ agent_offset,
+                  const int B, const long long out_cap, const int VC, const float *__restrict__ mu_prev,
+                  const float *__restrict__ mu_zero, float *__restrict__ act7) {
+    const long long n_rows = min((long long)agent_offset[B], out_cap);
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long r = i >> 3;
+    const int k = (int)(i & 7);
+    if (r >= n_rows || k == 0 || k >= PVE_OBS_H) return;
+    const int v = nbr_src[r * 8 + k];
+    const int env = ids[r * 4];
+    float a;
+    if (v < 0) a = mu_zero[0];                                                       /* TIS:1334: the all-zero row */
+    else if (v & 0x4000) a = mu_prev[(size_t)env * VC + (v & 0x3FFF)];               /* stored last tick */
+    else a = act7[((long long)agent_offset[env] + v) * PVE_OBS_H];                  /* this tick's row 0 of agent v */
+    act7[r * PVE_OBS_H + k] = a;
+}
+
 /* ---- plan: which rows add a record, and where ------------------------------------------------ */
 /* plan[r] = emits | is_new << 1 | (records of earlier rows of the same 256-row block) << 2 */
 __global__ void __launch_bounds__(PVN_PLAN_THREADS)

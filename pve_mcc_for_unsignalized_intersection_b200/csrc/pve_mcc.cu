@@ -126,7 +126,7 @@ struct PveResident {
         return nt == 96 ? BY_SMEM : nt == 512 ? (BY_SMEM < 2 ? BY_SMEM : 2) : (CTAS128 * 128 / nt > 0 ? CTAS128 * 128 / nt : 1);
     }
 };
-template <int NT, int VC, int AC>
+template <int NT, int VC, int AC, bool SRC>
 __global__ void __launch_bounds__(NT, PveResident<VC, AC>::blocks(NT))
 pve_step_kernel(const PveParams P, const PveState S, const pve_outputs O, const int32_t *spawn_tick,
                 const float *actions, const int phase) {
@@ -134,7 +134,7 @@ pve_step_kernel(const PveParams P, const PveState S, const pve_outputs O, const 
     /* CTAs are dispatched in index order; starting the busiest intersections first shortens the tail
      * of the launch (a CTA lives ~22 us, a launch of 4096 ~100 us) */
     const int b = S.order ? S.order[blockIdx.x] : (int)blockIdx.x;
-    pve_step_block<NT, VC, AC>(P, S, O, spawn_tick, actions, phase, b, pve_smem);
+    pve_step_block<NT, VC, AC, SRC>(P, S, O, spawn_tick, actions, phase, b, pve_smem);
 }
 
 /* order[i] = intersections sorted by their agent count, descending (counting sort, one CTA) */
@@ -323,19 +323,25 @@ static bool pick_class(int veh_cap, int agent_cap, int *VC, int *AC, size_t *sme
 }
 
 #ifndef PVE_HOST_EMULATION
-template <int NT, int VC, int AC>
-static cudaError_t launch_one(pve_scene *s, const float *actions, const pve_outputs &O, pve_stream_t stream) {
+template <int NT, int VC, int AC, bool SRC>
+static cudaError_t launch_variant(pve_scene *s, const float *actions, const pve_outputs &O, pve_stream_t stream) {
     static bool attr_set[16] = {false};
     int dev = s->device & 15;
     if (!attr_set[dev]) {
-        cudaError_t e = cudaFuncSetAttribute(pve_step_kernel<NT, VC, AC>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        cudaError_t e = cudaFuncSetAttribute(pve_step_kernel<NT, VC, AC, SRC>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              (int)(PveLayout<VC, AC>::BYTES + s->smem_pad));
         if (e != cudaSuccess) return e;
         attr_set[dev] = true;
     }
-    pve_step_kernel<NT, VC, AC><<<s->cfg.n_envs, NT, PveLayout<VC, AC>::BYTES + s->smem_pad, stream>>>(
+    pve_step_kernel<NT, VC, AC, SRC><<<s->cfg.n_envs, NT, PveLayout<VC, AC>::BYTES + s->smem_pad, stream>>>(
         s->prm, s->st, O, s->spawn_tick, actions, s->phase);
     return cudaGetLastError();
+}
+/* the instantiation that also writes pve_outputs.nbr_src only when the caller asks for that output */
+template <int NT, int VC, int AC>
+static cudaError_t launch_one(pve_scene *s, const float *actions, const pve_outputs &O, pve_stream_t stream) {
+    return O.nbr_src ? launch_variant<NT, VC, AC, true>(s, actions, O, stream)
+                     : launch_variant<NT, VC, AC, false>(s, actions, O, stream);
 }
 #endif
 
@@ -379,7 +385,7 @@ static int32_t launch_step(pve_scene *s, const float *actions, const pve_outputs
         done = true;                                                                           \
         for (int b = 0; b < B; ++b) {                                                          \
             memset(smem, 0xA5, s->smem_bytes); /* poison: catches reads of unwritten shared memory */ \
-            pve_step_block<64, vc, ac>(s->prm, s->st, O, s->spawn_tick, actions, s->phase, b, smem); \
+            pve_step_block<64, vc, ac, true>(s->prm, s->st, O, s->spawn_tick, actions, s->phase, b, smem); \
         }                                                                                      \
     }
     PVE_CLASSES(X)
@@ -836,15 +842,16 @@ void pve_actor_destroy(pve_actor *a) {
 #ifndef PVE_HOST_EMULATION
 static cudaError_t launch_actor(pve_actor *a, const float *rows, const pve_veh_meta *meta, const int32_t *n_veh,
                                 const float *noise, float noise_scale, float *actions, int slots_per_env, int n_env,
-                                long long n_slots, pve_stream_t stream, const int32_t *limit_dev = nullptr, int limit_mult = 1) {
+                                long long n_slots, pve_stream_t stream, const int32_t *limit_dev = nullptr, int limit_mult = 1,
+                                const uint8_t *mask = nullptr, int slot_step = 1) {
     if (a->use_mma) {
         const int blocks = n_env < a->blocks_mma ? n_env : a->blocks_mma;
         pve_actor_mma_kernel<<<blocks, PVM_THREADS, PVM_SMEM_BYTES, stream>>>(a->pw_dev, rows, meta, n_veh, noise, noise_scale,
-                                                                           actions, slots_per_env, n_env, n_slots, a->ticket, limit_dev, limit_mult);
+                                                                           actions, slots_per_env, n_env, n_slots, a->ticket, limit_dev, limit_mult, mask, slot_step);
     } else {
         const int blocks = n_env < a->blocks_ffma ? n_env : a->blocks_ffma;
         pve_actor_kernel<<<blocks, PVA_THREADS, PVA_SMEM_BYTES, stream>>>(a->w_dev, rows, meta, n_veh, noise, noise_scale,
-                                                                       actions, slots_per_env, n_env, n_slots, a->ticket, limit_dev, limit_mult);
+                                                                       actions, slots_per_env, n_env, n_slots, a->ticket, limit_dev, limit_mult, mask, slot_step);
     }
     return cudaGetLastError();
 }
@@ -961,6 +968,11 @@ struct pve_nstep {
     long long *counters;         /* [4] device */
     long long out_cap, pushes;
     int n_blk, device, fold_blocks;
+    /* pve_nstep_push_scene only (allocated on first use): referenced-row marks and actions of last tick's stored rows */
+    uint8_t *need;               /* [B][veh_cap] */
+    float *mu_prev;              /* [B][veh_cap] */
+    float *zero_row;             /* [28] zeros + [1] mu'(zero row) */
+    size_t scene_slots;
 };
 
 void pve_nstep_destroy(pve_nstep *f) {
@@ -968,6 +980,7 @@ void pve_nstep_destroy(pve_nstep *f) {
 #ifndef PVE_HOST_EMULATION
     cudaFree(f->T.key); cudaFree(f->T.fill); cudaFree(f->T.rew); cudaFree(f->T.frames);
     cudaFree(f->R.state); cudaFree(f->R.action); cudaFree(f->R.reward); cudaFree(f->R.next_state); cudaFree(f->R.done);
+    cudaFree(f->need); cudaFree(f->mu_prev); cudaFree(f->zero_row);
     cudaFree(f->act7); cudaFree(f->q); cudaFree(f->plan); cudaFree(f->blk_count); cudaFree(f->blk_base); cudaFree(f->counters);
 #endif
     free(f);
@@ -1019,6 +1032,10 @@ int32_t pve_nstep_create(int32_t n_envs, int32_t uid_slots, int32_t seq_max_step
 #endif
 }
 
+#ifndef PVE_HOST_EMULATION
+static int32_t nstep_fold(pve_nstep *f, const pve_outputs *O, double gamma, pve_critic *target_critic, void *stream_);
+#endif
+
 int32_t pve_nstep_push(pve_nstep *f, const pve_outputs *O, double gamma, pve_actor *target_actor,
                        pve_critic *target_critic, void *stream_) {
     if (!f || !O || !target_actor || !target_critic || !O->agent_offset || !O->ids || !O->status || !O->obs || !O->reward)
@@ -1028,12 +1045,20 @@ int32_t pve_nstep_push(pve_nstep *f, const pve_outputs *O, double gamma, pve_act
     return PVE_ESTATE;
 #else
     if (target_actor->device != f->device || target_critic->device != f->device) return PVE_EINVAL;
-    pve_stream_t stream = (pve_stream_t)stream_;
     const int32_t *n_rows_dev = O->agent_offset + f->T.B;
     /* mu'(s'[k]) for the 7 rows of every observation, then Q' (main.py:253-260) */
     int32_t rc = pve_actor_forward_n(target_actor, O->obs, f->out_cap * PVE_OBS_H, n_rows_dev, PVE_OBS_H, f->act7, stream_);
     if (rc != PVE_OK) return rc;
-    rc = pve_critic_forward(target_critic, O->obs, f->act7, f->out_cap, n_rows_dev, f->q, stream_);
+    return nstep_fold(f, O, gamma, target_critic, stream_);
+#endif
+}
+
+#ifndef PVE_HOST_EMULATION
+/* Q' from f->act7, then plan / scan / fold */
+static int32_t nstep_fold(pve_nstep *f, const pve_outputs *O, double gamma, pve_critic *target_critic, void *stream_) {
+    pve_stream_t stream = (pve_stream_t)stream_;
+    const int32_t *n_rows_dev = O->agent_offset + f->T.B;
+    int32_t rc = pve_critic_forward(target_critic, O->obs, f->act7, f->out_cap, n_rows_dev, f->q, stream_);
     if (rc != PVE_OK) return rc;
     const unsigned stamp = (unsigned)(++f->pushes);
     pvn_plan_kernel<<<f->n_blk, PVN_PLAN_THREADS, 0, stream>>>(f->T, O->ids, O->status, O->agent_offset, f->out_cap, stamp,
@@ -1042,6 +1067,57 @@ int32_t pve_nstep_push(pve_nstep *f, const pve_outputs *O, double gamma, pve_act
     pvn_fold_kernel<<<f->fold_blocks, 256, 0, stream>>>(f->T, f->R, O->ids, O->status, O->obs, O->reward, f->q, O->agent_offset,
                                                         f->out_cap, stamp, gamma, f->plan, f->blk_base);
     return cudaGetLastError() == cudaSuccess ? PVE_OK : PVE_ECUDA;
+}
+#endif
+
+int32_t pve_nstep_push_scene(pve_nstep *f, pve_scene *s, const pve_outputs *O, double gamma, pve_actor *target_actor,
+                             pve_critic *target_critic, void *stream_) {
+    if (!f || !s || !O || !target_actor || !target_critic || !O->agent_offset || !O->ids || !O->status || !O->obs
+        || !O->reward || !O->nbr_src)
+        return PVE_EINVAL;
+#ifdef PVE_HOST_EMULATION
+    (void)gamma; (void)stream_;
+    return PVE_ESTATE;
+#else
+    if (target_actor->device != f->device || target_critic->device != f->device || s->device != f->device
+        || s->cfg.n_envs != f->T.B)
+        return PVE_EINVAL;
+    pve_stream_t stream = (pve_stream_t)stream_;
+    const int B = f->T.B, VCc = s->prm.VC;
+    const size_t slots = (size_t)B * VCc;
+    if (!f->need || f->scene_slots != slots) {
+        cudaFree(f->need); cudaFree(f->mu_prev); cudaFree(f->zero_row);
+        f->need = nullptr; f->mu_prev = nullptr; f->zero_row = nullptr;
+        if (cudaMalloc((void **)&f->need, slots) != cudaSuccess || cudaMalloc((void **)&f->mu_prev, slots * sizeof(float)) != cudaSuccess
+            || cudaMalloc((void **)&f->zero_row, 32 * sizeof(float)) != cudaSuccess
+            || cudaMemsetAsync(f->zero_row, 0, 32 * sizeof(float), stream) != cudaSuccess) {
+            cudaGetLastError();
+            return PVE_ENOMEM;
+        }
+        f->scene_slots = slots;
+    }
+    const int32_t *n_rows_dev = O->agent_offset + B;
+    const long long rows7 = f->out_cap * PVE_OBS_H;
+    if (rows7 > 0x7fffffffLL || (long long)slots > 0x7fffffffLL) return PVE_EINVAL;
+    /* 1. this tick's agent rows (row 0 of every observation), written to act7[r][0] in place */
+    if (launch_actor(target_actor, O->obs, nullptr, nullptr, nullptr, 0.f, f->act7, PVA_TILE, (int)((rows7 + PVA_TILE - 1) / PVA_TILE),
+                     rows7, stream, n_rows_dev, PVE_OBS_H, nullptr, PVE_OBS_H) != cudaSuccess) return PVE_ECUDA;
+    /* 2. the rows stored last tick that some observation refers to (the buffer the last step read from) */
+    if (cudaMemsetAsync(f->need, 0, slots, stream) != cudaSuccess) return PVE_ECUDA;
+    const long long items = f->out_cap * 8;
+    const int grid = (int)((items + 255) / 256);
+    pvn_mark_kernel<<<grid, 256, 0, stream>>>(O->nbr_src, O->ids, O->agent_offset, B, f->out_cap, VCc, f->need);
+    if (launch_actor(target_actor, s->st.row0[s->phase ^ 1], nullptr, nullptr, nullptr, 0.f, f->mu_prev, PVA_TILE,
+                     (int)((slots + PVA_TILE - 1) / PVA_TILE), (long long)slots, stream, nullptr, 1, f->need, 1) != cudaSuccess)
+        return PVE_ECUDA;
+    /* 3. the all-zero row of a missing neighbour (TIS:1334) */
+    if (launch_actor(target_actor, f->zero_row, nullptr, nullptr, nullptr, 0.f, f->zero_row + 28, PVA_TILE, 1, 1, stream) != cudaSuccess)
+        return PVE_ECUDA;
+    /* 4. act7[r][1..6] through nbr_src */
+    pvn_gather_kernel<<<grid, 256, 0, stream>>>(O->nbr_src, O->ids, O->agent_offset, B, f->out_cap, VCc, f->mu_prev,
+                                                f->zero_row + 28, f->act7);
+    if (cudaGetLastError() != cudaSuccess) return PVE_ECUDA;
+    return nstep_fold(f, O, gamma, target_critic, stream_);
 #endif
 }
 

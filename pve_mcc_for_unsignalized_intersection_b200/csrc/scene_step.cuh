@@ -455,7 +455,9 @@ PVE_DEV void pve_world_xy(const PveParams &P, double p, int lane, double *x, dou
 /* ---------------------------------------------------------------------------------------------
  * one tick of intersection b
  * ------------------------------------------------------------------------------------------- */
-template <int NT, int VC, int AC>
+/* SRC: also write pve_outputs.nbr_src.  A template flag, not a run-time test: with the code present but switched off
+ * the default kernel measured 2-4 % slower (different register allocation), so it exists in its own instantiation. */
+template <int NT, int VC, int AC, bool SRC = false>
 PVE_DEV void pve_step_block(const PveParams &P, const PveState &S, const pve_outputs &O,
                             const int32_t *PVE_RESTRICT spawn_tick, const float *PVE_RESTRICT actions,
                             const int phase, const int b, unsigned char *smem) {
@@ -1145,6 +1147,25 @@ PVE_DEV void pve_step_block(const PveParams &P, const PveState &S, const pve_out
             PVE_RED_ADD(&st[PVE_STAT_Q5U], (double)misc[M_Q5U]);
         }
     PVE_END_TID_NOSYNC
+
+    /* ---- optional output: where the 7 observation rows of every agent were copied from (pve_outputs.nbr_src).
+     *      Only in the SRC instantiation of the kernel. */
+    if (SRC && O.nbr_src != nullptr && out_ok) {
+        PVE_FOR_TEAM(tid)
+            for (int g = tid; g < A; g += NS) {
+                uint32_t w4[4];
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                    const uint32_t c = q < PVE_OBS_H ? srcc[g * 7 + q] : (uint32_t)(AC * 7);
+                    const uint32_t v = c == (uint32_t)(AC * 7) ? 0xFFFFu
+                                       : (c & PVE_SRC_PREV) ? (0x4000u | ((c & 0x7FFFu) / 7u)) : c / 7u;
+                    if (q & 1) w4[q >> 1] |= v << 16; else w4[q >> 1] = v;
+                }
+                pve_v4 nb; nb.x = w4[0]; nb.y = w4[1]; nb.z = w4[2]; nb.w = w4[3];
+                ((pve_v4 *)O.nbr_src)[obase + g] = nb;
+            }
+        PVE_END_TID_NOSYNC
+    }
 
     /* ---- N: observation rows leave the SM (already under way on the upper half when the CTA is split) */
 #ifdef __CUDACC__

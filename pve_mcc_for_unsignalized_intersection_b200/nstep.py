@@ -170,11 +170,21 @@ class NStepFolder:
     def _stream(self):
         return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
 
-    def push(self, outputs, gamma):
-        """main.py:243-266 for the tick that produced ``outputs`` (a ``StepOutputs``).  Asynchronous."""
+    def push(self, outputs, gamma, distinct_rows=None):
+        """main.py:243-266 for the tick that produced ``outputs`` (a ``StepOutputs``).  Asynchronous.
+        ``distinct_rows``: None = use the scene's neighbour sources when it exports them; False = always evaluate the
+        target actor on all 7 rows of every observation."""
         o = outputs.native()
-        rc = self.lib.pve_nstep_push(self._h, C.byref(o), float(gamma), self.target_actor._h, self.target_critic._h,
-                                     self._stream())
+        if distinct_rows is None:
+            distinct_rows = getattr(outputs, "nbr_src", None) is not None and outputs is self.scene.out
+        if distinct_rows:
+            # the scene exported where every observation row came from (BatchedScene(neighbour_sources=True)): the
+            # target actor runs once per distinct row instead of on all 7 rows of every agent (same results)
+            rc = self.lib.pve_nstep_push_scene(self._h, self.scene._h, C.byref(o), float(gamma), self.target_actor._h,
+                                               self.target_critic._h, self._stream())
+        else:
+            rc = self.lib.pve_nstep_push(self._h, C.byref(o), float(gamma), self.target_actor._h, self.target_critic._h,
+                                         self._stream())
         if rc != 0:
             raise N.NativeError("pve_nstep_push failed with %d" % rc)
 

@@ -24,7 +24,7 @@ class StepOutputs:
     reused by the next ``step`` call.
     """
 
-    def __init__(self, B, out_cap, device):
+    def __init__(self, B, out_cap, device, neighbour_sources=False):
         z = lambda *s, dt: torch.zeros(*s, dtype=dt, device=device)
         self.agent_offset = z(B + 1, dt=torch.int32)
         self.obs = z(out_cap, OBS_H, OBS_W, dt=torch.float32)       # re_state
@@ -36,6 +36,9 @@ class StepOutputs:
         self.env_collisions = z(B, dt=torch.int32)                 # `collisions`
         self.env_lock = z(B, dt=torch.int32)                       # `lock`
         self.env_removed = z(B, dt=torch.int32)
+        # optional: where each of the 7 observation rows was copied from (include/pve_mcc.h, pve_outputs.nbr_src):
+        # -1 zero row; g' = row 0 of agent g' of the same intersection this tick; 0x4000 | k = last tick's row of slot k
+        self.nbr_src = z(out_cap, 8, dt=torch.int16) if neighbour_sources else None
         self._n = None
 
     FIELDS = ("agent_offset", "obs", "reward", "ids", "cpv", "status", "jerk_sum",
@@ -45,6 +48,7 @@ class StepOutputs:
         o = N.PveOutputs()
         for f in self.FIELDS:
             setattr(o, f, getattr(self, f).data_ptr())
+        o.nbr_src = self.nbr_src.data_ptr() if self.nbr_src is not None else None
         return o
 
     @property
@@ -68,7 +72,7 @@ class BatchedScene:
     """B independent 12-lane intersections resident on one GPU."""
 
     def __init__(self, n_envs, config=None, veh_cap=128, agent_cap=96, out_cap=None, device="cuda:0",
-                 threads=0, _library=None):
+                 threads=0, _library=None, neighbour_sources=False):
         self.cfg = config or SceneConfig()
         self.B, self.veh_cap, self.agent_cap = int(n_envs), int(veh_cap), int(agent_cap)
         self.out_cap = int(out_cap) if out_cap is not None else self.B * self.agent_cap
@@ -93,7 +97,7 @@ class BatchedScene:
         # capacities are rounded up to a compiled capacity class; the class value is the array stride
         self.veh_cap = int(self.lib.pve_veh_cap(self._h))
         self.agent_cap = int(self.lib.pve_agent_cap(self._h))
-        self.out = StepOutputs(self.B, self.out_cap, self.device)
+        self.out = StepOutputs(self.B, self.out_cap, self.device, neighbour_sources=neighbour_sources)
         self._out_native = self.out.native()
         self._spawn = None
         self._counters = torch.zeros(16, dtype=torch.float64, device=self.device)

@@ -18,14 +18,15 @@ from oracle.oracle import OracleScene, scene_params  # noqa: E402
 RTOL = 1e-5          # north-star tolerance: fp32 outputs against the float64 reference
 
 
-def make_scene(backend, B, vm=5, collision_thr=2, veh_cap=128, agent_cap=96, threads=0, out_cap=None):
+def make_scene(backend, B, vm=5, collision_thr=2, veh_cap=128, agent_cap=96, threads=0, out_cap=None,
+               neighbour_sources=False):
     cfg = SceneConfig(vm=vm, collision_thr=collision_thr)
     if backend == "cuda":
         return BatchedScene(B, cfg, veh_cap=veh_cap, agent_cap=agent_cap, out_cap=out_cap, device="cuda:0",
-                            threads=threads)
+                            threads=threads, neighbour_sources=neighbour_sources)
     from emul.build_emul import build_emul
     return BatchedScene(B, cfg, veh_cap=veh_cap, agent_cap=agent_cap, out_cap=out_cap, device="cpu",
-                        _library=build_emul())
+                        _library=build_emul(), neighbour_sources=neighbour_sources)
 
 
 def make_oracle(B, vm=5, collision_thr=2, veh_cap=128, n_threads=4):

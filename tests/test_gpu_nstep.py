@@ -233,3 +233,29 @@ def test_new_episode_keeps_the_memory_and_drops_the_buffers():
                 assert abs(rec["reward"][i] - target) <= T_RTOL * abs(target) + T_ATOL
             n_prev = c["num_experiences"]
     assert n_prev > 1000 and folder.counters()["slot_conflicts"] == 0
+
+
+def test_distinct_row_bootstrap_equals_the_seven_row_bootstrap():
+    """pve_nstep_push_scene (target actor once per distinct row, actions gathered through nbr_src) against pve_nstep_push
+    (target actor on all 7 rows of every observation): bootstrap values and replay memory bit for bit."""
+    aw, cw = nets()
+    B, S = 512, 12
+    scene = P.make_scene("cuda", B, vm=6, neighbour_sources=True)
+    scene.reset(synthetic_arrivals(B, 1000, 40.0, seed=8), warmup=False)
+    actor, critic = BatchedActor(aw), BatchedCritic(cw)
+    plain = NStepFolder(scene, actor, critic, S, buffer_size=3_000_000)
+    fast = NStepFolder(scene, actor, critic, S, buffer_size=3_000_000)
+    gen = torch.Generator(device="cuda").manual_seed(2)
+    for t in range(220):
+        acts = (torch.rand(B, scene.veh_cap, device="cuda", generator=gen) * 6 - 3) * scene.control_mask()
+        out = scene.step(acts.contiguous())
+        plain.push(out, 0.85, distinct_rows=False)
+        fast.push(out, 0.85)
+        if t % 20 == 19:
+            n = out.n_agents
+            assert torch.equal(plain.bootstrap_values()[:n], fast.bootstrap_values()[:n]), t
+    c0, c1 = plain.counters(), fast.counters()
+    assert c0["num_experiences"] == c1["num_experiences"] > 1_000_000 and c1["slot_conflicts"] == 0
+    n = c0["num_experiences"]
+    for k in ("state", "action", "reward", "next_state"):
+        assert torch.equal(plain.arrays()[k][:n], fast.arrays()[k][:n]), k

@@ -187,3 +187,7 @@ def test_step_host_zero_copy_and_staged_paths_at_scale(zerocopy, monkeypatch):
     n = scene.step_host(act, host2, copy_obs=True)
     P.compare_outputs(host_outputs_to_numpy(host2, n), o_ref, "pageable outputs")
     P.compare_states(scene.get_state(), orc.get_state(), "host path final")
+
+
+def test_neighbour_sources_name_the_copied_rows():
+    E.check_neighbour_sources("cuda")

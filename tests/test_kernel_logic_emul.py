@@ -129,3 +129,40 @@ def test_crafted_order_dependence_cases():
         for k in ("lane_n", "veh_rec", "head_lane", "head_j"):
             np.testing.assert_array_equal(st[k][0], r["post_" + k, c], err_msg="%s %s" % (name, k))
         P.assert_rel(st["row0"][0, :V], r["post_row0", c], name + " row0")
+
+
+def check_neighbour_sources(backend, ticks=160):
+    """pve_outputs.nbr_src: every observation row is bit for bit the row its source code names."""
+    B = 3
+    tabs = synthetic_arrivals(B, 1000, 40.0, seed=5, rows=32)
+    scene = P.make_scene(backend, B, vm=6, neighbour_sources=True)
+    scene.reset(tabs, warmup=True)
+    rng = np.random.RandomState(4)
+    seen = {"zero": 0, "new": 0, "prev": 0}
+    for t in range(ticks):
+        prev = scene.row0().detach().cpu().numpy().copy()           # rows stored by the previous tick, slot order
+        ctrl = scene.control_mask().detach().cpu().numpy()
+        out = scene.step(P.to_device_actions(scene, P.random_actions(rng, ctrl)))
+        n = out.n_agents
+        obs = out.obs[:n].detach().cpu().numpy()
+        src = out.nbr_src[:n].detach().cpu().numpy().astype(np.int32)
+        ids = out.ids[:n].detach().cpu().numpy()
+        off = out.agent_offset.detach().cpu().numpy()
+        assert np.all(src[:, 7] == -1)
+        for r in range(n):
+            b = ids[r, 0]
+            assert src[r, 0] == r - off[b]                          # entry 0: the agent itself
+            for k in range(1, 7):
+                v = src[r, k]
+                if v < 0:
+                    want = np.zeros(28, np.float32); seen["zero"] += 1
+                elif v & 0x4000:
+                    want = prev[b, v & 0x3FFF]; seen["prev"] += 1
+                else:
+                    want = obs[off[b] + v, 0]; seen["new"] += 1
+                assert np.array_equal(obs[r, k], want), (t, r, k, v)
+    assert min(seen.values()) > 100, seen
+
+
+def test_neighbour_sources_name_the_copied_rows():
+    check_neighbour_sources(BACKEND)
