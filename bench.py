@@ -394,9 +394,9 @@ def graft_arm(args, rank, world, local_rank):
                          "kernel": "pve_step_kernel", "kernel_ms_per_launch": my_kern_ms / K,
                          "algorithmic_bytes_per_launch": alg_bytes / K},
             # kernels inside the timed region of `value`: one step kernel per tick (+ one actor kernel in a rollout)
-            # (+ target actor on this tick's rows / last tick's referenced rows / the zero row, mark, gather, critic, plan,
-            # scan, fold in a training rollout)
-            "gpu_launches": K * ((11 if folder is not None else 2) if actor is not None else 1),
+            # (+ target actor on this tick's rows and on last tick's referenced rows, mark, gather, critic, plan, scan,
+            # fold in a training rollout; the memset of the marks is a driver operation)
+            "gpu_launches": K * ((10 if folder is not None else 2) if actor is not None else 1),
             "clocks": sampler.result(),
             "stats": {k: float(v) for k, v in zip(
                 ["agent_steps", "vehicle_steps", "env_steps", "spawned", "passed", "passed_step_total",
@@ -416,8 +416,8 @@ def graft_arm(args, rank, world, local_rank):
             fc = folder.counters()
             # per agent row: 784 B observation in + 784 B frame out; per record: 2 x 784 B frames in, 2 x 784 + 36 B out
             fold_bytes = (1568 * kA + 3172 * kA) / K
-            line["nstep"] = {"kernels": "pve_actor_mma_kernel x 3 (distinct rows: this tick's agents, last tick's referenced rows, "
-                                        "the zero row) + pvn_mark/gather + pve_critic_kernel + pvn_plan/scan/fold",
+            line["nstep"] = {"kernels": "pve_actor_mma_kernel x 2 (distinct rows: this tick's agents, last tick's referenced "
+                                        "rows) + pvn_mark/gather + pve_critic_kernel + pvn_plan/scan/fold",
                              "ms_per_push": float(sum(fold_ms)) / K, "seq_max_step": 12, "gamma": TRAIN_GAMMA,
                              "num_experiences": fc["num_experiences"], "records_last_push": fc["last_added"],
                              "slot_conflicts": fc["slot_conflicts"], "replay_capacity": folder.capacity,

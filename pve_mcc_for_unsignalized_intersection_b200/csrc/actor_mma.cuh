@@ -275,7 +275,6 @@ pve_actor_mma_kernel(const uint32_t *__restrict__ PW, const float *__restrict__ 
                 const int s = s0 + tid;
                 const long long gs = base + s;
                 bool want = s < total && gs < n_slots;
-                if (want && slot_step > 1) want = (gs % slot_step) == 0;      /* every slot_step-th row of a dense matrix */
                 if (want && mask) want = mask[gs] != 0;                      /* only the marked rows */
                 if (want && meta) {
                     const int e = s / slots_per_env;
@@ -286,7 +285,7 @@ pve_actor_mma_kernel(const uint32_t *__restrict__ PW, const float *__restrict__ 
                 int at = 0;
                 if (lane == 0 && bal) at = atomicAdd(&q_tail, __popc(bal));
                 at = __shfl_sync(0xffffffffu, at, 0);
-                if (want) ring[(at + __popc(bal & ((1u << lane) - 1u))) & (PVA_RING - 1)] = (int)gs;
+                if (want) ring[(at + __popc(bal & ((1u << lane) - 1u))) & (PVA_RING - 1)] = (int)(gs * slot_step);   /* slot -> row of `rows` / element of `actions` (slot_step > 1: strided matrix) */
             }
             __syncthreads();
         }

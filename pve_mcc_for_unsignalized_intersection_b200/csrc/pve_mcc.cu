@@ -785,6 +785,7 @@ struct pve_actor {
     int device;
     int blocks_ffma, blocks_mma; /* one resident wave of CTAs each */
     int use_mma;                 /* default 1; env PVE_ACTOR_IMPL=ffma selects the CUDA-core kernel */
+    float *zero_dev;             /* [28] zeros + [1] the action of an all-zero row (a missing neighbour, TIS:1334) */
 };
 
 int32_t pve_actor_create(const float *weights_host, int32_t n_floats, int32_t device, pve_actor **out) {
@@ -835,6 +836,7 @@ void pve_actor_destroy(pve_actor *a) {
     cudaFree(a->w_dev);
     cudaFree(a->pw_dev);
     cudaFree(a->ticket);
+    cudaFree(a->zero_dev);
 #endif
     free(a);
 }
@@ -971,7 +973,6 @@ struct pve_nstep {
     /* pve_nstep_push_scene only (allocated on first use): referenced-row marks and actions of last tick's stored rows */
     uint8_t *need;               /* [B][veh_cap] */
     float *mu_prev;              /* [B][veh_cap] */
-    float *zero_row;             /* [28] zeros + [1] mu'(zero row) */
     size_t scene_slots;
 };
 
@@ -980,7 +981,7 @@ void pve_nstep_destroy(pve_nstep *f) {
 #ifndef PVE_HOST_EMULATION
     cudaFree(f->T.key); cudaFree(f->T.fill); cudaFree(f->T.rew); cudaFree(f->T.frames);
     cudaFree(f->R.state); cudaFree(f->R.action); cudaFree(f->R.reward); cudaFree(f->R.next_state); cudaFree(f->R.done);
-    cudaFree(f->need); cudaFree(f->mu_prev); cudaFree(f->zero_row);
+    cudaFree(f->need); cudaFree(f->mu_prev);
     cudaFree(f->act7); cudaFree(f->q); cudaFree(f->plan); cudaFree(f->blk_count); cudaFree(f->blk_base); cudaFree(f->counters);
 #endif
     free(f);
@@ -1086,22 +1087,28 @@ int32_t pve_nstep_push_scene(pve_nstep *f, pve_scene *s, const pve_outputs *O, d
     const int B = f->T.B, VCc = s->prm.VC;
     const size_t slots = (size_t)B * VCc;
     if (!f->need || f->scene_slots != slots) {
-        cudaFree(f->need); cudaFree(f->mu_prev); cudaFree(f->zero_row);
-        f->need = nullptr; f->mu_prev = nullptr; f->zero_row = nullptr;
-        if (cudaMalloc((void **)&f->need, slots) != cudaSuccess || cudaMalloc((void **)&f->mu_prev, slots * sizeof(float)) != cudaSuccess
-            || cudaMalloc((void **)&f->zero_row, 32 * sizeof(float)) != cudaSuccess
-            || cudaMemsetAsync(f->zero_row, 0, 32 * sizeof(float), stream) != cudaSuccess) {
+        cudaFree(f->need); cudaFree(f->mu_prev);
+        f->need = nullptr; f->mu_prev = nullptr;
+        if (cudaMalloc((void **)&f->need, slots) != cudaSuccess || cudaMalloc((void **)&f->mu_prev, slots * sizeof(float)) != cudaSuccess) {
             cudaGetLastError();
             return PVE_ENOMEM;
         }
         f->scene_slots = slots;
     }
+    if (!target_actor->zero_dev) {      /* the action of the all-zero row of a missing neighbour (TIS:1334): once per network */
+        if (cudaMalloc((void **)&target_actor->zero_dev, 32 * sizeof(float)) != cudaSuccess) { cudaGetLastError(); return PVE_ENOMEM; }
+        if (cudaMemsetAsync(target_actor->zero_dev, 0, 32 * sizeof(float), stream) != cudaSuccess
+            || launch_actor(target_actor, target_actor->zero_dev, nullptr, nullptr, nullptr, 0.f, target_actor->zero_dev + 28,
+                            PVA_TILE, 1, 1, stream) != cudaSuccess)
+            return PVE_ECUDA;
+    }
     const int32_t *n_rows_dev = O->agent_offset + B;
     const long long rows7 = f->out_cap * PVE_OBS_H;
     if (rows7 > 0x7fffffffLL || (long long)slots > 0x7fffffffLL) return PVE_EINVAL;
     /* 1. this tick's agent rows (row 0 of every observation), written to act7[r][0] in place */
-    if (launch_actor(target_actor, O->obs, nullptr, nullptr, nullptr, 0.f, f->act7, PVA_TILE, (int)((rows7 + PVA_TILE - 1) / PVA_TILE),
-                     rows7, stream, n_rows_dev, PVE_OBS_H, nullptr, PVE_OBS_H) != cudaSuccess) return PVE_ECUDA;
+    if (launch_actor(target_actor, O->obs, nullptr, nullptr, nullptr, 0.f, f->act7, PVA_TILE,
+                     (int)((f->out_cap + PVA_TILE - 1) / PVA_TILE), f->out_cap, stream, n_rows_dev, 1, nullptr, PVE_OBS_H) != cudaSuccess)
+        return PVE_ECUDA;
     /* 2. the rows stored last tick that some observation refers to (the buffer the last step read from) */
     if (cudaMemsetAsync(f->need, 0, slots, stream) != cudaSuccess) return PVE_ECUDA;
     const long long items = f->out_cap * 8;
@@ -1110,12 +1117,9 @@ int32_t pve_nstep_push_scene(pve_nstep *f, pve_scene *s, const pve_outputs *O, d
     if (launch_actor(target_actor, s->st.row0[s->phase ^ 1], nullptr, nullptr, nullptr, 0.f, f->mu_prev, PVA_TILE,
                      (int)((slots + PVA_TILE - 1) / PVA_TILE), (long long)slots, stream, nullptr, 1, f->need, 1) != cudaSuccess)
         return PVE_ECUDA;
-    /* 3. the all-zero row of a missing neighbour (TIS:1334) */
-    if (launch_actor(target_actor, f->zero_row, nullptr, nullptr, nullptr, 0.f, f->zero_row + 28, PVA_TILE, 1, 1, stream) != cudaSuccess)
-        return PVE_ECUDA;
-    /* 4. act7[r][1..6] through nbr_src */
+    /* 3. act7[r][1..6] through nbr_src */
     pvn_gather_kernel<<<grid, 256, 0, stream>>>(O->nbr_src, O->ids, O->agent_offset, B, f->out_cap, VCc, f->mu_prev,
-                                                f->zero_row + 28, f->act7);
+                                                target_actor->zero_dev + 28, f->act7);
     if (cudaGetLastError() != cudaSuccess) return PVE_ECUDA;
     return nstep_fold(f, O, gamma, target_critic, stream_);
 #endif
