@@ -73,7 +73,7 @@ def workload_name(args):
         return "stress: headway 1.0 s on all 12 lanes, all-brake policy, %d intersections per GPU" % args.envs
     if args.workload == "train":
         return ("training rollout: %d intersections per GPU, synthetic Poisson arrivals %d veh/h/lane, pretrained actor "
-                "+ environment step + n-step folding (seq_max_step 12, target actor on 7 rows per agent, target critic) "
+                "+ environment step + n-step folding (seq_max_step 12, target actor once per distinct observation row, target critic) "
                 "+ replay writer (500 000 records) on the GPU every tick, vm=5" % (args.envs, args.density))
     if args.workload == "rollout":
         return ("full rollout: %d intersections per GPU, synthetic Poisson arrivals %d veh/h/lane, actions from the "
