@@ -20,6 +20,7 @@
 #include "scene_step.cuh"
 #include "actor_mma.cuh"
 #include "nstep.cuh"
+#include "critic_mma.cuh"
 
 #ifndef PVE_HOST_EMULATION
 #include <cuda_runtime.h>
@@ -909,8 +910,10 @@ int32_t pve_actor_forward_n(pve_actor *a, const float *rows_dev, int64_t max_row
 
 /* ---- critic + n-step folding + replay writer (N2) ------------------------------------------ */
 struct pve_critic {
-    float *w_dev;
-    int device, blocks;
+    float *w_dev;                /* flat fp32 parameters (FFMA kernel) */
+    uint32_t *pw_dev;            /* split bf16 fragments + vectors (tensor-core kernel) */
+    int device, blocks, blocks_mma;
+    int use_mma;                 /* default 1; env PVE_CRITIC_IMPL=ffma selects the CUDA-core kernel */
 };
 
 int32_t pve_critic_create(const float *weights_host, int32_t n_floats, int32_t device, pve_critic **out) {
@@ -925,12 +928,23 @@ int32_t pve_critic_create(const float *weights_host, int32_t n_floats, int32_t d
     c->device = device;
     int sms = 0, per_sm = 0;
     if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device) != cudaSuccess || sms <= 0) sms = 148;
-    bool ok = cudaFuncSetAttribute(pve_critic_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PVC_SMEM_BYTES) == cudaSuccess;
+    c->use_mma = 1;
+    if (const char *impl = getenv("PVE_CRITIC_IMPL")) c->use_mma = strcmp(impl, "ffma") != 0;
+    bool ok = cudaFuncSetAttribute(pve_critic_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PVC_SMEM_BYTES) == cudaSuccess
+              && cudaFuncSetAttribute(pve_critic_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PVQ_SMEM_BYTES) == cudaSuccess;
     if (ok && (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pve_critic_kernel, PVC_THREADS, PVC_SMEM_BYTES) != cudaSuccess || per_sm < 1)) per_sm = 1;
     c->blocks = per_sm * sms;
+    if (ok && (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pve_critic_mma_kernel, PVQ_THREADS, PVQ_SMEM_BYTES) != cudaSuccess || per_sm < 1)) per_sm = 1;
+    c->blocks_mma = per_sm * sms;
+    uint32_t *packed = ok ? (uint32_t *)malloc(sizeof(uint32_t) * PVQ_WORDS) : nullptr;
+    ok = ok && packed;
+    if (ok) pvq_pack(weights_host, packed);
     ok = ok && cudaMalloc((void **)&c->w_dev, sizeof(float) * PVE_CRITIC_FLOATS) == cudaSuccess
-            && cudaMemcpy(c->w_dev, weights_host, sizeof(float) * PVE_CRITIC_FLOATS, cudaMemcpyHostToDevice) == cudaSuccess;
-    if (!ok) { cudaFree(c->w_dev); free(c); cudaGetLastError(); return PVE_ECUDA; }
+            && cudaMalloc((void **)&c->pw_dev, sizeof(uint32_t) * PVQ_WORDS) == cudaSuccess
+            && cudaMemcpy(c->w_dev, weights_host, sizeof(float) * PVE_CRITIC_FLOATS, cudaMemcpyHostToDevice) == cudaSuccess
+            && cudaMemcpy(c->pw_dev, packed, sizeof(uint32_t) * PVQ_WORDS, cudaMemcpyHostToDevice) == cudaSuccess;
+    free(packed);
+    if (!ok) { cudaFree(c->w_dev); cudaFree(c->pw_dev); free(c); cudaGetLastError(); return PVE_ECUDA; }
     *out = c;
     return PVE_OK;
 #endif
@@ -940,6 +954,7 @@ void pve_critic_destroy(pve_critic *c) {
     if (!c) return;
 #ifndef PVE_HOST_EMULATION
     cudaFree(c->w_dev);
+    cudaFree(c->pw_dev);
 #endif
     free(c);
 }
@@ -952,10 +967,16 @@ int32_t pve_critic_forward(pve_critic *c, const float *obs_dev, const float *act
     return PVE_ESTATE;
 #else
     if (max_rows == 0) return PVE_OK;
-    const long long tiles = (max_rows + PVC_TILE - 1) / PVC_TILE;
-    const int blocks = (int)(tiles < c->blocks ? tiles : c->blocks);
-    pve_critic_kernel<<<blocks, PVC_THREADS, PVC_SMEM_BYTES, (pve_stream_t)stream_>>>(c->w_dev, obs_dev, act7_dev, q_dev,
-                                                                                     (long long)max_rows, n_rows_dev);
+    const long long tiles = (max_rows + PVC_TILE - 1) / PVC_TILE;              /* both kernels: 128 agents per tile */
+    if (c->use_mma) {
+        const int blocks = (int)(tiles < c->blocks_mma ? tiles : c->blocks_mma);
+        pve_critic_mma_kernel<<<blocks, PVQ_THREADS, PVQ_SMEM_BYTES, (pve_stream_t)stream_>>>(c->pw_dev, obs_dev, act7_dev, q_dev,
+                                                                                             (long long)max_rows, n_rows_dev);
+    } else {
+        const int blocks = (int)(tiles < c->blocks ? tiles : c->blocks);
+        pve_critic_kernel<<<blocks, PVC_THREADS, PVC_SMEM_BYTES, (pve_stream_t)stream_>>>(c->w_dev, obs_dev, act7_dev, q_dev,
+                                                                                         (long long)max_rows, n_rows_dev);
+    }
     return cudaGetLastError() == cudaSuccess ? PVE_OK : PVE_ECUDA;
 #endif
 }

@@ -40,8 +40,15 @@ def realistic_obs(rng, n):
     return obs
 
 
+@pytest.fixture(params=["mma", "ffma"])
+def critic_impl(request, monkeypatch):
+    """Both device implementations of the critic: tensor cores (bf16 x 3 split products, default) and fp32 FFMA."""
+    monkeypatch.setenv("PVE_CRITIC_IMPL", request.param)
+    return request.param
+
+
 @pytest.mark.parametrize("n", [1, 33, 127, 128, 129, 5000, 70001])
-def test_critic_kernel_against_oracle(n):
+def test_critic_kernel_against_oracle(n, critic_impl):
     _, cw = nets()
     critic = BatchedCritic(cw)
     rng = np.random.RandomState(n)
