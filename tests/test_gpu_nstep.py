@@ -242,7 +242,14 @@ def test_new_episode_keeps_the_memory_and_drops_the_buffers():
     assert n_prev > 1000 and folder.counters()["slot_conflicts"] == 0
 
 
-def test_distinct_row_bootstrap_equals_the_seven_row_bootstrap():
+@pytest.mark.parametrize("impl", ["mma", "ffma"])
+def test_distinct_row_bootstrap_equals_the_seven_row_bootstrap(impl, monkeypatch):
+    monkeypatch.setenv("PVE_ACTOR_IMPL", impl)             # both device implementations of the two networks
+    monkeypatch.setenv("PVE_CRITIC_IMPL", impl)
+    _distinct_row_bootstrap()
+
+
+def _distinct_row_bootstrap():
     """pve_nstep_push_scene (target actor once per distinct row, actions gathered through nbr_src) against pve_nstep_push
     (target actor on all 7 rows of every observation): bootstrap values and replay memory bit for bit."""
     aw, cw = nets()
