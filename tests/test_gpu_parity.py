@@ -191,3 +191,9 @@ def test_step_host_zero_copy_and_staged_paths_at_scale(zerocopy, monkeypatch):
 
 def test_neighbour_sources_name_the_copied_rows():
     E.check_neighbour_sources("cuda")
+
+
+def test_ragged_and_empty_intersections():
+    scene, n = E.free_run("cuda", E.edge_tables(), vm=5, ticks=320, seed=6)
+    st = scene.get_state()
+    assert st["id_seq"][1] == 36 and st["id_seq"][4] == 1 and st["tick"][3] > 30000 and n > 5000

@@ -166,3 +166,25 @@ def check_neighbour_sources(backend, ticks=160):
 
 def test_neighbour_sources_name_the_copied_rows():
     check_neighbour_sources(BACKEND)
+
+
+def edge_tables():
+    """Ragged batch: a normal intersection, one whose table runs out after three arrivals per lane, one fed on a
+    single lane only, one whose first arrival is 3 000 s away (the warm-up jumps there; sparse traffic afterwards),
+    one with a single early arrival followed by that sparse traffic."""
+    base = synthetic_arrivals(5, 1000, 40.0, seed=31, rows=24)
+    far = 3000.0                            # beyond the rollout, inside the clock table of to_spawn_ticks
+    t = base.copy()
+    t[1, 3:, :] = 0.0                       # zero-padded tail like the shipped fixtures: table exhausted
+    late = far + 10.0 * np.arange(t.shape[1])[:, None]
+    t[2, :, 1:] = late                      # only lane 0 receives traffic
+    t[3] = late                             # first arrival far away: the warm-up jumps there (TIS:214-220)
+    t[4] = late
+    t[4, 0, 7] = 2.0                        # one vehicle in the whole rollout
+    return t
+
+
+def test_ragged_and_empty_intersections():
+    scene, n = free_run(BACKEND, edge_tables(), vm=5, ticks=320, seed=6)
+    st = scene.get_state()
+    assert st["id_seq"][1] == 36 and st["id_seq"][4] == 1 and st["tick"][3] > 30000 and n > 5000
