@@ -197,3 +197,10 @@ def test_ragged_and_empty_intersections():
     scene, n = E.free_run("cuda", E.edge_tables(), vm=5, ticks=320, seed=6)
     st = scene.get_state()
     assert st["id_seq"][1] == 36 and st["id_seq"][4] == 1 and st["tick"][3] > 30000 and n > 5000
+
+
+def test_largest_capacity_class():
+    scene, n = E.free_run("cuda", stress_arrivals(1, 60.0, headway=0.7), vm=5, ticks=420, seed=3, veh_cap=576,
+                          agent_cap=416, policy="brake")
+    st = scene.get_state()
+    assert st["n_veh"][0] > 400 and st["n_ctrl"][0] > 384 and st["overflow"][0] == 0 and n > 100000

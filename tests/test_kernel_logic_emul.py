@@ -188,3 +188,12 @@ def test_ragged_and_empty_intersections():
     scene, n = free_run(BACKEND, edge_tables(), vm=5, ticks=320, seed=6)
     st = scene.get_state()
     assert st["id_seq"][1] == 36 and st["id_seq"][4] == 1 and st["tick"][3] > 30000 and n > 5000
+
+
+def test_largest_capacity_class():
+    """Headway 0.7 s on all 12 lanes with the all-brake policy fills an intersection to 483 vehicles / 407 agents:
+    only the 576/416 class holds that (maximum sizes; SURVEY 8: V <= 576, A <= 408)."""
+    scene, n = free_run(BACKEND, stress_arrivals(1, 60.0, headway=0.7), vm=5, ticks=420, seed=3, veh_cap=576,
+                        agent_cap=416, policy="brake")
+    st = scene.get_state()
+    assert st["n_veh"][0] > 400 and st["n_ctrl"][0] > 384 and st["overflow"][0] == 0 and n > 100000
