@@ -288,6 +288,8 @@ def graft_arm(args, rank, world, local_rank):
     barrier()
     wall1 = time.perf_counter()
     step_ms = [e0.elapsed_time(e1) for e0, e1 in ev]
+    first_timed = 1 + PRIME_TICKS + W          # index of the first timed step since reset
+    order_launches = sum(1 for t in range(first_timed, first_timed + K) if t % 32 == 0) if B >= 1024 else 0
     s1 = scene.stats()
     dA = s1["agent_steps"] - s0["agent_steps"]
     dV = s1["vehicle_steps"] - s0["vehicle_steps"]
@@ -396,7 +398,8 @@ def graft_arm(args, rank, world, local_rank):
             # kernels inside the timed region of `value`: one step kernel per tick (+ one actor kernel in a rollout)
             # (+ target actor on this tick's rows and on last tick's referenced rows, mark, gather, critic, plan, scan,
             # fold in a training rollout; the memset of the marks is a driver operation)
-            "gpu_launches": K * ((10 if folder is not None else 2) if actor is not None else 1),
+            # + pve_order_kernel, launched by every 32nd step since reset (the warm-up tick inside reset is step 0)
+            "gpu_launches": K * ((10 if folder is not None else 2) if actor is not None else 1) + order_launches,
             "clocks": sampler.result(),
             "stats": {k: float(v) for k, v in zip(
                 ["agent_steps", "vehicle_steps", "env_steps", "spawned", "passed", "passed_step_total",
