@@ -124,6 +124,7 @@ struct PveLayout {
     static constexpr uint32_t a16(uint32_t x) { return (x + 15u) & ~15u; }
     static constexpr uint32_t mx(uint32_t a, uint32_t b) { return a > b ? a : b; }
     static constexpr int EC = 5 * AC;
+    static constexpr int SC = EC + 12 * PVE_NLANE;      /* sorted lists: 6 sentinels below and above each direction's */
     static constexpr uint32_t HDR = 0;
     static constexpr uint32_t SP = a16(PVE_HDR_BYTES);
     static constexpr uint32_t SV = SP + 8 * VC;
@@ -137,9 +138,9 @@ struct PveLayout {
     static constexpr uint32_t ROW0 = R1;                          /* f32[AC + 1][28]; row AC is all zero */
     static constexpr uint32_t R1_BYTES = mx(mx(40 * VC, a16(10 * EC)), 112 * (AC + 1));
     static constexpr uint32_t R2 = a16(R1 + R1_BYTES);
-    static constexpr uint32_t SPOS = R2, SIDX = SPOS + 8 * EC;
+    static constexpr uint32_t SPOS = R2, SIDX = SPOS + 8 * SC;
     static constexpr uint32_t XY = R2;
-    static constexpr uint32_t R2_BYTES = mx(a16(10 * EC), 16 * AC);
+    static constexpr uint32_t R2_BYTES = mx(a16(10 * SC), 16 * AC);
     static constexpr uint32_t VIRDIS = a16(R2 + R2_BYTES);
     static constexpr uint32_t VD0 = VIRDIS + 8 * AC;
     static constexpr uint32_t DSUM = VD0 + 8 * AC;
@@ -162,7 +163,8 @@ struct PveLayout {
     static constexpr uint32_t NN0 = HDRA + 2 * AC;
     static constexpr uint32_t SRC = NN0 + 2 * AC;                /* u16[AC][8] gather codes */
     static constexpr uint32_t HEADK = SRC + 16 * AC;             /* i16[16] */
-    static constexpr uint32_t LANE_OF = HEADK + 32;
+    static constexpr uint32_t TIE = HEADK + 32;                  /* u8[16]: direction d has entries at equal positions */
+    static constexpr uint32_t LANE_OF = TIE + 16;
     static constexpr uint32_t FBITS = LANE_OF + VC;
     static constexpr uint32_t SSEL = FBITS + VC;
     static constexpr uint32_t DEL = SSEL + VC;
@@ -189,6 +191,7 @@ static_assert(M_COUNT <= 56, "misc block");
  * stored rows of this intersection (indexed by vehicle slot). */
 #define PVE_SRC_PREV 0x8000u
 #define PVE_ROW_BYTES (PVE_OBS_W * 4)
+#define PVE_INF (__builtin_huge_val())
 
 PVE_DEV void pve_prefetch_l2(const void *p) {
 #ifdef __CUDACC__
@@ -201,6 +204,21 @@ PVE_DEV void pve_prefetch_l2(const void *p) {
 PVE_DEV uint32_t pve_fbits(float f) { uint32_t u; memcpy(&u, &f, sizeof u); return u; }
 PVE_DEV pve_v4 pve_pack4(float a, float b, float c, float d) {
     pve_v4 r; r.x = pve_fbits(a); r.y = pve_fbits(b); r.z = pve_fbits(c); r.w = pve_fbits(d); return r;
+}
+/* byte q (0..11) of the 12-byte little-endian array {w0, w1, w2} */
+PVE_DEV uint32_t pve_byte12(uint32_t w0, uint32_t w1, uint32_t w2, int q) {
+    const uint32_t w = (q < 4) ? w0 : (q < 8 ? w1 : w2);
+    return (w >> ((q & 3) * 8)) & 0xFFu;
+}
+/* number of bytes of x that are <= the corresponding byte of y (unsigned) */
+PVE_DEV int pve_count_le4(uint32_t x, uint32_t y) {
+#ifdef __CUDACC__
+    return __popc(__vcmpleu4(x, y)) >> 3;
+#else
+    int c = 0;
+    for (int q = 0; q < 4; ++q) c += ((x >> (8 * q)) & 0xFFu) <= ((y >> (8 * q)) & 0xFFu);
+    return c;
+#endif
 }
 /* 1 if x < 0 else 0 (x is a difference of two finite doubles: a - b < 0 <=> a < b, and a - b is
  * +0 exactly when a == b) */
@@ -377,39 +395,42 @@ struct PveRowJob {
     int zero_row;                 /* index of the all-zero row of rows_smem */
 };
 
-template <int NT>
-PVE_DEV void pve_move_rows(const PveRowJob &J, int first_warp, int n_warps) {
+template <int NT, int NW>
+PVE_DEV void pve_move_rows(const PveRowJob &J, int first_warp) {
     if (J.oblk == nullptr) return;
 #ifdef __CUDACC__
-    /* The block of an intersection is contiguous: 49 16-byte pieces per agent.  Lane l of a mover warp
-     * handles piece x = l (mod the movers' width), so a warp stores 512 contiguous bytes per step.
-     * piece x -> row x / 7 -> its gather code -> source piece; the source is read from shared memory
-     * unless the code says "last tick's buffer", in which case a predicated global load overrides it.
-     * Four pieces are in flight per lane. */
-    const int n_v4 = J.A * (PVE_OBS_H * PVE_OBS_W / 4);
-    const int step = 32 * n_warps;
-    const pve_v4 *PVE_RESTRICT prev = (const pve_v4 *)J.rows_prev;
-    const pve_v4 *rows = (const pve_v4 *)J.rows_smem;
-    pve_v4 *PVE_RESTRICT dst = J.oblk;
+    /* The block of an intersection is contiguous: A x 7 rows of 7 16-byte pieces.  Eight lanes share a row
+     * (lane & 7 = piece, the eighth lane idles), so a quarter-warp reads one 112-byte row -- seven distinct
+     * bank groups, no conflicts whatever rows the four quarters hold -- and a warp stores 448 contiguous
+     * bytes.  The row's gather code is read once per row (a broadcast); the source is read from shared
+     * memory unless the code says "last tick's buffer", in which case a predicated global load overrides
+     * it.  Four rows are in flight per lane. */
+    const int t = (int)threadIdx.x - first_warp * 32;
+    const int piece = t & 7;
+    if (piece == 7) return;
+    const int n_rows = J.A * PVE_OBS_H;
+    constexpr int RSTEP = 4 * NW;                         /* rows taken by the mover warps per step */
+    const pve_v4 *PVE_RESTRICT prev = (const pve_v4 *)J.rows_prev + piece;
+    const pve_v4 *rows = (const pve_v4 *)J.rows_smem + piece;
+    pve_v4 *PVE_RESTRICT dst = J.oblk + piece;
     const uint32_t zero7 = (uint32_t)J.zero_row * 7u;
-    for (int x = (int)threadIdx.x - first_warp * 32; x < n_v4; x += 4 * step) {
+    for (int row = t >> 3; row < n_rows; row += 4 * RSTEP) {
         pve_v4 val[4];
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
-            const int xu = x + u * step;
-            const uint32_t row = __umulhi((uint32_t)xu, 613566757u);             /* xu / 7 */
-            const uint32_t code = (xu < n_v4) ? (uint32_t)J.srcc[row] : zero7;
+            const int ru = row + u * RSTEP;
+            const uint32_t code = (ru < n_rows) ? (uint32_t)J.srcc[ru] : zero7;
             const bool is_prev = (code & PVE_SRC_PREV) != 0;
-            const uint32_t src = (code & 0x7FFFu) + ((uint32_t)xu - row * 7u);
+            const uint32_t src = code & 0x7FFFu;
             val[u] = rows[is_prev ? zero7 : src];
             if (is_prev) val[u] = prev[src];
         }
 #pragma unroll
         for (int u = 0; u < 4; ++u)
-            if (x + u * step < n_v4) dst[x + u * step] = val[u];
+            if (row + u * RSTEP < n_rows) dst[(row + u * RSTEP) * 7] = val[u];
     }
 #else
-    (void)first_warp; (void)n_warps;
+    (void)first_warp;
     for (int it = 0; it < J.A * PVE_OBS_H; ++it) {
         const uint32_t c = J.srcc[it];
         const float *src = ((c & PVE_SRC_PREV) ? J.rows_prev : J.rows_smem) + (size_t)(c & 0x7FFFu) * 4;
@@ -488,6 +509,7 @@ PVE_DEV void pve_step_block(const PveParams &P, const PveState &S, const pve_out
     int16_t *const hdra = (int16_t *)(smem + L::HDRA);
     uint16_t *const nn0 = (uint16_t *)(smem + L::NN0), *const srcc = (uint16_t *)(smem + L::SRC);
     int16_t *const headk = (int16_t *)(smem + L::HEADK);
+    uint8_t *const tie = smem + L::TIE;
     uint8_t *const lane_of = smem + L::LANE_OF, *const fbits = smem + L::FBITS, *const ssel = smem + L::SSEL;
     uint8_t *const del = smem + L::DEL, *const slock = smem + L::SLOCK, *const ctl0 = smem + L::CTL0;
     int8_t *const slocka = (int8_t *)(smem + L::SLOCKA);
@@ -532,16 +554,33 @@ PVE_DEV void pve_step_block(const PveParams &P, const PveState &S, const pve_out
         }
         if (tid < PVE_HDR_BYTES / 16) ((pve_v4 *)hdr)[tid] = gh[tid];
         for (int q = tid + 1; q < M_COUNT; q += NT) misc[q] = 0;                 /* misc[M_V] is written below */
-        if (tid < 16) { vl_cnt[tid] = 0; headk[tid] = -1; }
-        int V_ = 0;
+        if (tid < 16) { vl_cnt[tid] = 0; headk[tid] = -1; tie[tid] = 0; }
+        /* lane lengths -> inclusive prefix, one byte per lane (V <= 255; the large classes take 16-bit sums) */
+        uint32_t ip0, ip1, ip2, ex0, ex1, ex2;
+        int V_;
+        if (VC <= 255) {
+            ip0 = lw[2]; ip1 = lw[3]; ip2 = lw[4];
+            ip0 += ip0 << 8; ip0 += ip0 << 16;
+            ip1 += ip1 << 8; ip1 += ip1 << 16;
+            ip2 += ip2 << 8; ip2 += ip2 << 16;
+            ip1 += (ip0 >> 24) * 0x01010101u;
+            ip2 += (ip1 >> 24) * 0x01010101u;
+            ex0 = ip0 << 8; ex1 = (ip1 << 8) | (ip0 >> 24); ex2 = (ip2 << 8) | (ip1 >> 24);      /* exclusive prefix */
+            V_ = (int)(ip2 >> 24);
+            if (tid <= PVE_NLANE) lane_off[tid] = tid < PVE_NLANE ? (int)pve_byte12(ex0, ex1, ex2, tid) : V_;
+            if (tid == 0) misc[M_V] = V_;
+        } else {
+            ip0 = ip1 = ip2 = ex0 = ex1 = ex2 = 0;
+            V_ = 0;
 #pragma unroll
-        for (int q = 0; q < PVE_NLANE; ++q) V_ += (int)PVE_LW_BYTE(8 + q);
-        if (tid == 0) {
-            int o = 0;
+            for (int q = 0; q < PVE_NLANE; ++q) V_ += (int)PVE_LW_BYTE(8 + q);
+            if (tid == 0) {
+                int o = 0;
 #pragma unroll
-            for (int q = 0; q < PVE_NLANE; ++q) { lane_off[q] = o; o += (int)PVE_LW_BYTE(8 + q); }
-            lane_off[PVE_NLANE] = o;
-            misc[M_V] = o;
+                for (int q = 0; q < PVE_NLANE; ++q) { lane_off[q] = o; o += (int)PVE_LW_BYTE(8 + q); }
+                lane_off[PVE_NLANE] = o;
+                misc[M_V] = o;
+            }
         }
         for (int k = tid; k < V_; k += NT) {
             if (k != tid) {
@@ -550,12 +589,22 @@ PVE_DEV void pve_step_block(const PveParams &P, const PveState &S, const pve_out
             }
             const double act = (double)actf;
             /* lane of slot k: the last lane whose first slot is <= k; and its virtual-lane head */
-            int i = 0, off_i = 0, o = 0;
-            int hl = (int)(int8_t)PVE_LW_BYTE(20), hj = (int)PVE_LW_BYTE(32);
+            int i, off_i, hl, hj;
+            if (VC <= 255) {
+                const uint32_t kk = (uint32_t)k * 0x01010101u;
+                i = pve_count_le4(ip0, kk) + pve_count_le4(ip1, kk) + pve_count_le4(ip2, kk);       /* lanes that end at or before k */
+                off_i = (int)pve_byte12(ex0, ex1, ex2, i);
+                hl = (int)(int8_t)pve_byte12(lw[5], lw[6], lw[7], i);
+                hj = (int)pve_byte12(lw[8], lw[9], lw[10], i);
+            } else {
+                int o = 0;
+                i = 0; off_i = 0;
+                hl = (int)(int8_t)PVE_LW_BYTE(20); hj = (int)PVE_LW_BYTE(32);
 #pragma unroll
-            for (int q = 1; q < PVE_NLANE; ++q) {
-                o += (int)PVE_LW_BYTE(8 + q - 1);
-                if (k >= o) { i = q; off_i = o; hl = (int)(int8_t)PVE_LW_BYTE(20 + q); hj = (int)PVE_LW_BYTE(32 + q); }
+                for (int q = 1; q < PVE_NLANE; ++q) {
+                    o += (int)PVE_LW_BYTE(8 + q - 1);
+                    if (k >= o) { i = q; off_i = o; hl = (int)(int8_t)PVE_LW_BYTE(20 + q); hj = (int)PVE_LW_BYTE(32 + q); }
+                }
             }
             const int j = k - off_i;
             const uint32_t fl = mt.packed >> 24;
@@ -731,7 +780,9 @@ PVE_DEV void pve_step_block(const PveParams &P, const PveState &S, const pve_out
         }
     PVE_END_TID
 
-    /* ---- F: stable sort by position (TIS:271) as a rank count on the key (pos, slot) ------ */
+    /* ---- F: stable sort by position (TIS:271) as a rank count on the key (pos, slot).  The sorted list of
+     *         direction d lives at spos[vl_base[d] + 12 d + 6 ...] between six -inf and six +inf sentinels,
+     *         so that phase G1 reads its twelve candidates without bounds checks ---------------------- */
     PVE_FOR_TID(tid)
         for (int e = tid; e < vl_base[PVE_NLANE]; e += NT) {
             const int d = edir[e];
@@ -739,22 +790,30 @@ PVE_DEV void pve_step_block(const PveParams &P, const PveState &S, const pve_out
                 const int base = vl_base[d], n = vl_cnt[d];
                 const double pos = epos[e];
                 const int idx = eidx[e];
-                uint32_t less = 0, greater = 0;
+                int less = 0, le = 0;
                 int t = 0;
 #pragma unroll 4
                 for (t = 0; t < n; ++t) {
                     const double pt = epos[base + t];
-                    less += pve_isneg(pt - pos);
-                    greater += pve_isneg(pos - pt);
+                    less += (pt < pos) ? 1 : 0;
+                    le += (pt <= pos) ? 1 : 0;
                 }
-                int rank = (int)less;
-                if (n - (int)less - (int)greater > 1)   /* equal positions keep insertion (slot) order */
+                int rank = less;
+                if (le - less > 1) {            /* equal positions keep insertion (slot) order */
                     for (t = 0; t < n; ++t)
                         rank += (epos[base + t] == pos && (int)eidx[base + t] < idx) ? 1 : 0;
-                spos[base + rank] = pos; sidx[base + rank] = (uint16_t)idx;
+                    tie[d] = 1;
+                }
+                const int sb = base + 12 * d + 6;
+                spos[sb + rank] = pos; sidx[sb + rank] = (uint16_t)idx;
                 if (lane_of[idx] == d) arank[acnt[idx]] = (uint16_t)rank;
                 if (rank == 0) headk[d] = (int16_t)idx;     /* virtual_lane_4[d][0], read by step() (Q2) */
             }
+        }
+        for (int q = tid; q < 12 * PVE_NLANE; q += NT) {       /* the sentinels */
+            const int d = q / 12, w = q - d * 12;
+            const int sb = vl_base[d] + 12 * d + 6;
+            if (w < 6) spos[sb - 1 - w] = -PVE_INF; else spos[sb + vl_cnt[d] + (w - 6)] = PVE_INF;
         }
     PVE_END_TID
 
@@ -763,83 +822,74 @@ PVE_DEV void pve_step_block(const PveParams &P, const PveState &S, const pve_out
         for (int g = tid; g < A; g += NT) {
             const int k = vidx[g];
             const int d = lane_of[k];
-            const int base = vl_base[d], n = vl_cnt[d], r = arank[g];
-            const double pe = spos[base + r];
-            /* vir_header / vir_dis, TIS:1349-1354 */
-            if (r == 0) { hdra[g] = -1; virdis[g] = 100.0; }
-            else { hdra[g] = (int16_t)acnt[sidx[base + r - 1]]; virdis[g] = pe - spos[base + r - 1]; }
+            const int sb = vl_base[d] + 12 * d + 6, n = vl_cnt[d], r = arank[g];
+            const double *const S = spos + sb;                  /* S[-6..-1] = -inf, S[n..n+5] = +inf */
+            const uint16_t *const SI = sidx + sb;
+            const double pe = S[r];
             /* Six nearest by |delta|, ties to the lower list index (stable sort, TIS:1389).  Only the six
-             * entries below and the six above the ego can qualify.  Instead of walking outwards (a
-             * serial chain of dependent loads) every candidate computes its position in the stable
-             * order by counting the candidates that precede it: below-side entries have lower list
-             * indices, so on equal |delta| they win against above-side ones, and among themselves the
-             * farther one (lower index) wins. */
-            pve_v4 *const orow = (pve_v4 *)(row0 + (size_t)g * PVE_OBS_W);
-            orow[0] = pve_pack4((float)pe, (float)sv[k], (float)sa[k], (float)d);        /* TIS:1336 */
-            srcc[g * 7] = (uint16_t)(g * 7);
-            nn0[g] = 0xFFFFu;
-            vd0s[g] = 0.0;
-            const double INF = 1.0e300;
+             * entries below and the six above the ego can qualify; both sides are sorted by distance, so the
+             * answer is the head of a two-way merge in which the below side wins ties (lower list index).
+             * Instead of walking outwards (a serial chain of dependent loads) the merge is evaluated in closed
+             * form: the first m outputs contain the t-th below entry iff dl[t-1] <= dh[m-t] (merge path), so
+             * a(m) = #below among the first m = sum over i + j = m - 1 of [dl[i] <= dh[j]]: 21 comparisons. */
             double dl[PVE_NNBR], dh[PVE_NNBR];
 #pragma unroll
-            for (int i = 0; i < PVE_NNBR; ++i) {
-                const int xl = r - 1 - i, xh = r + 1 + i;
-                dl[i] = (xl >= 0) ? fabs(spos[base + (xl >= 0 ? xl : 0)] - pe) : INF;
-                dh[i] = (xh < n) ? fabs(spos[base + (xh < n ? xh : 0)] - pe) : INF;
-            }
-            int ncand = 0;
-            /* a run of equal |delta| that continues below the window puts farther (lower-index) entries
-             * first: resolve that rare case with the reference's own outward walk */
-            const bool edge_tie = (r - 1 - PVE_NNBR >= 0) && dl[PVE_NNBR - 1] != INF &&
-                                  fabs(spos[base + (r - 1 - PVE_NNBR >= 0 ? r - 1 - PVE_NNBR : 0)] - pe) == dl[PVE_NNBR - 1];
-            if (edge_tie) {
+            for (int i = 0; i < PVE_NNBR; ++i) { dl[i] = pe - S[r - 1 - i]; dh[i] = S[r + 1 + i] - pe; }
+            /* vir_header / vir_dis, TIS:1349-1354 */
+            if (r == 0) { hdra[g] = -1; virdis[g] = 100.0; }
+            else { hdra[g] = (int16_t)acnt[SI[r - 1]]; virdis[g] = dl[0]; }
+            pve_v4 *const orow = (pve_v4 *)(row0 + (size_t)g * PVE_OBS_W);
+            orow[0] = pve_pack4((float)pe, (float)sv[k], (float)sa[k], (float)d);        /* TIS:1336 */
+            uint16_t *const sc = srcc + g * 7;
+            sc[0] = (uint16_t)(g * 7);
+            int nb0 = 0xFFFF;
+            double vd0 = 0.0;
+            const int below = r < PVE_NNBR ? r : PVE_NNBR, above = (n - 1 - r) < PVE_NNBR ? (n - 1 - r) : PVE_NNBR;
+            const int ncand = (below + above) < PVE_NNBR ? (below + above) : PVE_NNBR;
+            if (tie[d]) {
+                /* entries at equal positions in this list (rare): among equal |delta| below the ego the farther
+                 * list index comes first -- resolved with the reference's own outward walk */
                 int lo = r - 1, hi = r + 1, run_cur = 0, run_end = -1;
                 double run_d = 0;
                 for (int q = 0; q < PVE_NNBR; ++q) {
                     if (run_cur > run_end && lo >= 0) {
-                        run_end = lo; run_d = fabs(spos[base + lo] - pe);
+                        run_end = lo; run_d = fabs(S[lo] - pe);
                         int x = lo;
-                        while (x - 1 >= 0 && fabs(spos[base + x - 1] - pe) == run_d) --x;
+                        while (x - 1 >= 0 && fabs(S[x - 1] - pe) == run_d) --x;
                         run_cur = x; lo = x - 1;
                     }
                     const bool has_lo = run_cur <= run_end, has_hi = hi < n;
                     int pick = -1;
-                    if (has_lo && (!has_hi || run_d <= fabs(spos[base + hi] - pe))) pick = run_cur++;
+                    if (has_lo && (!has_hi || run_d <= fabs(S[hi] - pe))) pick = run_cur++;
                     else if (has_hi) pick = hi++;
                     if (pick >= 0) {
-                        const int kn = sidx[base + pick];
-                        const double vd = spos[base + pick];
+                        const int kn = SI[pick];
+                        const double vd = S[pick];
                         orow[q + 1] = pve_pack4((float)vd, (float)sv[kn], (float)sa[kn], (float)lane_of[kn]);
-                        srcc[g * 7 + q + 1] = (kn < k) ? (uint16_t)(acnt[kn] * 7) : (uint16_t)(PVE_SRC_PREV | (kn * 7));
-                        if (q == 0) { nn0[g] = (uint16_t)kn; vd0s[g] = vd; }
-                        ++ncand;
+                        sc[q + 1] = (kn < k) ? (uint16_t)(acnt[kn] * 7) : (uint16_t)(PVE_SRC_PREV | (kn * 7));
+                        if (q == 0) { nb0 = kn; vd0 = vd; }
                     }
                 }
-            } else
+            } else {
+                int am[PVE_NNBR + 1];
+                am[0] = 0;
 #pragma unroll
-            for (int side = 0; side < 2; ++side) {
+                for (int m = 1; m <= PVE_NNBR; ++m) {
+                    int c = 0;
 #pragma unroll
-                for (int i = 0; i < PVE_NNBR; ++i) {
-                    const int x = side ? r + 1 + i : r - 1 - i;
-                    const bool ok = side ? (x < n) : (x >= 0);
-                    const double di = side ? dh[i] : dl[i];
-                    int rk = side ? i : 0;
+                    for (int t = 1; t <= m; ++t) c += (dl[t - 1] <= dh[m - t]) ? 1 : 0;
+                    am[m] = c;
+                }
 #pragma unroll
-                    for (int j = 0; j < PVE_NNBR; ++j) {
-                        if (side) rk += (dl[j] <= di) ? 1 : 0;
-                        else {
-                            if (j != i) rk += (dl[j] < di || (dl[j] == di && j > i)) ? 1 : 0;
-                            rk += (dh[j] < di) ? 1 : 0;
-                        }
-                    }
-                    ncand += ok ? 1 : 0;
-                    if (ok && rk < PVE_NNBR) {
-                        const int kn = sidx[base + x];
-                        const double vd = spos[base + x];
-                        orow[rk + 1] = pve_pack4((float)vd, (float)sv[kn], (float)sa[kn], (float)lane_of[kn]);   /* TIS:1330 */
+                for (int q = 0; q < PVE_NNBR; ++q) {
+                    if (q < ncand) {
+                        const int x = (am[q + 1] != am[q]) ? r - 1 - am[q] : r + 1 + q - am[q];
+                        const int kn = SI[x];
+                        const double vd = S[x];
+                        orow[q + 1] = pve_pack4((float)vd, (float)sv[kn], (float)sa[kn], (float)lane_of[kn]);   /* TIS:1330 */
                         /* Q3: neighbour already processed this tick -> its new row, else last tick's */
-                        srcc[g * 7 + rk + 1] = (kn < k) ? (uint16_t)(acnt[kn] * 7) : (uint16_t)(PVE_SRC_PREV | (kn * 7));
-                        if (rk == 0) { nn0[g] = (uint16_t)kn; vd0s[g] = vd; }
+                        sc[q + 1] = (kn < k) ? (uint16_t)(acnt[kn] * 7) : (uint16_t)(PVE_SRC_PREV | (kn * 7));
+                        if (q == 0) { nb0 = kn; vd0 = vd; }
                     }
                 }
             }
@@ -847,8 +897,10 @@ PVE_DEV void pve_step_block(const PveParams &P, const PveState &S, const pve_out
             for (int q = 0; q < PVE_NNBR; ++q)
                 if (q >= ncand) {
                     orow[q + 1] = pve_pack4(0.f, 0.f, 0.f, 0.f);                 /* TIS:1334 */
-                    srcc[g * 7 + q + 1] = (uint16_t)(AC * 7);                    /* the zero row */
+                    sc[q + 1] = (uint16_t)(AC * 7);                              /* the zero row */
                 }
+            nn0[g] = (uint16_t)nb0;
+            vd0s[g] = vd0;
         }
         if (tid < PVE_OBS_W / 4) ((pve_v4 *)(row0 + (size_t)AC * PVE_OBS_W))[tid] = pve_pack4(0.f, 0.f, 0.f, 0.f);
     PVE_END_TID
@@ -860,7 +912,7 @@ PVE_DEV void pve_step_block(const PveParams &P, const PveState &S, const pve_out
     RJ.A = A; RJ.srcc = srcc; RJ.rows_smem = row0; RJ.rows_prev = row0_prev_base; RJ.oblk = oblk; RJ.zero_row = AC;
 #ifdef __CUDACC__
     if (NS < NT && (int)threadIdx.x >= NS) {
-        pve_move_rows<NT>(RJ, NS / 32, (NT - NS) / 32);
+        pve_move_rows<NT, (NT > NS ? (NT - NS) / 32 : 1)>(RJ, NS / 32);
 #ifdef PVE_PHASE_TIMING
         if ((int)threadIdx.x == NS && S.stats) ((long long *)S.dbg)[(size_t)b * 48 + 47] = clock64();
 #endif
@@ -1169,9 +1221,9 @@ PVE_DEV void pve_step_block(const PveParams &P, const PveState &S, const pve_out
 
     /* ---- N: observation rows leave the SM (already under way on the upper half when the CTA is split) */
 #ifdef __CUDACC__
-    if (NS == NT) pve_move_rows<NT>(RJ, 0, NT / 32);
+    if (NS == NT) pve_move_rows<NT, NT / 32>(RJ, 0);
 #else
-    pve_move_rows<NT>(RJ, 0, 1);
+    pve_move_rows<NT, 1>(RJ, 0);
 #endif
 #if defined(PVE_PHASE_TIMING) && defined(__CUDACC__)
     if (threadIdx.x == 0 && S.stats) {      /* debug build: overwrite this intersection's stats rows with stamps */
