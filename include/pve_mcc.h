@@ -68,6 +68,11 @@ typedef struct pve_config {
      * vd = b + delta.  First index: ego movement 0 = left, 1 = straight; second: k in lane2lane */
     double vd_a1[2][4], vd_a2[2][4], vd_b[2][4];
     double rot_cos[4], rot_sin[4];   /* cos/sin(3.141593/2 * approach)         TIS:1251, 1287 */
+    /* != 0: the action of a vehicle whose `control` flag is off is taken as 0 whatever the action array holds --
+     * what the reference driver does on the host (`else: action = 0`, MAIN:401-405), for callers that fill every
+     * slot without reading the control flags back.  0: actions are used as given (step() semantics, TIS:1502) */
+    int32_t zero_uncontrolled;
+    int32_t reserved0;
 } pve_config;
 
 /* Per-intersection header as stored on the device (little endian, 144 bytes). */

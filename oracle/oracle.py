@@ -127,6 +127,8 @@ class OracleScene:
         L.orc_count_agents.argtypes = [C.c_void_p]
         L.orc_step.argtypes = [C.c_void_p, _PTR, C.POINTER(_Outputs), C.c_int32]
         L.orc_overflow.argtypes = [C.c_void_p]
+        L.orc_control_mask.argtypes = [C.c_void_p, _PTR]
+        L.orc_control_mask.restype = None
         self.B, self.cap, self.n_threads = int(n_envs), int(veh_cap), int(n_threads)
         self.params = params if params is not None else scene_params()
         self.h = L.orc_create(self.B, self.cap, C.byref(self.params))
@@ -166,15 +168,41 @@ class OracleScene:
         self.lib.orc_get_state(self.h, C.byref(self._view(st)))
         return st
 
+    def control_mask(self):
+        """bool ``[B, veh_cap]``: ``veh["control"]`` of every slot (main.py:399-405)."""
+        m = np.zeros((self.B, self.cap), np.uint8)
+        self.lib.orc_control_mask(self.h, m.ctypes.data)
+        return m.astype(bool)
+
     def count_agents(self):
         return int(self.lib.orc_count_agents(self.h))
 
-    def step(self, actions):
-        """``actions``: float32 ``[B, veh_cap]``, one per vehicle slot in (lane, j) order."""
+    def step(self, actions, reuse_buffers=False):
+        """``actions``: float32 ``[B, veh_cap]``, one per vehicle slot in (lane, j) order.
+
+        ``reuse_buffers``: write into arrays allocated once for ``B * veh_cap`` rows and return views of them
+        (valid until the next call) instead of allocating 1.7 KB of zeros per agent every tick -- used by the
+        timed CPU baseline so that it measures the scene, not numpy's allocator."""
         act = np.ascontiguousarray(actions, dtype=np.float32)
         assert act.shape == (self.B, self.cap), act.shape
         A = self.count_agents()
-        o = {
+        if reuse_buffers:
+            if getattr(self, "_buf", None) is None:
+                self._buf = self._alloc_outputs(self.B * self.cap)
+            full = self._buf
+            o = {k: (a if k in ("agent_offset", "collisions", "lock", "n_removed", "q5_undefined") else a[:A])
+                 for k, a in full.items()}
+        else:
+            full = o = self._alloc_outputs(A)
+        ov = _Outputs()
+        for k, a in full.items():
+            setattr(ov, k, a.ctypes.data)
+        self.lib.orc_step(self.h, act.ctypes.data, C.byref(ov), self.n_threads)
+        o["overflow"] = int(self.lib.orc_overflow(self.h))
+        return o
+
+    def _alloc_outputs(self, A):
+        return {
             "agent_offset": np.zeros(self.B + 1, np.int64),
             "ids": np.zeros((A, 2), np.int32), "uid": np.zeros(A, np.int32),
             "obs": np.zeros((A, OBS_H, OBS_W), np.float64), "reward": np.zeros(A, np.float64),
@@ -183,9 +211,3 @@ class OracleScene:
             "collisions": np.zeros(self.B, np.int32), "lock": np.zeros(self.B, np.int32),
             "n_removed": np.zeros(self.B, np.int32), "q5_undefined": np.zeros(self.B, np.int32),
         }
-        ov = _Outputs()
-        for k, a in o.items():
-            setattr(ov, k, a.ctypes.data)
-        self.lib.orc_step(self.h, act.ctypes.data, C.byref(ov), self.n_threads)
-        o["overflow"] = int(self.lib.orc_overflow(self.h))
-        return o

@@ -7,15 +7,17 @@
  * j asc), its list-building and its stable sorts, so that it is an independent check of the
  * order-free formulation used by the CUDA kernels.
  *
- * Build: gcc -O2 -fPIC -shared -fopenmp -ffp-contract=off -fno-builtin-pow (see Makefile).
+ * Build: gcc -O2 -fPIC -shared -pthread -ffp-contract=off -fno-builtin-pow (see Makefile).
  * -ffp-contract=off keeps every a*b+c as two IEEE operations, like CPython does.
  */
+#define _GNU_SOURCE          /* pthread_barrier_t */
 #include "scene_oracle.h"
 
 #include <math.h>
 #include <stdlib.h>
 #include <string.h>
 #include <pthread.h>
+#include <stdatomic.h>
 
 typedef struct {
     double p, v, a, jerk, jerk_sum, vir_dis;
@@ -38,6 +40,16 @@ typedef struct {
     veh_t *veh;
 } env_t;
 
+typedef struct orc_scratch {          /* per-thread work arrays of env_tick */
+    vq_ent *vq;
+    vl_ent *vl;
+    uint8_t *used;
+    veh_t *tmp;
+} scratch_t;
+typedef struct orc_pool orc_pool;
+static void pool_destroy(orc_scene *S);
+static void scratch_free(scratch_t *W);
+
 struct orc_scene {
     int32_t B, cap, K;
     orc_params prm;
@@ -46,6 +58,9 @@ struct orc_scene {
     double *arrive;      /* [B][K][12] */
     int32_t *kvalid;     /* [B][12] */
     int32_t overflow;
+    struct orc_pool *workers;          /* persistent worker threads of orc_step (null until first used) */
+    int scratch_ok;
+    struct orc_scratch scratch0;       /* the calling thread's scratch */
 };
 
 /* lane2lane for the 12-lane intersection, TIS:153-166 */
@@ -283,12 +298,6 @@ static int check_lock(const orc_params *P, env_t *e, int i, int j) {
  * One tick of one environment: main.py:398-407 (step for every vehicle), TIS:222-376
  * (scene_update), TIS:435-444 (delete_vehicle).
  * ---------------------------------------------------------------------------------------- */
-typedef struct {
-    vq_ent *vq;
-    vl_ent *vl;
-    uint8_t *used;
-    veh_t *tmp;
-} scratch_t;
 
 static void env_tick(orc_scene *S, int b, const float *act, orc_outputs *out, scratch_t *W) {
     const orc_params *P = &S->prm;
@@ -483,10 +492,22 @@ orc_scene *orc_create(int32_t n_envs, int32_t veh_cap, const orc_params *prm) {
 
 void orc_destroy(orc_scene *S) {
     if (!S) return;
+    pool_destroy(S);
+    if (S->scratch_ok) scratch_free(&S->scratch0);
     free(S->env); free(S->pool); free(S->arrive); free(S->kvalid); free(S);
 }
 
 int32_t orc_overflow(const orc_scene *S) { return S->overflow; }
+
+/* veh["control"] of every slot (0 past the live count): what main.py:399-405 reads to choose between the policy
+ * and 0 */
+void orc_control_mask(const orc_scene *S, uint8_t *out) {
+    for (int b = 0; b < S->B; b++) {
+        const env_t *e = &S->env[b];
+        const int V = total_veh(e);
+        for (int k = 0; k < S->cap; k++) out[(size_t)b * S->cap + k] = (k < V) ? (uint8_t)e->veh[k].control : 0;
+    }
+}
 
 int64_t orc_count_agents(const orc_scene *S) {
     int64_t a = 0;
@@ -609,24 +630,77 @@ int32_t orc_get_state(const orc_scene *S, orc_state_view *out) {
     return 0;
 }
 
-/* environments are independent (main.py creates exactly one scene, main.py:230): worker t
- * handles blocks of 16 environments, round-robin */
-typedef struct { orc_scene *S; const float *actions; orc_outputs *out; int tid, nth; } worker_t;
+/* environments are independent (main.py creates exactly one scene, main.py:230): a persistent pool of
+ * worker threads takes blocks of 4 environments from a shared counter (created on the first multi-threaded
+ * orc_step, reused by every later tick, joined by orc_destroy) */
+struct orc_pool {
+    int n;                              /* threads including the caller */
+    pthread_t *th;
+    pthread_barrier_t start, end;
+    orc_scene *S;
+    const float *actions;
+    orc_outputs *out;
+    atomic_int next;
+    int quit;
+};
 
-static void *worker_main(void *arg) {
-    worker_t *w = (worker_t *)arg;
-    orc_scene *S = w->S;
-    scratch_t W;
-    W.vq = (vq_ent *)malloc(sizeof(vq_ent) * (size_t)S->cap);
-    W.vl = (vl_ent *)malloc(sizeof(vl_ent) * (size_t)S->cap);
-    W.used = (uint8_t *)malloc((size_t)S->cap);
-    W.tmp = (veh_t *)malloc(sizeof(veh_t) * (size_t)S->cap);
-    const int blk = 16;
-    for (int b0 = w->tid * blk; b0 < S->B; b0 += w->nth * blk)
+static void pool_work(orc_pool *P, scratch_t *W) {
+    orc_scene *S = P->S;
+    const int blk = 4;
+    for (;;) {
+        const int b0 = atomic_fetch_add(&P->next, blk);
+        if (b0 >= S->B) break;
         for (int b = b0; b < b0 + blk && b < S->B; b++)
-            env_tick(S, b, w->actions + (size_t)b * S->cap, w->out, &W);
-    free(W.vq); free(W.vl); free(W.used); free(W.tmp);
+            env_tick(S, b, P->actions + (size_t)b * S->cap, P->out, W);
+    }
+}
+
+static int scratch_init(scratch_t *W, int cap) {
+    W->vq = (vq_ent *)malloc(sizeof(vq_ent) * (size_t)cap);
+    W->vl = (vl_ent *)malloc(sizeof(vl_ent) * (size_t)cap);
+    W->used = (uint8_t *)malloc((size_t)cap);
+    W->tmp = (veh_t *)malloc(sizeof(veh_t) * (size_t)cap);
+    return (W->vq && W->vl && W->used && W->tmp) ? 0 : 1;
+}
+static void scratch_free(scratch_t *W) { free(W->vq); free(W->vl); free(W->used); free(W->tmp); }
+
+static void *pool_main(void *arg) {
+    orc_pool *P = (orc_pool *)arg;
+    scratch_t W;
+    scratch_init(&W, P->S->cap);
+    for (;;) {
+        pthread_barrier_wait(&P->start);
+        if (P->quit) break;
+        pool_work(P, &W);
+        pthread_barrier_wait(&P->end);
+    }
+    scratch_free(&W);
     return NULL;
+}
+
+static void pool_destroy(orc_scene *S) {
+    orc_pool *P = S->workers;
+    if (!P) return;
+    P->quit = 1;
+    pthread_barrier_wait(&P->start);
+    for (int t = 1; t < P->n; t++) pthread_join(P->th[t], NULL);
+    pthread_barrier_destroy(&P->start); pthread_barrier_destroy(&P->end);
+    free(P->th); free(P);
+    S->workers = NULL;
+}
+
+static orc_pool *pool_get(orc_scene *S, int n) {
+    if (S->workers && S->workers->n == n) return S->workers;
+    pool_destroy(S);
+    orc_pool *P = (orc_pool *)calloc(1, sizeof *P);
+    if (!P) return NULL;
+    P->n = n; P->S = S;
+    P->th = (pthread_t *)calloc((size_t)n, sizeof(pthread_t));
+    pthread_barrier_init(&P->start, NULL, (unsigned)n);
+    pthread_barrier_init(&P->end, NULL, (unsigned)n);
+    for (int t = 1; t < n; t++) pthread_create(&P->th[t], NULL, pool_main, P);
+    S->workers = P;
+    return P;
 }
 
 int32_t orc_step(orc_scene *S, const float *actions, orc_outputs *out, int32_t n_threads) {
@@ -639,16 +713,19 @@ int32_t orc_step(orc_scene *S, const float *actions, orc_outputs *out, int32_t n
         out->agent_offset[b + 1] = out->agent_offset[b] + a;
     }
     if (n_threads < 1) n_threads = 1;
-    if (n_threads > S->B) n_threads = S->B;
+    if (n_threads > (S->B + 3) / 4) n_threads = (S->B + 3) / 4;
     if (n_threads > 1024) n_threads = 1024;
-    worker_t *w = (worker_t *)calloc((size_t)n_threads, sizeof(worker_t));
-    pthread_t *th = (pthread_t *)calloc((size_t)n_threads, sizeof(pthread_t));
-    for (int t = 0; t < n_threads; t++) {
-        w[t].S = S; w[t].actions = actions; w[t].out = out; w[t].tid = t; w[t].nth = n_threads;
+    if (!S->scratch_ok) { if (scratch_init(&S->scratch0, S->cap)) return -1; S->scratch_ok = 1; }
+    if (n_threads == 1) {
+        for (int b = 0; b < S->B; b++) env_tick(S, b, actions + (size_t)b * S->cap, out, &S->scratch0);
+    } else {
+        orc_pool *P = pool_get(S, n_threads);
+        if (!P) return -1;
+        P->actions = actions; P->out = out;
+        atomic_store(&P->next, 0);
+        pthread_barrier_wait(&P->start);
+        pool_work(P, &S->scratch0);
+        pthread_barrier_wait(&P->end);
     }
-    for (int t = 1; t < n_threads; t++) pthread_create(&th[t], NULL, worker_main, &w[t]);
-    worker_main(&w[0]);
-    for (int t = 1; t < n_threads; t++) pthread_join(th[t], NULL);
-    free(w); free(th);
     return S->overflow ? 1 : 0;
 }

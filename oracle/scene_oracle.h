@@ -81,6 +81,8 @@ int64_t orc_count_agents(const orc_scene *s);
 /* one tick for every environment: step() for each vehicle, scene_update(), delete_vehicle() */
 int32_t orc_step(orc_scene *s, const float *actions, orc_outputs *out, int32_t n_threads);
 int32_t orc_overflow(const orc_scene *s);
+/* out[B][veh_cap]: veh["control"] of every slot, 0 past the live count (main.py:399-405) */
+void orc_control_mask(const orc_scene *s, uint8_t *out);
 
 #ifdef __cplusplus
 }

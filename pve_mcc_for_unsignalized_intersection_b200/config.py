@@ -34,6 +34,7 @@ class PveConfig(C.Structure):
         ("remove_p", C.c_double), ("lane_cw", C.c_double),
         ("vd_a1", (C.c_double * 4) * 2), ("vd_a2", (C.c_double * 4) * 2), ("vd_b", (C.c_double * 4) * 2),
         ("rot_cos", C.c_double * 4), ("rot_sin", C.c_double * 4),
+        ("zero_uncontrolled", C.c_int32), ("reserved0", C.c_int32),
     ]
 
 
@@ -57,6 +58,8 @@ class SceneConfig:
     lane_cw: float = 2.5
     lane_num: int = 12
     o_agent_num: int = 6
+    #: take the action of every uncontrolled vehicle as 0 like the reference driver does (MAIN:401-405)
+    zero_uncontrolled_actions: bool = False
 
     def __post_init__(self):
         if self.lane_num != 12:
@@ -134,4 +137,5 @@ class SceneConfig:
         cs, sn = self.rotation()
         for k in range(4):
             c.rot_cos[k], c.rot_sin[k] = cs[k], sn[k]
+        c.zero_uncontrolled = int(bool(self.zero_uncontrolled_actions))
         return c

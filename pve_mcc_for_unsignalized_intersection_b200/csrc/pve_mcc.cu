@@ -52,6 +52,15 @@ struct pve_scene {
     int n_groups;
     int32_t *n_ctrl_buf[2];      /* ping-pong with `phase` */
     int32_t *order;              /* busiest-first CTA order */
+    /* dual mode (default class, default CTA size): two concurrent kernels per tick, see PveState::klass */
+    int dual;
+    uint8_t *klass_buf[2];       /* ping-pong with `phase` */
+    int32_t *big_list_buf[2];
+    int32_t *big_cnt3;           /* [3], rotates with `rot` */
+#ifndef PVE_HOST_EMULATION
+    cudaStream_t side;           /* the big kernel's stream */
+    cudaEvent_t ev_fork, ev_join;
+#endif
     int order_age;               /* ticks since the order was refreshed (-1: never) */
     const int32_t *spawn_tick;   /* borrowed */
     float *actions_dev;          /* staging for pve_step_host */
@@ -135,7 +144,34 @@ pve_step_kernel(const PveParams P, const PveState S, const pve_outputs O, const 
     /* CTAs are dispatched in index order; starting the busiest intersections first shortens the tail
      * of the launch (a CTA lives ~22 us, a launch of 4096 ~100 us) */
     const int b = S.order ? S.order[blockIdx.x] : (int)blockIdx.x;
-    pve_step_block<NT, VC, AC, SRC>(P, S, O, spawn_tick, actions, phase, b, pve_smem);
+    /* dual mode: intersections of the big kernel are skipped (pve_step_block tests klass[b] after it has issued its
+     * first loads, so the test costs no extra memory round trip) */
+    pve_step_block<NT, VC, AC, SRC>(P, S, O, spawn_tick, actions, phase, b, pve_smem, S.klass);
+}
+
+/* dual mode: the intersections that do not fit the small class, a few per tick */
+template <int NT, int VC, int AC, bool SRC>
+__global__ void __launch_bounds__(NT, PveResident<VC, AC>::blocks(NT))
+pve_step_big_kernel(const PveParams P, const PveState S, const pve_outputs O, const int32_t *spawn_tick,
+                    const float *actions, const int phase) {
+    extern __shared__ __align__(16) unsigned char pve_smem[];
+    const int n = *S.big_cnt;
+    for (int i = (int)blockIdx.x; i < n; i += (int)gridDim.x) {
+        pve_step_block<NT, VC, AC, SRC>(P, S, O, spawn_tick, actions, phase, S.big_list[i], pve_smem, nullptr);
+        __syncthreads();                                   /* shared memory is reused by the next one */
+    }
+}
+
+/* dual mode, after reset / set_state: classes and the big kernel's list from the headers */
+__global__ void pve_classify_kernel(PveState S, int B) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    const pve_env_header *h = S.hdr + b;
+    int due = 0;
+    for (int i = 0; i < PVE_NLANE; ++i) due += (h->tick + 1 >= h->next_spawn[i]) ? 1 : 0;
+    const int big = (h->n_veh + due > S.small_vc || h->n_ctrl + due > S.small_ac) ? 1 : 0;
+    S.klass_next[b] = (uint8_t)big;
+    if (big) S.big_list_next[atomicAdd(S.big_cnt_next, 1)] = b;
 }
 
 /* order[i] = intersections sorted by their agent count, descending (counting sort, one CTA) */
@@ -295,6 +331,12 @@ static void set_rotation(pve_scene *s) {
     s->st.gs_read = s->gsum + (size_t)(s->rot % 3) * G;
     s->st.gs_acc = s->gsum + (size_t)((s->rot + 1) % 3) * G;
     s->st.gs_zero = s->gsum + (size_t)((s->rot + 2) % 3) * G;
+    if (s->dual) {
+        s->st.klass = s->klass_buf[s->phase]; s->st.klass_next = s->klass_buf[s->phase ^ 1];
+        s->st.big_list = s->big_list_buf[s->phase]; s->st.big_list_next = s->big_list_buf[s->phase ^ 1];
+        s->st.big_cnt = s->big_cnt3 + s->rot % 3; s->st.big_cnt_next = s->big_cnt3 + (s->rot + 1) % 3;
+        s->st.big_cnt_zero = s->big_cnt3 + (s->rot + 2) % 3;
+    }
 }
 
 /* after reset / set_state: group sums from n_ctrl, rotation restarted */
@@ -306,6 +348,13 @@ static int32_t launch_gsum(pve_scene *s, pve_stream_t stream) {
     pve_gsum_kernel<<<(G + 127) / 128, 128, 0, stream>>>(s->st.n_ctrl, s->gsum, s->gsum + G, s->gsum + 2 * (size_t)G,
                                                           s->cfg.n_envs, G);
     RT_CHECK(s, cudaGetLastError());
+    if (s->dual) {      /* classes of the coming tick from the headers: written through the *_next pointers */
+        PveState t = s->st;
+        t.klass_next = s->klass_buf[s->phase]; t.big_list_next = s->big_list_buf[s->phase]; t.big_cnt_next = s->big_cnt3;
+        RT_CHECK(s, cudaMemsetAsync(s->big_cnt3, 0, 3 * sizeof(int32_t), stream));
+        pve_classify_kernel<<<(s->cfg.n_envs + 127) / 128, 128, 0, stream>>>(t, s->cfg.n_envs);
+        RT_CHECK(s, cudaGetLastError());
+    }
 #else
     (void)stream;
     emul_gsum(s->st.n_ctrl, s->gsum, s->gsum + G, s->gsum + 2 * (size_t)G, s->cfg.n_envs, G);
@@ -314,7 +363,7 @@ static int32_t launch_gsum(pve_scene *s, pve_stream_t stream) {
 }
 
 /* capacity classes (compile-time shared-memory layouts): veh_cap / agent_cap are rounded up to one */
-#define PVE_CLASSES(X) X(128, 80) X(128, 96) X(192, 128) X(384, 320) X(576, 416)
+#define PVE_CLASSES(X) X(96, 48) X(96, 64) X(128, 80) X(128, 96) X(192, 128) X(384, 320) X(576, 416)
 
 static bool pick_class(int veh_cap, int agent_cap, int *VC, int *AC, size_t *smem) {
 #define X(vc, ac) if (veh_cap <= vc && agent_cap <= ac) { *VC = vc; *AC = ac; *smem = PveLayout<vc, ac>::BYTES; return true; }
@@ -338,6 +387,37 @@ static cudaError_t launch_variant(pve_scene *s, const float *actions, const pve_
         s->prm, s->st, O, s->spawn_tick, actions, s->phase);
     return cudaGetLastError();
 }
+/* dual mode: the small kernel (96 threads, class PVE_SMALL_VC / PVE_SMALL_AC: more intersections resident per SM) on
+ * the caller's stream and, concurrently on the side stream, the big kernel for the intersections that do not fit */
+#define PVE_SMALL_VC 96
+#define PVE_SMALL_AC 64
+#define PVE_SMALL_NT 96
+template <int VC, int AC, bool SRC>
+static cudaError_t launch_dual(pve_scene *s, const float *actions, const pve_outputs &O, pve_stream_t stream) {
+    static bool attr_set[16] = {false};
+    int dev = s->device & 15;
+    const size_t smem_small = PveLayout<PVE_SMALL_VC, PVE_SMALL_AC>::BYTES, smem_big = PveLayout<VC, AC>::BYTES;
+    cudaError_t e;
+    if (!attr_set[dev]) {
+        e = cudaFuncSetAttribute(pve_step_kernel<PVE_SMALL_NT, PVE_SMALL_VC, PVE_SMALL_AC, SRC>,
+                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(smem_small + s->smem_pad));
+        if (e != cudaSuccess) return e;
+        e = cudaFuncSetAttribute(pve_step_big_kernel<128, VC, AC, SRC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_big);
+        if (e != cudaSuccess) return e;
+        attr_set[dev] = true;
+    }
+    if ((e = cudaEventRecord(s->ev_fork, stream)) != cudaSuccess) return e;
+    if ((e = cudaStreamWaitEvent(s->side, s->ev_fork, 0)) != cudaSuccess) return e;
+    const int big_grid = s->cfg.n_envs < 148 ? s->cfg.n_envs : 148;
+    pve_step_big_kernel<128, VC, AC, SRC><<<big_grid, 128, smem_big, s->side>>>(s->prm, s->st, O, s->spawn_tick, actions, s->phase);
+    if ((e = cudaGetLastError()) != cudaSuccess) return e;
+    if ((e = cudaEventRecord(s->ev_join, s->side)) != cudaSuccess) return e;
+    pve_step_kernel<PVE_SMALL_NT, PVE_SMALL_VC, PVE_SMALL_AC, SRC><<<s->cfg.n_envs, PVE_SMALL_NT, smem_small + s->smem_pad, stream>>>(
+        s->prm, s->st, O, s->spawn_tick, actions, s->phase);
+    if ((e = cudaGetLastError()) != cudaSuccess) return e;
+    return cudaStreamWaitEvent(stream, s->ev_join, 0);
+}
+
 /* the instantiation that also writes pve_outputs.nbr_src only when the caller asks for that output */
 template <int NT, int VC, int AC>
 static cudaError_t launch_one(pve_scene *s, const float *actions, const pve_outputs &O, pve_stream_t stream) {
@@ -362,6 +442,11 @@ static int32_t launch_step(pve_scene *s, const float *actions, const pve_outputs
     }
     if (s->profiling) RT_CHECK(s, cudaEventRecord(s->ev[0], stream));
     bool done = false;
+    if (s->dual) {
+        done = true;
+        if (ACc == 96) RT_CHECK(s, (O.nbr_src ? launch_dual<128, 96, true>(s, actions, O, stream) : launch_dual<128, 96, false>(s, actions, O, stream)));
+        else RT_CHECK(s, (O.nbr_src ? launch_dual<128, 80, true>(s, actions, O, stream) : launch_dual<128, 80, false>(s, actions, O, stream)));
+    }
 #define X(vc, ac)                                                                              \
     if (!done && VCc == vc && ACc == ac) {                                                     \
         done = true;                                                                           \
@@ -386,7 +471,7 @@ static int32_t launch_step(pve_scene *s, const float *actions, const pve_outputs
         done = true;                                                                           \
         for (int b = 0; b < B; ++b) {                                                          \
             memset(smem, 0xA5, s->smem_bytes); /* poison: catches reads of unwritten shared memory */ \
-            pve_step_block<64, vc, ac, true>(s->prm, s->st, O, s->spawn_tick, actions, s->phase, b, smem); \
+            pve_step_block<64, vc, ac, true>(s->prm, s->st, O, s->spawn_tick, actions, s->phase, b, smem, nullptr); \
         }                                                                                      \
     }
     PVE_CLASSES(X)
@@ -458,8 +543,13 @@ void pve_destroy(pve_scene *s) {
     rt_free(s->n_ctrl_buf[0]); rt_free(s->n_ctrl_buf[1]); rt_free(s->st.n_veh); rt_free(s->st.stats); rt_free(s->gsum); rt_free(s->order);
     rt_free(s->actions_dev); rt_free(s->counters_dev);
     rt_host_free(s->pinned_i32); rt_host_free(s->pinned_gs);
+    rt_free(s->klass_buf[0]); rt_free(s->klass_buf[1]); rt_free(s->big_list_buf[0]); rt_free(s->big_list_buf[1]);
+    rt_free(s->big_cnt3);
 #ifndef PVE_HOST_EMULATION
     for (int i = 0; i < 3; ++i) if (s->ev[i]) cudaEventDestroy(s->ev[i]);
+    if (s->side) cudaStreamDestroy(s->side);
+    if (s->ev_fork) cudaEventDestroy(s->ev_fork);
+    if (s->ev_join) cudaEventDestroy(s->ev_join);
 #endif
     delete s;
 }
@@ -488,6 +578,11 @@ int32_t pve_create(const pve_config *cfg, int32_t device, pve_scene **out) {
      * (stress: V ~ 345, 1 600 virtual-lane entries; two CTAs per SM at 64 registers = 32 warps per SM.  Measured per
      * tick of 4 096 stress intersections: 128 threads 0.766 ms, 256: 0.586, 512: 0.487) */
     s->threads = cfg->threads == 0 ? (VC >= 384 ? 512 : 128) : cfg->threads;
+#ifndef PVE_HOST_EMULATION
+    /* dual mode for the default class with the default CTA size (env PVE_DUAL=0 turns it off) */
+    s->dual = (cfg->threads == 0 && VC == 128) ? 1 : 0;
+    if (const char *d = getenv("PVE_DUAL")) s->dual = s->dual && atoi(d) != 0;
+#endif
     if (const char *pad = getenv("PVE_SMEM_PAD")) s->smem_pad = (size_t)atoi(pad);
     s->host_zerocopy = 1;
     if (const char *zc = getenv("PVE_HOST_ZEROCOPY")) s->host_zerocopy = atoi(zc);
@@ -519,6 +614,8 @@ int32_t pve_create(const pve_config *cfg, int32_t device, pve_scene **out) {
         }
     }
     P.B = B; P.VC = VC; P.AC = AC; P.K = 0; P.out_cap = cfg->out_cap;
+    s->st.small_vc = 0; s->st.small_ac = 0;
+    P.zero_unctl = cfg->zero_uncontrolled ? 1 : 0;
 #ifndef PVE_HOST_EMULATION
     RT_CHECK(s, cudaSetDevice(device));
 #endif
@@ -538,6 +635,21 @@ int32_t pve_create(const pve_config *cfg, int32_t device, pve_scene **out) {
     RT_CHECK(s, rt_alloc((void **)&s->st.stats, sizeof(double) * (size_t)B * PVE_NSTAT));
     RT_CHECK(s, rt_alloc((void **)&s->order, sizeof(int32_t) * (size_t)B));
     s->order_age = -1;
+#ifndef PVE_HOST_EMULATION
+    if (s->dual) {
+        s->st.small_vc = PVE_SMALL_VC; s->st.small_ac = PVE_SMALL_AC;
+        for (int i = 0; i < 2; ++i) {
+            RT_CHECK(s, rt_alloc((void **)&s->klass_buf[i], (size_t)B));
+            RT_CHECK(s, rt_alloc((void **)&s->big_list_buf[i], sizeof(int32_t) * (size_t)B));
+        }
+        RT_CHECK(s, rt_alloc((void **)&s->big_cnt3, sizeof(int32_t) * 3));
+        int prio_lo = 0, prio_hi = 0;        /* the few big CTAs take free SM slots before the queue of small ones */
+        RT_CHECK(s, cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+        RT_CHECK(s, cudaStreamCreateWithPriority(&s->side, cudaStreamNonBlocking, prio_hi));
+        RT_CHECK(s, cudaEventCreateWithFlags(&s->ev_fork, cudaEventDisableTiming));
+        RT_CHECK(s, cudaEventCreateWithFlags(&s->ev_join, cudaEventDisableTiming));
+    }
+#endif
     s->n_groups = (B + (1 << PVE_GROUP_SHIFT) - 1) >> PVE_GROUP_SHIFT;
     RT_CHECK(s, rt_alloc((void **)&s->gsum, sizeof(int32_t) * 3 * (size_t)s->n_groups));
     RT_CHECK(s, rt_host_alloc((void **)&s->pinned_gs, sizeof(int32_t) * (size_t)s->n_groups));

@@ -74,6 +74,7 @@ static inline int pve_emul_atomic_add(int *p, int v) { int o = *p; *p = o + v; r
 #endif
 
 struct alignas(16) pve_v4 { uint32_t x, y, z, w; };
+struct alignas(16) pve_d2 { double x, y; };
 
 /* kernel parameters (by value; lives in the constant bank) */
 struct PveParams {
@@ -87,6 +88,7 @@ struct PveParams {
     int8_t rev_dir[PVE_NLANE][4];  /* directions d whose lane2lane[d] contains this lane ... */
     int8_t rev_k[PVE_NLANE][4];    /* ... and its position k there */
     int32_t B, VC, AC, K;
+    int32_t zero_unctl, pad_;      /* pve_config.zero_uncontrolled */
     int64_t out_cap;
 };
 
@@ -106,6 +108,16 @@ struct PveState {
     int32_t *gs_acc, *gs_zero;
     void *dbg;                /* tools/phase_timing.py builds only: [B][48] cycle stamps */
     const int32_t *order;     /* CTA index -> intersection, busiest first (refreshed every few ticks), or null */
+    /* Two kernels per tick (pve_mcc.cu, "dual mode"): intersections that fit the small capacity class run in small
+     * CTAs, the few others in CTAs of the handle's full class.  Every CTA classifies its intersection for the NEXT
+     * tick when it ends (klass_next, big_list_next); the three counters rotate like the group sums. */
+    const uint8_t *klass;     /* [B] 1: this tick the intersection belongs to the big kernel; null: single kernel */
+    uint8_t *klass_next;
+    const int32_t *big_list;  /* intersections of the big kernel this tick, big_cnt[0] of them */
+    int32_t *big_list_next;
+    const int32_t *big_cnt;
+    int32_t *big_cnt_next, *big_cnt_zero;
+    int32_t small_vc, small_ac;
 };
 
 enum { PVE_STAT_AGENT = 0, PVE_STAT_VEH, PVE_STAT_COLL, PVE_STAT_LOCK, PVE_STAT_JERK, PVE_STAT_RSUM,
@@ -115,7 +127,7 @@ enum { PVE_STAT_AGENT = 0, PVE_STAT_VEH, PVE_STAT_COLL, PVE_STAT_LOCK, PVE_STAT_
  * shared-memory layout: compile-time offsets for a capacity class (VC vehicle slots, AC agents,
  * EC = 5*AC virtual-lane entries).  Regions R1 and R2 are reused along the tick:
  *   R1: step candidates (phases A-C) -> unsorted virtual-lane entries (E-F) -> row 0 of every agent (G1-M)
- *   R2: sorted virtual lanes (F-G1) -> world coordinates of the agents (G2-G3)
+ *   R2: sorted virtual lanes (F-I)
  * (per-row cp.async.bulk stores were measured and rejected: ~225 tiny TMA operations per
  * intersection saturate the copy engine)
  * ------------------------------------------------------------------------------------------- */
@@ -123,14 +135,13 @@ template <int VC, int AC>
 struct PveLayout {
     static constexpr uint32_t a16(uint32_t x) { return (x + 15u) & ~15u; }
     static constexpr uint32_t mx(uint32_t a, uint32_t b) { return a > b ? a : b; }
-    static constexpr int EC = 5 * AC;
+    static constexpr int EC = 5 * AC + 16;              /* each direction's segment is padded to an even length */
     static constexpr int SC = EC + 12 * PVE_NLANE;      /* sorted lists: 6 sentinels below and above each direction's */
     static constexpr uint32_t HDR = 0;
     static constexpr uint32_t SP = a16(PVE_HDR_BYTES);
     static constexpr uint32_t SV = SP + 8 * VC;
     static constexpr uint32_t SA = SV + 8 * VC;
-    static constexpr uint32_t SJR = SA + 8 * VC;     /* jerk / dt */
-    static constexpr uint32_t SJS = SJR + 8 * VC;
+    static constexpr uint32_t SJS = SA + 8 * VC;
     static constexpr uint32_t R1 = a16(SJS + 8 * VC);
     static constexpr uint32_t CTA0 = R1, CP0 = CTA0 + 8 * VC, CV0 = CP0 + 8 * VC,
                               CP1 = CV0 + 8 * VC, CV1 = CP1 + 8 * VC;
@@ -139,11 +150,9 @@ struct PveLayout {
     static constexpr uint32_t R1_BYTES = mx(mx(40 * VC, a16(10 * EC)), 112 * (AC + 1));
     static constexpr uint32_t R2 = a16(R1 + R1_BYTES);
     static constexpr uint32_t SPOS = R2, SIDX = SPOS + 8 * SC;
-    static constexpr uint32_t XY = R2;
-    static constexpr uint32_t R2_BYTES = mx(a16(10 * SC), 16 * AC);
-    static constexpr uint32_t VIRDIS = a16(R2 + R2_BYTES);
-    static constexpr uint32_t VD0 = VIRDIS + 8 * AC;
-    static constexpr uint32_t DSUM = VD0 + 8 * AC;
+    static constexpr uint32_t R2_BYTES = a16(10 * SC);
+    static constexpr uint32_t XY = a16(R2 + R2_BYTES);               /* world coordinates of the agents (G1-G3) */
+    static constexpr uint32_t DSUM = XY + 16 * AC;
     static constexpr uint32_t REW = DSUM + 8 * 8;
     static constexpr uint32_t SUID = REW + 4 * AC;
     static constexpr uint32_t SPK = SUID + 4 * VC;
@@ -152,8 +161,9 @@ struct PveLayout {
     static constexpr uint32_t CPV = INCT + 4 * AC;
     static constexpr uint32_t LANE_OFF = CPV + 4 * AC;           /* int[16] */
     static constexpr uint32_t VL_BASE = LANE_OFF + 64;           /* int[16] */
-    static constexpr uint32_t VL_CNT = VL_BASE + 64;             /* int[16] */
-    static constexpr uint32_t MISC = VL_CNT + 64;                /* int[56] */
+    static constexpr uint32_t AFIRST = VL_BASE + 64;             /* int[16]: first agent of each lane */
+    static constexpr uint32_t SEG = AFIRST + 64;                 /* u16[48]: offset of source lane q inside direction d's segment */
+    static constexpr uint32_t MISC = SEG + 96;                   /* int[56] */
     static constexpr uint32_t WSUM = MISC + 224;                 /* int[96]: [0,32) scans, [32,64) chain, [64,80) first row; 16 warps */
     static constexpr uint32_t ACNT = WSUM + 384;                 /* u16[VC+2] */
     static constexpr uint32_t SURV = ACNT + a16(2 * (VC + 2));
@@ -161,8 +171,8 @@ struct PveLayout {
     static constexpr uint32_t ARANK = VIDX + 2 * AC;
     static constexpr uint32_t HDRA = ARANK + 2 * AC;
     static constexpr uint32_t NN0 = HDRA + 2 * AC;
-    static constexpr uint32_t SRC = NN0 + 2 * AC;                /* u16[AC][8] gather codes */
-    static constexpr uint32_t HEADK = SRC + 16 * AC;             /* i16[16] */
+    static constexpr uint32_t SRC = NN0 + 2 * AC;                /* u16[AC][7] gather codes */
+    static constexpr uint32_t HEADK = a16(SRC + 14 * AC);        /* i16[16] */
     static constexpr uint32_t TIE = HEADK + 32;                  /* u8[16]: direction d has entries at equal positions */
     static constexpr uint32_t LANE_OF = TIE + 16;
     static constexpr uint32_t FBITS = LANE_OF + VC;
@@ -250,6 +260,7 @@ PVE_DEV int pve_block_excl_scan(const uint8_t *flag, uint16_t *out, int n, int32
     const int tid = (int)threadIdx.x, lane = tid & 31, warp = tid >> 5;
     constexpr int NW = NT / 32;
     int carry = 0;
+#pragma unroll 1
     for (int base = 0; base < n; base += NT) {
         const int k = base + tid;
         const int f = (k < n) ? (flag[k] != 0) : 0;
@@ -288,6 +299,7 @@ PVE_DEV void pve_resolve_chain(const uint8_t *fbits, uint8_t *sel, int n, int32_
     const int tid = (int)threadIdx.x, lane = tid & 31, warp = tid >> 5;
     constexpr int NW = NT / 32;
     uint32_t carry = 0;                                   /* state entering the chunk */
+#pragma unroll 1
     for (int base = 0; base < n; base += NT) {
         const int k = base + tid;
         uint32_t g = (k < n) ? (uint32_t)fbits[k] : 2u;   /* 2 = identity */
@@ -337,7 +349,9 @@ PVE_DEV int pve_first_row(const PveState &S, int b, PveRowPart rp, int32_t *ws) 
 #ifdef __CUDACC__
     const int tid = (int)threadIdx.x, lane = tid & 31, warp = tid >> 5;
     int part = rp.g + rp.n;
+#pragma unroll 1
     for (int i = tid + NT; i < (b >> PVE_GROUP_SHIFT); i += NT) part += S.gs_read[i];          /* B > 128 * NT only */
+#pragma unroll 1
     for (int i = ((b >> PVE_GROUP_SHIFT) << PVE_GROUP_SHIFT) + tid + NT; i < b; i += NT) part += S.n_ctrl[i];
 #pragma unroll
     for (int d = 16; d > 0; d >>= 1) part += __shfl_xor_sync(0xffffffffu, part, d);
@@ -356,14 +370,19 @@ PVE_DEV int pve_first_row(const PveState &S, int b, PveRowPart rp, int32_t *ws) 
 #endif
 }
 
-/* statistics of the tick, computed by warp 0 only (no barrier): sum r, sum r^2, sum y */
+/* statistics of the tick, computed by warp 0 only (no barrier): sum r, sum r^2, sum of jerk_sum of the agents
+ * that finished this tick (TIS:358) */
 template <int NT>
-PVE_DEV void pve_warp0_sums(const float *x, const double *y, int n, double *out3) {
+PVE_DEV void pve_warp0_sums(const float *x, const uint8_t *fin, const double *js, const uint16_t *vidx, int n, double *out3) {
 #ifdef __CUDACC__
     const int tid = (int)threadIdx.x;
     if (tid < 32) {
         double s0 = 0, s1 = 0, s2 = 0;
-        for (int k = tid; k < n; k += 32) { const double r = (double)x[k]; s0 += r; s1 += r * r; s2 += y[k]; }
+#pragma unroll 1
+        for (int k = tid; k < n; k += 32) {
+            const double r = (double)x[k]; s0 += r; s1 += r * r;
+            if (fin[k]) s2 += js[vidx[k]];
+        }
 #pragma unroll
         for (int d = 16; d > 0; d >>= 1) {
             s0 += __shfl_xor_sync(0xffffffffu, s0, d);
@@ -374,9 +393,17 @@ PVE_DEV void pve_warp0_sums(const float *x, const double *y, int n, double *out3
     }
 #else
     double a0 = 0, a1 = 0, a2 = 0;
-    for (int k = 0; k < n; ++k) { const double r = (double)x[k]; a0 += r; a1 += r * r; a2 += y[k]; }
+    for (int k = 0; k < n; ++k) { const double r = (double)x[k]; a0 += r; a1 += r * r; if (fin[k]) a2 += js[vidx[k]]; }
     out3[0] = a0; out3[1] = a1; out3[2] = a2;
 #endif
+}
+
+/* vir_dis of agent t (TIS:1349-1354): gap to the entry just ahead in its own virtual lane, 100 for the head.
+ * aidx[t] = index of the agent's entry in the sorted lists; the entry below a head is a -inf sentinel */
+PVE_DEV double pve_vir_dis(const double *spos, const uint16_t *aidx, int t) {
+    const double *const S = spos + aidx[t];
+    const double below = S[-1];
+    return below == -PVE_INF ? 100.0 : S[0] - below;
 }
 
 /* ---------------------------------------------------------------------------------------------
@@ -412,23 +439,27 @@ PVE_DEV void pve_move_rows(const PveRowJob &J, int first_warp) {
     constexpr int RSTEP = 4 * NW;                         /* rows taken by the mover warps per step */
     const pve_v4 *PVE_RESTRICT prev = (const pve_v4 *)J.rows_prev + piece;
     const pve_v4 *rows = (const pve_v4 *)J.rows_smem + piece;
-    pve_v4 *PVE_RESTRICT dst = J.oblk + piece;
-    const uint32_t zero7 = (uint32_t)J.zero_row * 7u;
-    for (int row = t >> 3; row < n_rows; row += 4 * RSTEP) {
+    int row = t >> 3;
+    pve_v4 *PVE_RESTRICT dst = J.oblk + piece + row * 7;
+    const uint16_t *sc = J.srcc + row;
+    for (; row + 3 * RSTEP < n_rows; row += 4 * RSTEP, dst += 4 * RSTEP * 7, sc += 4 * RSTEP) {      /* four full steps */
         pve_v4 val[4];
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
-            const int ru = row + u * RSTEP;
-            const uint32_t code = (ru < n_rows) ? (uint32_t)J.srcc[ru] : zero7;
-            const bool is_prev = (code & PVE_SRC_PREV) != 0;
+            const uint32_t code = sc[u * RSTEP];
             const uint32_t src = code & 0x7FFFu;
-            val[u] = rows[is_prev ? zero7 : src];
-            if (is_prev) val[u] = prev[src];
+            if (code & PVE_SRC_PREV) val[u] = prev[src]; else val[u] = rows[src];
         }
 #pragma unroll
-        for (int u = 0; u < 4; ++u)
-            if (row + u * RSTEP < n_rows) dst[(row + u * RSTEP) * 7] = val[u];
+        for (int u = 0; u < 4; ++u) dst[u * RSTEP * 7] = val[u];
     }
+#pragma unroll
+    for (int u = 0; u < 3; ++u)                                                                     /* the tail */
+        if (row + u * RSTEP < n_rows) {
+            const uint32_t code = sc[u * RSTEP];
+            const uint32_t src = code & 0x7FFFu;
+            dst[u * RSTEP * 7] = (code & PVE_SRC_PREV) ? prev[src] : rows[src];
+        }
 #else
     (void)first_warp;
     for (int it = 0; it < J.A * PVE_OBS_H; ++it) {
@@ -474,6 +505,33 @@ PVE_DEV void pve_world_xy(const PveParams &P, double p, int lane, double *x, dou
 }
 
 /* ---------------------------------------------------------------------------------------------
+ * TIS:293-320 reward of an agent: p, v, jerk/dt of the ego; vd0, v0 = virtual position and speed of its
+ * nearest neighbour (has_nb false: none)
+ * ------------------------------------------------------------------------------------------- */
+PVE_DEV float pve_reward(const PveParams &P, double p, double v, double jr, bool has_nb, double vd0, double v0) {
+    /* The three transcendental terms are evaluated unconditionally on safe arguments and selected afterwards: in a
+     * warp some agent needs each of them anyway, and without branches their dependent chains (division -> exp ->
+     * division; log) overlap instead of running one after the other. */
+    const double gap = p - vd0;
+    const double d_raw = fabs(gap);                                              /* TIS:300 */
+    const bool near = has_nb && d_raw != 0;
+    const double t_distance = near ? gap / (v - v0 + 0.0001) : 2.0;              /* TIS:304 (default TIS:293) */
+    const double d_distance = has_nb ? d_raw : 10.0;                             /* TIS:300 (default TIS:294) */
+    const bool use_t = 0 < t_distance && t_distance < 4;
+    const bool use_d = d_distance < 10;
+    /* 1 / tanh(-t / 4) = -(1 + 2 / (exp(t / 2) - 1)) for t in (0, 4) */
+    const double e1 = exp((use_t ? t_distance : 2.0) * 0.5) - 1.0;
+    const double term_t = -(1.0 + 2.0 / e1);                                     /* TIS:314 */
+    const double x = (use_d ? d_distance : 5.0) * 0.1, x2 = x * x;
+    const double term_d = log(x2 * x2 * x + 0.00001);                            /* TIS:318 */
+    double r_ = use_t ? term_t : 0.0;
+    r_ -= jr * jr * (3.0 / 3600.0);                                              /* TIS:316 */
+    r_ += use_d ? term_d : 0.0;
+    r_ += (v - P.vm) * (2.0 / P.aspan);                                          /* TIS:319 */
+    return (float)fmin(20.0, fmax(-20.0, r_));                                   /* TIS:320 */
+}
+
+/* ---------------------------------------------------------------------------------------------
  * one tick of intersection b
  * ------------------------------------------------------------------------------------------- */
 /* SRC: also write pve_outputs.nbr_src.  A template flag, not a run-time test: with the code present but switched off
@@ -481,11 +539,14 @@ PVE_DEV void pve_world_xy(const PveParams &P, double p, int lane, double *x, dou
 template <int NT, int VC, int AC, bool SRC = false>
 PVE_DEV void pve_step_block(const PveParams &P, const PveState &S, const pve_outputs &O,
                             const int32_t *PVE_RESTRICT spawn_tick, const float *PVE_RESTRICT actions,
-                            const int phase, const int b, unsigned char *smem) {
+                            const int phase, const int b, unsigned char *smem, const uint8_t *skip_class) {
     typedef PveLayout<VC, AC> L;
+    /* after phase G1 threads [0, NS) ("team") finish the tick, threads [NS, NT) ("movers") evaluate the rewards and
+     * move the observation rows; NS == NT: no split */
+    constexpr int NS = (NT >= 128) ? NT / 2 : (NT == 96 ? 64 : NT);      /* 96: two team warps, one mover warp */
     pve_env_header *const hdr = (pve_env_header *)(smem + L::HDR);
     double *const sp = (double *)(smem + L::SP), *const sv = (double *)(smem + L::SV);
-    double *const sa = (double *)(smem + L::SA), *const sjr = (double *)(smem + L::SJR);
+    double *const sa = (double *)(smem + L::SA);
     double *const sjs = (double *)(smem + L::SJS);
     double *const cta0 = (double *)(smem + L::CTA0);
     double *const cp0 = (double *)(smem + L::CP0), *const cv0 = (double *)(smem + L::CV0);
@@ -494,7 +555,6 @@ PVE_DEV void pve_step_block(const PveParams &P, const PveState &S, const pve_out
     uint16_t *const eidx = (uint16_t *)(smem + L::EIDX), *const sidx = (uint16_t *)(smem + L::SIDX);
     float *const row0 = (float *)(smem + L::ROW0);
     double *const xy = (double *)(smem + L::XY);
-    double *const virdis = (double *)(smem + L::VIRDIS), *const vd0s = (double *)(smem + L::VD0);
     double *const dsum = (double *)(smem + L::DSUM);
     float *const rew = (float *)(smem + L::REW);
     int32_t *const suid = (int32_t *)(smem + L::SUID);
@@ -502,7 +562,8 @@ PVE_DEV void pve_step_block(const PveParams &P, const PveState &S, const pve_out
     int32_t *const incb = (int32_t *)(smem + L::INCB), *const inct = (int32_t *)(smem + L::INCT);
     int32_t *const cpv = (int32_t *)(smem + L::CPV);
     int32_t *const lane_off = (int32_t *)(smem + L::LANE_OFF), *const vl_base = (int32_t *)(smem + L::VL_BASE);
-    int32_t *const vl_cnt = (int32_t *)(smem + L::VL_CNT), *const misc = (int32_t *)(smem + L::MISC);
+    int32_t *const afirst = (int32_t *)(smem + L::AFIRST), *const misc = (int32_t *)(smem + L::MISC);
+    uint16_t *const seg = (uint16_t *)(smem + L::SEG);
     int32_t *const wsum = (int32_t *)(smem + L::WSUM);
     uint16_t *const acnt = (uint16_t *)(smem + L::ACNT), *const surv = (uint16_t *)(smem + L::SURV);
     uint16_t *const vidx = (uint16_t *)(smem + L::VIDX), *const arank = (uint16_t *)(smem + L::ARANK);
@@ -516,7 +577,7 @@ PVE_DEV void pve_step_block(const PveParams &P, const PveState &S, const pve_out
     uint8_t *const hit = smem + L::HIT, *const q5 = smem + L::Q5, *const fin5 = smem + L::FIN5;
     uint8_t *const status = smem + L::STATUS, *const edir = smem + L::EDIR;
 
-    const size_t vbase = (size_t)b * (size_t)VC;
+    const size_t vbase = (size_t)b * (size_t)P.VC;      /* P.VC: slots per intersection in HBM; VC: slots this kernel stages */
 #if defined(PVE_PHASE_TIMING) && defined(__CUDACC__)
     long long pve_stamp[48];
     int pve_nstamp = 0;
@@ -552,9 +613,11 @@ PVE_DEV void pve_step_block(const PveParams &P, const PveState &S, const pve_out
             p = S.p[vbase + tid]; v = S.v[vbase + tid]; a = S.a[vbase + tid]; js = S.js[vbase + tid];
             mt = S.meta[vbase + tid]; actf = actions[vbase + tid];
         }
+        if (skip_class != nullptr && skip_class[b]) return;          /* dual mode: the other kernel's intersection */
         if (tid < PVE_HDR_BYTES / 16) ((pve_v4 *)hdr)[tid] = gh[tid];
+#pragma unroll 1
         for (int q = tid + 1; q < M_COUNT; q += NT) misc[q] = 0;                 /* misc[M_V] is written below */
-        if (tid < 16) { vl_cnt[tid] = 0; headk[tid] = -1; tie[tid] = 0; }
+        if (tid < 16) { headk[tid] = -1; tie[tid] = 0; }
         /* lane lengths -> inclusive prefix, one byte per lane (V <= 255; the large classes take 16-bit sums) */
         uint32_t ip0, ip1, ip2, ex0, ex1, ex2;
         int V_;
@@ -582,12 +645,12 @@ PVE_DEV void pve_step_block(const PveParams &P, const PveState &S, const pve_out
                 misc[M_V] = o;
             }
         }
+#pragma unroll 1
         for (int k = tid; k < V_; k += NT) {
             if (k != tid) {
                 p = S.p[vbase + k]; v = S.v[vbase + k]; a = S.a[vbase + k]; js = S.js[vbase + k];
                 mt = S.meta[vbase + k]; actf = actions[vbase + k];
             }
-            const double act = (double)actf;
             /* lane of slot k: the last lane whose first slot is <= k; and its virtual-lane head */
             int i, off_i, hl, hj;
             if (VC <= 255) {
@@ -609,6 +672,7 @@ PVE_DEV void pve_step_block(const PveParams &P, const PveState &S, const pve_out
             const int j = k - off_i;
             const uint32_t fl = mt.packed >> 24;
             const bool ctrl = (fl & PVE_F_CONTROL) != 0;
+            const double act = (P.zero_unctl && !ctrl) ? 0.0 : (double)actf;     /* MAIN:401-405 when asked for */
             const int lock_a = (int)((fl >> 3) & 3u) - 1;
             double ta = fmin(P.aM, fmax(P.am, act));                             /* TIS:1502 */
             if ((fl & PVE_F_LOCK) && lock_a != 0 && p > 70.0) ta = a + (double)lock_a;   /* TIS:1503-1505 */
@@ -643,6 +707,7 @@ PVE_DEV void pve_step_block(const PveParams &P, const PveState &S, const pve_out
 
     /* ---- B: F_k(s) = "rear-end override fires on k if its leader took candidate s" -------- */
     PVE_FOR_TID(tid)
+#pragma unroll 1
         for (int k = tid; k < V; k += NT) {
             const int i = lane_of[k];
             int f = 0;
@@ -675,12 +740,12 @@ PVE_DEV void pve_step_block(const PveParams &P, const PveState &S, const pve_out
 
     /* ---- C: commit kinematics -------------------------------------------------------------- */
     PVE_FOR_TID(tid)
+#pragma unroll 1
         for (int k = tid; k < V; k += NT) {
             const int s = ssel[k];
             const double a_new = (s && !del[k]) ? P.am : cta0[k];                /* TIS:1516-1520 */
             del[k] = 0;
             const double jr = (a_new - sa[k]) / P.dt;                            /* TIS:1522, 316, 321 */
-            sjr[k] = jr;
             if (ctl0[k]) sjs[k] += fabs(jr);                                     /* TIS:321 */
             sa[k] = a_new;                                                       /* TIS:1523 */
             sp[k] = s ? cp1[k] : cp0[k];
@@ -701,213 +766,235 @@ PVE_DEV void pve_step_block(const PveParams &P, const PveState &S, const pve_out
 
     /* ---- D: agent tables (each thread uses only the counts it wrote itself) ---------------- */
     PVE_FOR_TID(tid)
+#pragma unroll 1
         for (int k = tid; k < V; k += NT)
             if (ctl0[k]) vidx[acnt[k]] = (uint16_t)k;
+#pragma unroll 1
         for (int g = tid; g < A; g += NT) {
             incb[g] = 0; inct[g] = 0; q5[g] = 0; fin5[g] = 0; status[g] = 0; hit[g] = 0;
         }
-        for (int e = tid; e < (L::EC + 3) / 4; e += NT) ((uint32_t *)edir)[e] = 0xFFFFFFFFu;
+        /* the sorted lists' region is preset to +inf (an upper bound of what the 12 lists and their sentinels take):
+         * whatever phase F does not overwrite is an upper sentinel */
+#pragma unroll 1
+        for (int e = tid; e < 5 * A + 12 + 12 * PVE_NLANE && e < L::SC; e += NT) spos[e] = PVE_INF;
     PVE_END_TID
 
-    /* ---- D2: capacity of each virtual lane: own agents + agents of the 4 conflicting lanes; the
-     *          bases are the exclusive prefix over the 12 lanes (lanes of warp 0) -------------- */
+    /* ---- D2: the unsorted entries of direction d form one segment: its own agents, then the agents of
+     *          its 4 conflicting lanes, each source lane at a fixed offset (seg) so that phase E places every
+     *          entry without a reservation; segments are padded to an even length with a +inf entry and the
+     *          bases are the exclusive prefix over the 12 lanes (lanes of warp 0) ------------------------- */
     PVE_FOR_TID(tid)
         if (tid < 32) {
 #ifdef __CUDACC__
             const int d0 = tid, d1 = tid + 1;
 #else
-            const int d0 = 0, d1 = (tid == 0) ? PVE_NLANE : 0;                   /* thread 0 walks all lanes */
+            const int d0 = 0, d1 = (tid == 0) ? PVE_NLANE + 1 : 0;               /* thread 0 walks all lanes */
             int run = 0;
 #endif
             for (int d = d0; d < d1; ++d) {
                 int o = 0;
-                if (d < PVE_NLANE && hdr->lane_n[d] > 0) {                       /* TIS:234 */
-                    o = (int)acnt[lane_off[d + 1]] - (int)acnt[lane_off[d]];
-                    if (d % 3 != 2) {
+                if (d < PVE_NLANE) {
+                    afirst[d] = (int)acnt[lane_off[d]];
+                    if (hdr->lane_n[d] > 0) {                                    /* TIS:234 */
+                        o = (int)acnt[lane_off[d + 1]] - (int)acnt[lane_off[d]];
+                        if (d % 3 != 2) {
 #pragma unroll
-                        for (int q = 0; q < 4; ++q) {
-                            const int Lq = P.l2l[d][q];
-                            o += (int)acnt[lane_off[Lq + 1]] - (int)acnt[lane_off[Lq]];
+                            for (int q = 0; q < 4; ++q) {
+                                const int Lq = P.l2l[d][q];
+                                seg[d * 4 + q] = (uint16_t)o;
+                                o += (int)acnt[lane_off[Lq + 1]] - (int)acnt[lane_off[Lq]];
+                            }
                         }
                     }
                 }
+                const int o4 = (o + 1) & ~1;                                     /* even: phase F loads pairs */
 #ifdef __CUDACC__
-                int incl = o;
+                int incl = o4;
 #pragma unroll
                 for (int sh = 1; sh < 16; sh <<= 1) {
                     const int t = __shfl_up_sync(0xffffffffu, incl, sh);
                     if (tid >= sh) incl += t;
                 }
-                if (d <= PVE_NLANE) vl_base[d] = incl - o;
+                const int base = incl - o4;
 #else
-                vl_base[d] = run; run += o;
-                if (d == PVE_NLANE - 1) vl_base[PVE_NLANE] = run;
+                const int base = run; run += o4;
 #endif
+                if (d <= PVE_NLANE) vl_base[d] = base;
+                if (o4 != o) { epos[base + o] = PVE_INF; edir[base + o] = 0xFF; }
             }
         }
     PVE_END_TID
 
-    /* ---- E: virtual-lane membership: each agent offers itself to its own lane and to the four
-     *         lanes it conflicts with.  All slot reservations are issued before the first store so
-     *         that their latencies overlap ------------------------------------------------------- */
+    /* ---- E: virtual-lane membership: each agent offers itself to its own lane and to the four lanes it
+     *         conflicts with (slot = segment base + source-lane offset + its index among its lane's agents;
+     *         an agent that is not a member leaves a +inf entry) --------------------------------------- */
     PVE_FOR_TID(tid)
+#pragma unroll 1
         for (int g = tid; g < A; g += NT) {
             const int k = vidx[g];
             const int Lk = lane_of[k];
             const double p = sp[k];
-            double pos[4];
-            int dir[4], slot[4];
-            const bool crossing = (Lk % 3 != 2);
-#pragma unroll
-            for (int s = 0; s < 4; ++s) {
-                const int dd = P.rev_dir[Lk][s], q = P.rev_k[Lk][s];
-                const int mv = dd % 3;
-                const double delta = (p - P.vd_a1[mv][q]) + P.vd_a2[mv][q];      /* TIS:733-803 */
-                pos[s] = P.vd_b[mv][q] + delta;
-                dir[s] = (crossing && hdr->lane_n[dd] > 0 && delta > 0) ? dd : -1;       /* TIS:234, 259 */
-            }
-            const int e0 = vl_base[Lk] + PVE_ATOMIC_ADD(&vl_cnt[Lk], 1);         /* TIS:242-249 */
-#pragma unroll
-            for (int s = 0; s < 4; ++s)
-                slot[s] = (dir[s] >= 0) ? PVE_ATOMIC_ADD(&vl_cnt[dir[s]], 1) : 0;
+            const int ai = g - afirst[Lk];
+            const int e0 = vl_base[Lk] + ai;                                     /* TIS:242-249 */
             epos[e0] = p; eidx[e0] = (uint16_t)k; edir[e0] = (uint8_t)Lk;
+            if (Lk % 3 != 2) {
+                /* all look-ups first, the stores afterwards: four independent chains instead of four branches */
+                int e[4], edv[4];
+                double pos[4];
+                bool ex[4];
 #pragma unroll
-            for (int s = 0; s < 4; ++s)
-                if (dir[s] >= 0) {
-                    const int e = vl_base[dir[s]] + slot[s];
-                    epos[e] = pos[s]; eidx[e] = (uint16_t)k; edir[e] = (uint8_t)dir[s];
+                for (int s = 0; s < 4; ++s) {
+                    const int dd = P.rev_dir[Lk][s], q = P.rev_k[Lk][s];
+                    const int mv = dd % 3;
+                    ex[s] = hdr->lane_n[dd] > 0;                                 /* TIS:234 */
+                    const double delta = (p - P.vd_a1[mv][q]) + P.vd_a2[mv][q];  /* TIS:733-803 */
+                    const bool member = delta > 0;                               /* TIS:259 */
+                    pos[s] = member ? P.vd_b[mv][q] + delta : PVE_INF;
+                    edv[s] = member ? dd : 0xFF;
+                    e[s] = vl_base[dd] + (int)seg[dd * 4 + q] + ai;              /* meaningless unless ex[s] */
                 }
+#pragma unroll
+                for (int s = 0; s < 4; ++s)
+                    if (ex[s]) { epos[e[s]] = pos[s]; eidx[e[s]] = (uint16_t)k; edir[e[s]] = (uint8_t)edv[s]; }
+            }
         }
     PVE_END_TID
 
     /* ---- F: stable sort by position (TIS:271) as a rank count on the key (pos, slot).  The sorted list of
      *         direction d lives at spos[vl_base[d] + 12 d + 6 ...] between six -inf and six +inf sentinels,
-     *         so that phase G1 reads its twelve candidates without bounds checks ---------------------- */
+     *         so that phase G1 reads its twelve candidates without bounds checks.  A segment has an even
+     *         number of entries and its non-members are +inf, so the count runs unchecked, two entries per load */
     PVE_FOR_TID(tid)
+#pragma unroll 1
         for (int e = tid; e < vl_base[PVE_NLANE]; e += NT) {
             const int d = edir[e];
             if (d != 0xFF) {
-                const int base = vl_base[d], n = vl_cnt[d];
+                const int base = vl_base[d], n2 = vl_base[d + 1] - base;
                 const double pos = epos[e];
                 const int idx = eidx[e];
-                int less = 0, le = 0;
-                int t = 0;
+                uint32_t less = 0, greater = 0;
+                const pve_d2 *const ep2 = (const pve_d2 *)(epos + base);
 #pragma unroll 4
-                for (t = 0; t < n; ++t) {
-                    const double pt = epos[base + t];
-                    less += (pt < pos) ? 1 : 0;
-                    le += (pt <= pos) ? 1 : 0;
+                for (int t = 0; t < n2; t += 2) {
+                    const pve_d2 u0 = ep2[t >> 1];
+                    less += pve_isneg(u0.x - pos); greater += pve_isneg(pos - u0.x);
+                    less += pve_isneg(u0.y - pos); greater += pve_isneg(pos - u0.y);
                 }
-                int rank = less;
-                if (le - less > 1) {            /* equal positions keep insertion (slot) order */
-                    for (t = 0; t < n; ++t)
+                int rank = (int)less;
+                const int sb = base + 12 * d + 6;
+                if (n2 - (int)less - (int)greater > 1) {      /* equal positions keep insertion (slot) order */
+#pragma unroll 1
+                    for (int t = 0; t < n2; ++t)
                         rank += (epos[base + t] == pos && (int)eidx[base + t] < idx) ? 1 : 0;
                     tie[d] = 1;
                 }
-                const int sb = base + 12 * d + 6;
                 spos[sb + rank] = pos; sidx[sb + rank] = (uint16_t)idx;
-                if (lane_of[idx] == d) arank[acnt[idx]] = (uint16_t)rank;
+                if (lane_of[idx] == d) arank[acnt[idx]] = (uint16_t)(sb + rank);   /* where the agent sits in its own list */
                 if (rank == 0) headk[d] = (int16_t)idx;     /* virtual_lane_4[d][0], read by step() (Q2) */
             }
         }
-        for (int q = tid; q < 12 * PVE_NLANE; q += NT) {       /* the sentinels */
-            const int d = q / 12, w = q - d * 12;
-            const int sb = vl_base[d] + 12 * d + 6;
-            if (w < 6) spos[sb - 1 - w] = -PVE_INF; else spos[sb + vl_cnt[d] + (w - 6)] = PVE_INF;
+#pragma unroll 1
+        for (int q = tid; q < 6 * PVE_NLANE; q += NT) {        /* the lower sentinels */
+            const int d = q / 6, w = q - d * 6;
+            spos[vl_base[d] + 12 * d + 5 - w] = -PVE_INF;
         }
     PVE_END_TID
 
     /* ---- G1: per agent: vir_header, six neighbours, row 0, gather codes -------------------- */
     PVE_FOR_TID(tid)
+#pragma unroll 1
         for (int g = tid; g < A; g += NT) {
             const int k = vidx[g];
             const int d = lane_of[k];
-            const int sb = vl_base[d] + 12 * d + 6, n = vl_cnt[d], r = arank[g];
-            const double *const S = spos + sb;                  /* S[-6..-1] = -inf, S[n..n+5] = +inf */
-            const uint16_t *const SI = sidx + sb;
-            const double pe = S[r];
+            const int ax = arank[g];                            /* the ego's entry in the sorted lists (phase F) */
+            const double a_old = S.a[vbase + k];                /* last tick's a, still in HBM: jerk of the reward (TIS:316) */
+            const double *const S_ = spos + ax;                 /* S_[-r-6 .. -r-1] = -inf, S_[n-r .. n-r+5] = +inf */
+            const uint16_t *const SI = sidx + ax;
+            const double pe = S_[0];
             /* Six nearest by |delta|, ties to the lower list index (stable sort, TIS:1389).  Only the six
              * entries below and the six above the ego can qualify; both sides are sorted by distance, so the
              * answer is the head of a two-way merge in which the below side wins ties (lower list index).
-             * Instead of walking outwards (a serial chain of dependent loads) the merge is evaluated in closed
-             * form: the first m outputs contain the t-th below entry iff dl[t-1] <= dh[m-t] (merge path), so
-             * a(m) = #below among the first m = sum over i + j = m - 1 of [dl[i] <= dh[j]]: 21 comparisons. */
-            double dl[PVE_NNBR], dh[PVE_NNBR];
-#pragma unroll
-            for (int i = 0; i < PVE_NNBR; ++i) { dl[i] = pe - S[r - 1 - i]; dh[i] = S[r + 1 + i] - pe; }
-            /* vir_header / vir_dis, TIS:1349-1354 */
-            if (r == 0) { hdra[g] = -1; virdis[g] = 100.0; }
-            else { hdra[g] = (int16_t)acnt[SI[r - 1]]; virdis[g] = dl[0]; }
+             * The sentinels make bounds checks unnecessary: an exhausted side has distance +inf. */
+            const double dl0 = pe - S_[-1];
+            /* vir_header, TIS:1349-1354 (vir_dis: pve_vir_dis, phase I) */
+            hdra[g] = (dl0 == PVE_INF) ? (int16_t)-1 : (int16_t)acnt[SI[-1]];
             pve_v4 *const orow = (pve_v4 *)(row0 + (size_t)g * PVE_OBS_W);
             orow[0] = pve_pack4((float)pe, (float)sv[k], (float)sa[k], (float)d);        /* TIS:1336 */
             uint16_t *const sc = srcc + g * 7;
             sc[0] = (uint16_t)(g * 7);
-            int nb0 = 0xFFFF;
-            double vd0 = 0.0;
-            const int below = r < PVE_NNBR ? r : PVE_NNBR, above = (n - 1 - r) < PVE_NNBR ? (n - 1 - r) : PVE_NNBR;
-            const int ncand = (below + above) < PVE_NNBR ? (below + above) : PVE_NNBR;
+            int nb0 = 0xFFFF, x0 = 0;                          /* nearest neighbour: vehicle slot, list index relative to the ego */
             if (tie[d]) {
                 /* entries at equal positions in this list (rare): among equal |delta| below the ego the farther
                  * list index comes first -- resolved with the reference's own outward walk */
-                int lo = r - 1, hi = r + 1, run_cur = 0, run_end = -1;
+                int lo = -1, hi = 1, run_cur = 0, run_end = -1;           /* list indices relative to the ego */
                 double run_d = 0;
+#pragma unroll 1
                 for (int q = 0; q < PVE_NNBR; ++q) {
-                    if (run_cur > run_end && lo >= 0) {
-                        run_end = lo; run_d = fabs(S[lo] - pe);
+                    if (run_cur > run_end && S_[lo] != -PVE_INF) {
+                        run_end = lo; run_d = fabs(S_[lo] - pe);
                         int x = lo;
-                        while (x - 1 >= 0 && fabs(S[x - 1] - pe) == run_d) --x;
+                        while (fabs(S_[x - 1] - pe) == run_d) --x;              /* a -inf sentinel ends the run */
                         run_cur = x; lo = x - 1;
                     }
-                    const bool has_lo = run_cur <= run_end, has_hi = hi < n;
-                    int pick = -1;
-                    if (has_lo && (!has_hi || run_d <= fabs(S[hi] - pe))) pick = run_cur++;
+                    const bool has_lo = run_cur <= run_end, has_hi = S_[hi] != PVE_INF;
+                    int pick = 0;
+                    if (has_lo && (!has_hi || run_d <= fabs(S_[hi] - pe))) pick = run_cur++;
                     else if (has_hi) pick = hi++;
-                    if (pick >= 0) {
+                    if (pick != 0) {
                         const int kn = SI[pick];
-                        const double vd = S[pick];
+                        const double vd = S_[pick];
                         orow[q + 1] = pve_pack4((float)vd, (float)sv[kn], (float)sa[kn], (float)lane_of[kn]);
                         sc[q + 1] = (kn < k) ? (uint16_t)(acnt[kn] * 7) : (uint16_t)(PVE_SRC_PREV | (kn * 7));
-                        if (q == 0) { nb0 = kn; vd0 = vd; }
+                        if (q == 0) { nb0 = kn; x0 = pick; }
+                    } else {
+                        orow[q + 1] = pve_pack4(0.f, 0.f, 0.f, 0.f);             /* TIS:1334 */
+                        sc[q + 1] = (uint16_t)(AC * 7);                          /* the zero row */
                     }
                 }
             } else {
-                int am[PVE_NNBR + 1];
-                am[0] = 0;
-#pragma unroll
-                for (int m = 1; m <= PVE_NNBR; ++m) {
-                    int c = 0;
-#pragma unroll
-                    for (int t = 1; t <= m; ++t) c += (dl[t - 1] <= dh[m - t]) ? 1 : 0;
-                    am[m] = c;
-                }
-#pragma unroll
+                /* the merge itself, rolled (code size: the kernel's instruction stream is fetched once per CTA and does
+                 * not fit the instruction cache): the next candidate of each side is kept one step ahead */
+                int lo = -1, hi = 1;
+                double dlo = dl0, dhi = S_[1] - pe;
+#pragma unroll 1
                 for (int q = 0; q < PVE_NNBR; ++q) {
-                    if (q < ncand) {
-                        const int x = (am[q + 1] != am[q]) ? r - 1 - am[q] : r + 1 + q - am[q];
+                    const bool take_lo = dlo <= dhi;                             /* below wins ties: lower list index */
+                    const int x = take_lo ? lo : hi;
+                    pve_v4 piece = pve_pack4(0.f, 0.f, 0.f, 0.f);                /* TIS:1334 */
+                    uint32_t code = (uint32_t)(AC * 7);                          /* the zero row */
+                    if ((take_lo ? dlo : dhi) != PVE_INF) {                      /* else: both sides exhausted */
                         const int kn = SI[x];
-                        const double vd = S[x];
-                        orow[q + 1] = pve_pack4((float)vd, (float)sv[kn], (float)sa[kn], (float)lane_of[kn]);   /* TIS:1330 */
+                        const double vd = S_[x];
+                        piece = pve_pack4((float)vd, (float)sv[kn], (float)sa[kn], (float)lane_of[kn]);          /* TIS:1330 */
                         /* Q3: neighbour already processed this tick -> its new row, else last tick's */
-                        sc[q + 1] = (kn < k) ? (uint16_t)(acnt[kn] * 7) : (uint16_t)(PVE_SRC_PREV | (kn * 7));
-                        if (q == 0) { nb0 = kn; vd0 = vd; }
+                        code = (kn < k) ? (uint32_t)(acnt[kn] * 7) : (PVE_SRC_PREV | (uint32_t)(kn * 7));
+                        if (q == 0) { nb0 = kn; x0 = x; }
                     }
+                    orow[q + 1] = piece;
+                    sc[q + 1] = (uint16_t)code;
+                    if (take_lo) { --lo; dlo = pe - S_[lo]; } else { ++hi; dhi = S_[hi] - pe; }
                 }
             }
-#pragma unroll
-            for (int q = 0; q < PVE_NNBR; ++q)
-                if (q >= ncand) {
-                    orow[q + 1] = pve_pack4(0.f, 0.f, 0.f, 0.f);                 /* TIS:1334 */
-                    sc[q + 1] = (uint16_t)(AC * 7);                              /* the zero row */
-                }
             nn0[g] = (uint16_t)nb0;
-            vd0s[g] = vd0;
+            /* reward (TIS:293-320): everything it needs is in this thread's hands */
+            {
+                const bool has_nb = nb0 != 0xFFFF;
+                const double jr = (sa[k] - a_old) / P.dt;                        /* TIS:1522, 316 */
+                rew[g] = pve_reward(P, pe, sv[k], jr, has_nb, S_[x0], has_nb ? sv[nb0] : 0.0);
+            }
         }
         if (tid < PVE_OBS_W / 4) ((pve_v4 *)(row0 + (size_t)AC * PVE_OBS_W))[tid] = pve_pack4(0.f, 0.f, 0.f, 0.f);
+        /* world positions (TIS:1250-1290) on the threads that have no agent in this phase */
+        if (NS < NT && tid >= NS)
+#pragma unroll 1
+            for (int g = tid - NS; g < A; g += NT - NS) {
+                const int k = vidx[g];
+                pve_world_xy(P, sp[k], lane_of[k], &xy[2 * g], &xy[2 * g + 1]);
+            }
     PVE_END_TID
 
     /* ---- CTA split: the upper half of the CTA moves the observation rows (everything they need is
      *      final after G1) while the lower half ("team") finishes the tick ------------------------ */
-    constexpr int NS = (NT >= 128) ? NT / 2 : (NT == 96 ? 64 : NT);      /* 96: two team warps, one mover warp */
     PveRowJob RJ;
     RJ.A = A; RJ.srcc = srcc; RJ.rows_smem = row0; RJ.rows_prev = row0_prev_base; RJ.oblk = oblk; RJ.zero_row = AC;
 #ifdef __CUDACC__
@@ -920,43 +1007,21 @@ PVE_DEV void pve_step_block(const PveParams &P, const PveState &S, const pve_out
     }
 #endif
 
-    /* ---- G2: two work items per agent: reward (TIS:293-320), world position (TIS:1250-1290) */
+    /* ---- G2 (no CTA split only): world positions (TIS:1250-1290), which the mover warps otherwise computed
+     *          during G1 ---------------------------------------------------------------------------------- */
+    if (NS == NT) {
     PVE_FOR_TEAM(tid)
-        const int A32 = (A + 31) & ~31;         /* the two item kinds start on warp boundaries */
-        for (int it = tid; it < A32 + A; it += NS) {
-            const bool is_xy = it >= A32;
-            const int g = is_xy ? it - A32 : it;
-            if (g >= A) continue;
+#pragma unroll 1
+        for (int g = tid; g < A; g += NS) {
             const int k = vidx[g];
-            if (is_xy) {
-                double x, y;
-                pve_world_xy(P, sp[k], lane_of[k], &x, &y);
-                xy[2 * g] = x; xy[2 * g + 1] = y;
-            } else {
-                const double p = sp[k], v = sv[k];
-                const int k0 = nn0[g];
-                double t_distance = 2, d_distance = 10;
-                if (k0 != 0xFFFF) {
-                    const double vd0 = vd0s[g];
-                    d_distance = fabs(p - vd0);                                  /* TIS:300 */
-                    if (d_distance != 0) t_distance = (p - vd0) / (v - sv[k0] + 0.0001);  /* TIS:304 */
-                }
-                double r_ = 0;
-                if (0 < t_distance && t_distance < 4) r_ += 1 / tanh(t_distance * -0.25);   /* TIS:314 */
-                const double jr = sjr[k];
-                r_ -= jr * jr * (3.0 / 3600.0);                                  /* TIS:316 */
-                if (d_distance < 10) {
-                    const double x = d_distance * 0.1, x2 = x * x;
-                    r_ += log(x2 * x2 * x + 0.00001);                            /* TIS:318 */
-                }
-                r_ += (v - P.vm) * (2.0 / P.aspan);                              /* TIS:319 */
-                rew[g] = (float)fmin(20.0, fmax(-20.0, r_));                     /* TIS:320 */
-            }
+            pve_world_xy(P, sp[k], lane_of[k], &xy[2 * g], &xy[2 * g + 1]);
         }
     PVE_END_TEAM
+    }
 
     /* ---- G3: collision test in world space, TIS:322-334 ------------------------------------ */
     PVE_FOR_TEAM(tid)
+#pragma unroll 1
         for (int g = tid; g < A; g += NS) {
             const int k0 = nn0[g];
             if (k0 != 0xFFFF) {
@@ -973,6 +1038,7 @@ PVE_DEV void pve_step_block(const PveParams &P, const PveState &S, const pve_out
 
     /* ---- H: removal / finish flags for every vehicle, TIS:335-359 ------------------------- */
     PVE_FOR_TEAM(tid)
+#pragma unroll 1
         for (int k = tid; k < V; k += NS) {
             const int g = ctl0[k] ? (int)acnt[k] : -1;
             uint32_t pk = spk[k];
@@ -1020,12 +1086,12 @@ PVE_DEV void pve_step_block(const PveParams &P, const PveState &S, const pve_out
 #ifndef __CUDACC__
         if (tid < PVE_NLANE) misc[M_NEXT0 + tid] = hdr->next_spawn[tid];        /* serial stand-in for J's ballot */
 #endif
+#pragma unroll 1
         for (int g = tid; g < A; g += NS) {
             const int k = vidx[g];
             /* reward[-1] overrides in processing order: a later -10 beats the agent's own +5 (Q5) */
             if (q5[g]) rew[g] = -10.f;                                           /* TIS:346 */
             else if (fin5[g]) rew[g] = 5.f;                                      /* TIS:357 */
-            vd0s[g] = fin5[g] ? sjs[k] : 0.0;                                    /* TIS:358 (statistics) */
             if (out_ok) {                                                        /* the small per-agent outputs */
                 if (O.reward) O.reward[obase + g] = rew[g];
                 if (O.ids) {
@@ -1039,7 +1105,7 @@ PVE_DEV void pve_step_block(const PveParams &P, const PveState &S, const pve_out
             }
             if (!((spk[k] >> 24) & PVE_F_CONTROL) || del[k]) continue;
             int t = g, len = 0;
-#pragma unroll
+#pragma unroll 1
             for (int hop = 1; hop <= 10; ++hop) {                                /* TIS:1470-1478 */
                 t = (t >= 0 && len == 0) ? (int)hdra[t] : -1;
                 len = (t == g) ? hop : len;
@@ -1048,6 +1114,7 @@ PVE_DEV void pve_step_block(const PveParams &P, const PveState &S, const pve_out
             slock[k] = 1;                                                        /* TIS:1482 */
             int mn = g;
             t = g;
+#pragma unroll 1
             for (int hop = 0; hop < len; ++hop) { t = hdra[t]; mn = t < mn ? t : mn; }
             if (mn != g) continue;          /* the first member in (lane, j) order reports the ring */
             PVE_ATOMIC_ADD(&misc[M_LOCK], 1);
@@ -1056,12 +1123,14 @@ PVE_DEV void pve_step_block(const PveParams &P, const PveState &S, const pve_out
              * per output position instead of materialising the list. */
             double last_d = -1.0e300, sum = 0, first_d = 0;
             int last_o = -1, first_o = -1;
+#pragma unroll 1
             for (int x = 0; x < len; ++x) {
                 double best_d = 1.0e300;
                 int best_o = 0x7FFFFFFF;
                 t = g;
+#pragma unroll 1
                 for (int hop = 0; hop < len; ++hop) {
-                    const double dd = virdis[t];
+                    const double dd = pve_vir_dis(spos, arank, t);
                     const bool after = dd > last_d || (dd == last_d && t > last_o);
                     const bool better = dd < best_d || (dd == best_d && t < best_o);
                     if (after && better) { best_d = dd; best_o = t; }
@@ -1140,8 +1209,9 @@ PVE_DEV void pve_step_block(const PveParams &P, const PveState &S, const pve_out
     PVE_END_TEAM
 
     /* ---- K: write the state back, compacted; header; statistics ---------------------------------- */
-    pve_warp0_sums<NT>(rew, vd0s, A, dsum);
+    pve_warp0_sums<NT>(rew, fin5, sjs, vidx, A, dsum);
     PVE_FOR_TEAM(tid)
+#pragma unroll 1
         for (int k = tid; k < V; k += NS)
             if (!del[k]) {
                 const size_t o = vbase + (size_t)((int)surv[k] + misc[M_SPREF0 + lane_of[k]]);
@@ -1165,6 +1235,7 @@ PVE_DEV void pve_step_block(const PveParams &P, const PveState &S, const pve_out
             for (int q = 0; q < PVE_OBS_W / 4; ++q) ((pve_v4 *)(row0_next + (size_t)np * PVE_OBS_W))[q] = z;
         }
         /* stored row 0 of every surviving agent -> next tick's neighbour rows / actor input */
+#pragma unroll 1
         for (int it = tid; it < A * 8; it += NS) {
             const int g = it >> 3, q = it & 7;
             const int k = vidx[g];
@@ -1178,6 +1249,15 @@ PVE_DEV void pve_step_block(const PveParams &P, const PveState &S, const pve_out
             S.n_ctrl_next[b] = hdr->n_ctrl; S.n_veh[b] = hdr->n_veh;
             PVE_RED_ADD(&S.gs_acc[b >> PVE_GROUP_SHIFT], hdr->n_ctrl);         /* next tick's group sums */
             if ((b & ((1 << PVE_GROUP_SHIFT) - 1)) == 0) S.gs_zero[b >> PVE_GROUP_SHIFT] = 0;
+            if (S.klass_next) {      /* next tick: vehicles stepped + arrivals already due must fit the small class */
+                int due = 0;
+#pragma unroll 1
+                for (int i = 0; i < PVE_NLANE; ++i) due += (hdr->tick + 1 >= hdr->next_spawn[i]) ? 1 : 0;
+                const int big = (hdr->n_veh + due > S.small_vc || hdr->n_ctrl + due > S.small_ac) ? 1 : 0;
+                S.klass_next[b] = (uint8_t)big;
+                if (big) S.big_list_next[PVE_ATOMIC_ADD(S.big_cnt_next, 1)] = b;
+                if (b == 0) *S.big_cnt_zero = 0;
+            }
             if (O.agent_offset) {
                 O.agent_offset[b] = (int32_t)obase;
                 if (b == P.B - 1) O.agent_offset[P.B] = (int32_t)obase + A;
@@ -1204,6 +1284,7 @@ PVE_DEV void pve_step_block(const PveParams &P, const PveState &S, const pve_out
      *      Only in the SRC instantiation of the kernel. */
     if (SRC && O.nbr_src != nullptr && out_ok) {
         PVE_FOR_TEAM(tid)
+#pragma unroll 1
             for (int g = tid; g < A; g += NS) {
                 uint32_t w4[4];
 #pragma unroll

@@ -19,8 +19,8 @@ RTOL = 1e-5          # north-star tolerance: fp32 outputs against the float64 re
 
 
 def make_scene(backend, B, vm=5, collision_thr=2, veh_cap=128, agent_cap=96, threads=0, out_cap=None,
-               neighbour_sources=False):
-    cfg = SceneConfig(vm=vm, collision_thr=collision_thr)
+               neighbour_sources=False, zero_uncontrolled_actions=False):
+    cfg = SceneConfig(vm=vm, collision_thr=collision_thr, zero_uncontrolled_actions=zero_uncontrolled_actions)
     if backend == "cuda":
         return BatchedScene(B, cfg, veh_cap=veh_cap, agent_cap=agent_cap, out_cap=out_cap, device="cuda:0",
                             threads=threads, neighbour_sources=neighbour_sources)

@@ -55,6 +55,26 @@ def test_free_running_train_setting_vm6_accel():
     free_run(BACKEND, tabs, vm=6, ticks=330, seed=2, policy="accel")
 
 
+def test_zero_uncontrolled_actions_option():
+    """pve_config.zero_uncontrolled: garbage in the slots of uncontrolled vehicles == the reference driver's 0 (MAIN:401-405)."""
+    tabs = synthetic_arrivals(2, 1000, 40.0, seed=5, rows=32)
+    scene = P.make_scene(BACKEND, 2, vm=5, zero_uncontrolled_actions=True)
+    orc = P.make_oracle(2, vm=5, veh_cap=scene.veh_cap)
+    scene.reset(tabs, warmup=True)
+    orc.reset(tabs, warmup=True)
+    rng = np.random.RandomState(11)
+    n_unctl = 0
+    for t in range(300):
+        ctrl = (orc.get_state()["flags"] & 1) != 0
+        raw = rng.uniform(-3, 3, size=ctrl.shape).astype(np.float32)          # every slot filled
+        o_ref = orc.step(np.where(ctrl, raw, 0).astype(np.float32))
+        o_dev = P.outputs_to_numpy(scene.step(P.to_device_actions(scene, raw)))
+        P.compare_outputs(o_dev, o_ref, "tick %d" % t)
+        n_unctl += int((~ctrl & (np.arange(ctrl.shape[1])[None, :] < orc.get_state()["lane_n"].sum(axis=1)[:, None])).sum())
+    P.compare_states(scene.get_state(), orc.get_state(), "final")
+    assert n_unctl > 1000
+
+
 def test_stress_occupancy_brake():
     tabs = stress_arrivals(1, 40.0)
     free_run(BACKEND, tabs, vm=5, ticks=300, seed=3, veh_cap=384, agent_cap=320, policy="brake")
