@@ -553,6 +553,7 @@ def graft_arm(args, rank, world, local_rank, veh_cap, agent_cap):
             "config": {"workload": workload_name(args), "l2": "flushed between timed steps (384 MiB fill)",
                        "prime_ticks": PRIME_TICKS, "veh_cap": veh_cap, "agent_cap": agent_cap,
                        "threads_per_cta": scene.threads, "smem_per_cta": scene.smem_bytes,
+                       "launch": scene.launch_info,
                        "agents_per_env_step": dA / (K * B), "vehicles_per_env_step": dV / (K * B),
                        "env_steps_per_s": world * B * K / (total_ms * 1e-3)},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",

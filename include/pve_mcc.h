@@ -181,6 +181,11 @@ int32_t pve_set_profiling(pve_scene *s, int32_t on);
 int32_t pve_kernel_ms(pve_scene *s, float *step_ms, float *scan_ms);
 int64_t pve_smem_bytes(const pve_scene *s);
 int32_t pve_threads(const pve_scene *s);
+/* How a tick is launched.  out[0] = 1: "dual mode" (the default class with the default CTA size): two concurrent
+ * kernels per tick -- intersections whose vehicles and due arrivals fit out[1] slots / out[2] agents run in CTAs of
+ * out[3] threads with out[4] bytes of shared memory, the few others in CTAs of pve_threads() / pve_smem_bytes() on an
+ * internal high-priority stream; results are identical to the single-kernel launch (out[0] = 0; env PVE_DUAL=0). */
+int32_t pve_launch_info(const pve_scene *s, int32_t out[8]);
 /* capacities actually in use: the requested ones rounded up to a compiled capacity class
  * (128/80, 128/96, 192/128, 384/320, 576/416); every [B][veh_cap] array uses pve_veh_cap() as its stride */
 int32_t pve_veh_cap(const pve_scene *s);

@@ -77,6 +77,7 @@ def load_library(path=None):
     lib.pve_smem_bytes.argtypes = [vp]
     lib.pve_smem_bytes.restype = i64
     lib.pve_threads.argtypes = [vp]
+    lib.pve_launch_info.argtypes = [vp, C.POINTER(C.c_int32 * 8)]
     lib.pve_veh_cap.argtypes = [vp]
     lib.pve_agent_cap.argtypes = [vp]
     lib.pve_stats.argtypes = [vp, vp, vp]

@@ -871,6 +871,17 @@ const pve_veh_meta *pve_meta_dev(const pve_scene *s) { return s ? s->st.meta : n
 const pve_env_header *pve_hdr_dev(const pve_scene *s) { return s ? s->st.hdr : nullptr; }
 int64_t pve_smem_bytes(const pve_scene *s) { return s ? (int64_t)s->smem_bytes : 0; }
 int32_t pve_threads(const pve_scene *s) { return s ? s->threads : 0; }
+int32_t pve_launch_info(const pve_scene *s, int32_t out[8]) {
+    if (!s || !out) return PVE_EINVAL;
+    for (int i = 0; i < 8; ++i) out[i] = 0;
+#ifndef PVE_HOST_EMULATION
+    if (s->dual) {
+        out[0] = 1; out[1] = PVE_SMALL_VC; out[2] = PVE_SMALL_AC; out[3] = PVE_SMALL_NT;
+        out[4] = (int32_t)PveLayout<PVE_SMALL_VC, PVE_SMALL_AC>::BYTES;
+    }
+#endif
+    return PVE_OK;
+}
 #ifdef PVE_PHASE_TIMING
 const void *pve_debug_stamps(const pve_scene *s) { return s ? s->st.dbg : nullptr; }
 #endif

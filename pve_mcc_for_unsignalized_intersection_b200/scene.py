@@ -132,6 +132,15 @@ class BatchedScene:
     def threads(self):
         return int(self.lib.pve_threads(self._h))
 
+    @property
+    def launch_info(self):
+        """How a tick is launched (``pve_launch_info``): ``{"dual": bool, "small_veh_cap", "small_agent_cap",
+        "small_threads", "small_smem_bytes"}``."""
+        out = (C.c_int32 * 8)()
+        self._check(self.lib.pve_launch_info(self._h, C.byref(out)))
+        return {"dual": bool(out[0]), "small_veh_cap": out[1], "small_agent_cap": out[2], "small_threads": out[3],
+                "small_smem_bytes": out[4]}
+
     # ---- reset: TrafficInteraction(arrive_time, ...) TIS:195-220 --------------------------
     def reset(self, arrive_time=None, warmup=True, spawn_ticks=None):
         """``arrive_time``: float64 seconds ``[K, 12]`` (shared) or ``[B, K, 12]`` (per intersection),

@@ -344,6 +344,9 @@ SPECS = {
     "mat600_vm5": (lambda: mat_table(600, 20), 460, "uniform", 5, 18),
     "mat800_vm6": (lambda: mat_table(800, 28), 440, "uniform", 6, 19),
     "mat900_vm5": (lambda: mat_table(900, 30), 440, "accel", 5, 20),
+    # args.collision_thr, the one CLI flag that reaches the scene (main.py:104 -> TIS:32, 332, 1495)
+    "mat1200_thr15": (lambda: mat_table(1200, 40), 420, "uniform", 5, 21, 1.5),
+    "mat1000_thr3": (lambda: mat_table(1000, 40), 420, "mixed", 6, 22, 3.0),
 }
 
 
@@ -351,9 +354,10 @@ def main(names):
     """``python make_golden.py``: everything; ``python make_golden.py name ...``: only those rollouts
     (``crafted`` = the crafted single-tick cases)."""
     mod = load_reference()
-    for name, (table, ticks, policy, vm, seed) in SPECS.items():
+    for name, spec in SPECS.items():
+        table, ticks, policy, vm, seed = spec[:5]
         if not names or name in names:
-            rollout(mod, name, table(), ticks, policy, vm=vm, seed=seed)
+            rollout(mod, name, table(), ticks, policy, vm=vm, seed=seed, collision_thr=spec[5] if len(spec) > 5 else 2)
     if not names or "crafted" in names:
         crafted(mod)
 

@@ -5,7 +5,7 @@ import numpy as np
 
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 ROLLOUTS = ["mat1000_vm5", "mat1200_vm6", "mat200_vm5", "stress_brake", "synth1000_accel", "synth800_mixed",
-            "mat400_vm6", "mat600_vm5", "mat800_vm6", "mat900_vm5"]
+            "mat400_vm6", "mat600_vm5", "mat800_vm6", "mat900_vm5", "mat1200_thr15", "mat1000_thr3"]
 STATE_KEYS_V = ["p", "v", "a", "jerk_sum", "collision", "step", "seq_in_lane", "uid", "control",
                 "finish", "lock", "lock_a"]
 STATE_KEYS_E = ["tick", "lane_n", "veh_rec", "head_lane", "head_j", "id_seq", "passed_veh",

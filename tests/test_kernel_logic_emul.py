@@ -85,7 +85,7 @@ def test_golden_rollout_direct(name):
     """Kernel logic against the reference's own trace (no oracle in between)."""
     z, r = load_rollout(name)
     big = name == "stress_brake"
-    scene = P.make_scene(BACKEND, 1, vm=float(z["vm"]), veh_cap=384 if big else 128, agent_cap=320 if big else 96)
+    scene = P.make_scene(BACKEND, 1, vm=float(z["vm"]), collision_thr=float(z["collision_thr"]), veh_cap=384 if big else 128, agent_cap=320 if big else 96)
     scene.reset(z["table"], warmup=True)
     obs_at = {int(t): k for k, t in enumerate(z["obs_ticks"])}
     for t in range(int(z["n_ticks"])):
