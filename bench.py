@@ -352,6 +352,16 @@ def graft_arm(args, rank, world, local_rank, veh_cap, agent_cap):
         raise RuntimeError("bench.py needs a CUDA device: the environment step has no CPU fallback")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    if world > 1:
+        # one rank per GPU on one host: give every rank its own cores (host threads of the pipelined host path and of the
+        # launches do not migrate or compete) -- the node's GPUs all report the same CPU affinity, so a plain split
+        try:
+            cpus = sorted(os.sched_getaffinity(0))
+            per = max(1, len(cpus) // world)
+            mine = cpus[local_rank * per:(local_rank + 1) * per] or cpus
+            os.sched_setaffinity(0, mine)
+        except (AttributeError, OSError):
+            pass
     if world > 1 and not dist.is_initialized():
         # stdout carries exactly one JSON line: whatever the communicator set-up writes to file descriptor 1 (NCCL's
         # banner and, with NCCL_DEBUG=INFO, its log) goes to stderr instead; NCCL_DEBUG itself is left as the caller set it
@@ -490,20 +500,34 @@ def graft_arm(args, rank, world, local_rank, veh_cap, agent_cap):
     # veh["state"] and buffers state_next on the host, main.py:234-245); e2e_no_obs: everything but the observations
     e2e = {}
     if not args.no_e2e and actor is None:
-        host = scene.make_host_outputs()
+        pairs = scene.make_async_buffers()
         hact = [p.cpu().pin_memory() for p in pool[:4]]
         for name, with_obs in (("e2e_no_obs", False), ("e2e", True)):
-            for t in range(max(3, W)):
-                scene.step_host(hact[t % len(hact)], host, copy_obs=with_obs)
+            host_s = [0.0, 0.0]
+
+            def run(n_ticks):
+                rows = 0
+                for t in range(n_ticks):
+                    c0 = time.perf_counter()
+                    scene.step_host_async(hact[t % len(hact)], pairs[t % 3], copy_obs=with_obs)
+                    c1 = time.perf_counter()
+                    if t >= 2:
+                        rows += scene.host_wait()[0]          # tick t - 2 is in host memory; ticks t - 1 and t are under way
+                    host_s[0] += c1 - c0
+                    host_s[1] += time.perf_counter() - c1
+                for _ in range(min(2, n_ticks)):
+                    rows += scene.host_wait()[0]
+                return rows
+            run(max(3, W))
             barrier()
             t0 = time.perf_counter()
-            n_rows = 0
-            for t in range(K):
-                n_rows += scene.step_host(hact[t % len(hact)], host, copy_obs=with_obs)
+            n_rows = run(K)
             barrier()
             e2e_s = time.perf_counter() - t0
-            d2h = n_rows / K * (4 + 16 + 4 + 1 + 4 + (OBS_BYTES if with_obs else 0)) + (B + 1) * 4 + 3 * B * 4
+            d2h = n_rows / K * (16 + (OBS_BYTES if with_obs else 0)) + (B + 1) * 4 + 3 * B * 4
             e2e[name] = {"agent_steps": n_rows, "seconds": e2e_s, "h2d": B * veh_cap * 4, "d2h": d2h}
+            print("%s: %.1f us per tick; host time in step_host_async %.1f us, in host_wait %.1f us (incl. warm-up ticks)" % (
+                name, 1e6 * e2e_s / K, 1e6 * host_s[0] / (K + max(3, W)), 1e6 * host_s[1] / (K + max(3, W))), file=sys.stderr)
 
     # ---------------- reduce over ranks ----------------
     vec = torch.tensor([total_ms, total_kern_ms, e2e["e2e"]["seconds"] if e2e else 0.0,
@@ -597,9 +621,11 @@ def graft_arm(args, rank, world, local_rank, veh_cap, agent_cap):
         if e2e:
             line["e2e"] = {"value": e2e_rows / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(e2e["e2e"]["h2d"]),
                            "d2h_bytes_per_step": int(e2e["e2e"]["d2h"]),
-                           "note": "pve_step_host with copy_mask = outputs | observations: actions from pinned host memory, the "
-                                   "whole 9-tuple (7x28 observation of every agent, reward, ids, cpv, status, jerk_sum, offsets, "
-                                   "per-intersection counters) in pinned host memory when the call returns"}
+                           "note": "pve_step_host_async + pve_host_wait, three ticks in flight: every tick's actions travel from pinned "
+                                   "host memory (DMA) and the whole 9-tuple -- the 7x28 observation of every agent, a 16-byte record "
+                                   "{reward, uid, lane, j, status, cpv, jerk_sum} per agent, offsets, per-intersection counters -- is "
+                                   "in pinned host memory when pve_host_wait returns for that tick; ticks t+1 and t+2 are enqueued before "
+                                   "tick t is waited for (the actions are pre-generated, as in the device-resident measurement)"}
             line["e2e_no_obs"] = {"value": e2e_no_rows / e2e_no_s, "unit": UNIT,
                                   "h2d_bytes_per_step": int(e2e["e2e_no_obs"]["h2d"]),
                                   "d2h_bytes_per_step": int(e2e["e2e_no_obs"]["d2h"]),

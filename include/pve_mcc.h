@@ -127,7 +127,20 @@ typedef struct pve_outputs {
      * 0x4000 | k = the row stored LAST tick for vehicle slot k of the same intersection (slot order before this
      * tick's removals).  Entry 7 is padding (-1).  Lets a consumer evaluate a network once per distinct row. */
     int16_t *nbr_src;
+    /* optional (may be null): [out_cap] pve_agent_record, the per-agent scalars of a row in ONE 16-byte record --
+     * what a host-side consumer needs of reward / ids / cpv / status / jerk_sum at 16 instead of 29 bytes per agent
+     * (the intersection index is implied by agent_offset).  pve_step_host_async delivers these records. */
+    void *packed;
 } pve_outputs;
+
+typedef struct pve_agent_record {
+    float reward;           /* as pve_outputs.reward                                           */
+    int32_t uid;            /* as ids[3]                                                       */
+    uint8_t lane, j;        /* as ids[1], ids[2]                                               */
+    uint8_t status;         /* as pve_outputs.status                                           */
+    uint8_t cpv;            /* as pve_outputs.cpv, saturating at 255                           */
+    float jerk_sum;         /* as pve_outputs.jerk_sum                                         */
+} pve_agent_record;
 
 /* End-of-rollout statistics (MAIN:407-415, 566-581), summed over the handle's intersections.
  * Multi-GPU callers all-reduce this 16-double vector (NCCL sum). */
@@ -161,6 +174,19 @@ int32_t pve_step(pve_scene *s, const float *actions_dev, const pve_outputs *out_
  * are then not written this tick (obs always is).  Pageable buffers are staged through device copies. */
 int32_t pve_step_host(pve_scene *s, const float *actions_host, const pve_outputs *out_dev,
                       const pve_outputs *out_host, int32_t copy_mask, void *stream);
+
+/* Pipelined host path: the same tick, but nothing waits.  Actions travel by DMA from `actions_host` (pinned), the
+ * kernel runs on `stream`, and agent_offset + the per-intersection counters + the 16-byte agent records
+ * (out_dev->packed, required) -- with copy_mask bit1 also the observations -- travel by DMA into `out_host` on an
+ * internal copy stream while the caller already enqueues the next ticks.  Three ticks may be in flight: give
+ * consecutive calls different `out_dev` / `out_host` buffer sets (three of them, used in turn) and call
+ * pve_host_wait() for tick t before the call for tick t + 3.  The call itself only waits for the previous tick's KERNEL
+ * (it needs that tick's row count to size the copies). */
+int32_t pve_step_host_async(pve_scene *s, const float *actions_host, const pve_outputs *out_dev,
+                            const pve_outputs *out_host, int32_t copy_mask, void *stream);
+/* waits until the OLDEST tick enqueued by pve_step_host_async has landed in its host buffers; returns its row count
+ * (negative: error) */
+int64_t pve_host_wait(pve_scene *s);
 
 /* rows the NEXT pve_step will emit (device scan result; synchronises `stream`) */
 int64_t pve_next_agent_total(pve_scene *s, void *stream);

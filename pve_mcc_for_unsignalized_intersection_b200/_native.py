@@ -20,7 +20,10 @@ HDR_DTYPE = np.dtype([
     ("next_spawn", "<i4", (NLANE,)), ("veh_rec", "<u2", (NLANE,)), ("lane_n", "u1", (NLANE,)),
     ("head_lane", "i1", (NLANE,)), ("head_j", "u1", (NLANE,)), ("pad_", "u1", (4,))])
 META_DTYPE = np.dtype([("uid", "<i4"), ("packed", "<u4")])
-assert HDR_DTYPE.itemsize == 144 and META_DTYPE.itemsize == 8
+#: pve_agent_record: the per-agent scalars of one output row in 16 bytes
+RECORD_DTYPE = np.dtype([("reward", "<f4"), ("uid", "<i4"), ("lane", "u1"), ("j", "u1"), ("status", "u1"), ("cpv", "u1"),
+                         ("jerk_sum", "<f4")])
+assert HDR_DTYPE.itemsize == 144 and META_DTYPE.itemsize == 8 and RECORD_DTYPE.itemsize == 16
 
 F_CONTROL, F_FINISH, F_LOCK = 1, 2, 4
 ST_DONE, ST_REMOVED, ST_FINISHED = 1, 2, 4
@@ -36,7 +39,7 @@ class PveStateView(C.Structure):
 class PveOutputs(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in
                 ("agent_offset", "obs", "reward", "ids", "cpv", "status", "jerk_sum",
-                 "env_collisions", "env_lock", "env_removed", "nbr_src")]
+                 "env_collisions", "env_lock", "env_removed", "nbr_src", "packed")]
 
 
 class PveReplayView(C.Structure):
@@ -67,6 +70,9 @@ def load_library(path=None):
     lib.pve_reset.argtypes = [vp, vp, i32, i32, vp]
     lib.pve_step.argtypes = [vp, vp, C.POINTER(PveOutputs), vp]
     lib.pve_step_host.argtypes = [vp, vp, C.POINTER(PveOutputs), C.POINTER(PveOutputs), i32, vp]
+    lib.pve_step_host_async.argtypes = [vp, vp, C.POINTER(PveOutputs), C.POINTER(PveOutputs), i32, vp]
+    lib.pve_host_wait.argtypes = [vp]
+    lib.pve_host_wait.restype = i64
     lib.pve_next_agent_total.argtypes = [vp, vp]
     lib.pve_next_agent_total.restype = i64
     lib.pve_set_state.argtypes = [vp, C.POINTER(PveStateView), vp]

@@ -14,6 +14,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <time.h>
 
 #include <new>
 
@@ -39,6 +40,8 @@ const int8_t kLane2Lane[PVE_NLANE][4] = {            /* TIS:153-166 */
 
 }  // namespace
 
+#define PVE_ASYNC_SLOTS 3      /* ticks in flight on the pipelined host path */
+
 struct pve_scene {
     pve_config cfg;
     PveParams prm;
@@ -60,6 +63,17 @@ struct pve_scene {
 #ifndef PVE_HOST_EMULATION
     cudaStream_t side;           /* the big kernel's stream */
     cudaEvent_t ev_fork, ev_join;
+    /* pipelined host path (pve_step_host_async): copy-in / copy-out streams, two ticks in flight */
+    cudaStream_t s_in, s_out, s_cnt;
+    cudaEvent_t a_in[PVE_ASYNC_SLOTS], a_k[PVE_ASYNC_SLOTS], a_cnt[PVE_ASYNC_SLOTS], a_done[PVE_ASYNC_SLOTS];
+    float *a_act[PVE_ASYNC_SLOTS];       /* device action buffers */
+    int64_t *a_total;                    /* pinned [PVE_ASYNC_SLOTS]: rows of the tick AFTER the one in the slot */
+    int64_t a_rows[PVE_ASYNC_SLOTS];
+    int64_t a_seq, a_waited;             /* ticks enqueued / waited for; slot = tick % PVE_ASYNC_SLOTS */
+    int a_ready;                         /* streams/events created */
+    int64_t a_copied;                    /* ticks whose copy-out has been enqueued */
+    pve_outputs a_odev[PVE_ASYNC_SLOTS], a_ohost[PVE_ASYNC_SLOTS];
+    int32_t a_mask[PVE_ASYNC_SLOTS];
 #endif
     int order_age;               /* ticks since the order was refreshed (-1: never) */
     const int32_t *spawn_tick;   /* borrowed */
@@ -160,6 +174,15 @@ pve_step_big_kernel(const PveParams P, const PveState S, const pve_outputs O, co
         pve_step_block<NT, VC, AC, SRC>(P, S, O, spawn_tick, actions, phase, S.big_list[i], pve_smem, nullptr);
         __syncthreads();                                   /* shared memory is reused by the next one */
     }
+}
+
+/* pipelined host path: next tick's row count, written straight into (mapped) pinned host memory -- a DMA copy for
+ * these few bytes would queue behind the bulk copies of the copy engines */
+__global__ void pve_total_kernel(const int32_t *__restrict__ gs, int G, volatile int64_t *total_host) {
+    int64_t t = 0;
+    for (int g = threadIdx.x; g < G; g += 32) t += gs[g];
+    for (int d = 16; d > 0; d >>= 1) t += __shfl_xor_sync(0xffffffffu, t, d);
+    if (threadIdx.x == 0) *total_host = t;
 }
 
 /* dual mode, after reset / set_state: classes and the big kernel's list from the headers */
@@ -548,6 +571,13 @@ void pve_destroy(pve_scene *s) {
 #ifndef PVE_HOST_EMULATION
     for (int i = 0; i < 3; ++i) if (s->ev[i]) cudaEventDestroy(s->ev[i]);
     if (s->side) cudaStreamDestroy(s->side);
+    if (s->a_ready) {
+        cudaStreamDestroy(s->s_in); cudaStreamDestroy(s->s_out); cudaStreamDestroy(s->s_cnt); cudaFreeHost(s->a_total);
+        for (int i = 0; i < PVE_ASYNC_SLOTS; ++i) {
+            cudaEventDestroy(s->a_in[i]); cudaEventDestroy(s->a_k[i]); cudaEventDestroy(s->a_cnt[i]); cudaEventDestroy(s->a_done[i]);
+            cudaFree(s->a_act[i]);
+        }
+    }
     if (s->ev_fork) cudaEventDestroy(s->ev_fork);
     if (s->ev_join) cudaEventDestroy(s->ev_join);
 #endif
@@ -825,6 +855,145 @@ int32_t pve_step_host(pve_scene *s, const float *actions_host, const pve_outputs
     for (int g = 0; g < s->n_groups; ++g) t += s->pinned_gs[g];
     s->next_total = t;
     return PVE_OK;
+}
+
+#ifndef PVE_HOST_EMULATION
+static int32_t async_setup(pve_scene *s) {
+    if (s->a_ready) return PVE_OK;
+    const size_t nv = (size_t)s->cfg.n_envs * s->cfg.veh_cap;
+    RT_CHECK(s, cudaStreamCreateWithFlags(&s->s_in, cudaStreamNonBlocking));
+    RT_CHECK(s, cudaStreamCreateWithFlags(&s->s_out, cudaStreamNonBlocking));
+    RT_CHECK(s, cudaStreamCreateWithFlags(&s->s_cnt, cudaStreamNonBlocking));
+    RT_CHECK(s, rt_host_alloc((void **)&s->a_total, sizeof(int64_t) * PVE_ASYNC_SLOTS));
+    for (int i = 0; i < PVE_ASYNC_SLOTS; ++i) {
+        RT_CHECK(s, cudaEventCreateWithFlags(&s->a_in[i], cudaEventDisableTiming));
+        RT_CHECK(s, cudaEventCreateWithFlags(&s->a_k[i], cudaEventDisableTiming));
+        RT_CHECK(s, cudaEventCreateWithFlags(&s->a_cnt[i], cudaEventDisableTiming));
+        RT_CHECK(s, cudaEventCreateWithFlags(&s->a_done[i], cudaEventDisableTiming));
+        RT_CHECK(s, rt_alloc((void **)&s->a_act[i], sizeof(float) * nv));
+    }
+    s->a_ready = 1;
+    return PVE_OK;
+}
+#endif
+
+#ifndef PVE_HOST_EMULATION
+/* copy-out of tick `seq` (enqueued one call late, when its row count has long arrived): DMA behind its kernel */
+static int32_t async_copy_out(pve_scene *s, int64_t seq) {
+    const int slot = (int)(seq % PVE_ASYNC_SLOTS);
+    const int B = s->cfg.n_envs;
+    int64_t A = s->a_rows[slot];
+    if (A < 0) {                               /* the sums the previous tick's kernel sent home */
+        const int prev = (int)((seq + PVE_ASYNC_SLOTS - 1) % PVE_ASYNC_SLOTS);
+        RT_CHECK(s, cudaEventSynchronize(s->a_cnt[prev]));
+        A = s->a_total[prev];
+        s->a_rows[slot] = A;
+    }
+    if (A > s->cfg.out_cap) {
+        snprintf(s->err, sizeof s->err, "tick emits %lld rows but out_cap is %lld", (long long)A, (long long)s->cfg.out_cap);
+        return PVE_ESTATE;
+    }
+    const size_t a = (size_t)A;
+    const pve_outputs *out_dev = &s->a_odev[slot], *out_host = &s->a_ohost[slot];
+    RT_CHECK(s, cudaStreamWaitEvent(s->s_out, s->a_k[slot], 0));
+#define D2HA(field, bytes) \
+    if (out_host->field && out_dev->field) RT_CHECK(s, cudaMemcpyAsync(out_host->field, out_dev->field, (bytes), cudaMemcpyDeviceToHost, s->s_out))
+    /* agent_offset[B+1] | env_collisions[B] | env_lock[B] | env_removed[B] in one allocation on both sides: one copy */
+    const bool small_contig = out_dev->env_collisions == out_dev->agent_offset + B + 1 && out_dev->env_lock == out_dev->env_collisions + B &&
+                              out_dev->env_removed == out_dev->env_lock + B && out_host->env_collisions == out_host->agent_offset + B + 1 &&
+                              out_host->env_lock == out_host->env_collisions + B && out_host->env_removed == out_host->env_lock + B;
+    if (small_contig) {
+        D2HA(agent_offset, sizeof(int32_t) * (4 * (size_t)B + 1));
+    } else {
+        D2HA(agent_offset, sizeof(int32_t) * ((size_t)B + 1));
+        D2HA(env_collisions, sizeof(int32_t) * (size_t)B);
+        D2HA(env_lock, sizeof(int32_t) * (size_t)B);
+        D2HA(env_removed, sizeof(int32_t) * (size_t)B);
+    }
+    D2HA(packed, sizeof(pve_agent_record) * a);
+    if (s->a_mask[slot] & 2) D2HA(obs, sizeof(float) * PVE_OBS_H * PVE_OBS_W * a);
+#undef D2HA
+    RT_CHECK(s, cudaEventRecord(s->a_done[slot], s->s_out));
+    s->a_copied = seq + 1;
+    return PVE_OK;
+}
+#endif
+
+int32_t pve_step_host_async(pve_scene *s, const float *actions_host, const pve_outputs *out_dev,
+                            const pve_outputs *out_host, int32_t copy_mask, void *stream_) {
+    if (!s || !actions_host || !out_dev || !out_host) return PVE_EINVAL;
+#ifdef PVE_HOST_EMULATION
+    (void)copy_mask; (void)stream_;
+    return PVE_ESTATE;                       /* device only */
+#else
+    pve_stream_t stream = (pve_stream_t)stream_;
+    if (!out_dev->packed || !out_host->packed || !out_dev->agent_offset || !out_host->agent_offset ||
+        ((copy_mask & 2) && (!out_dev->obs || !out_host->obs))) {
+        snprintf(s->err, sizeof s->err, "pve_step_host_async needs packed + agent_offset (and obs with bit1) in out_dev and out_host");
+        return PVE_EINVAL;
+    }
+    const int inflight = (int)(s->a_seq - s->a_waited);
+    if (inflight >= PVE_ASYNC_SLOTS) {
+        snprintf(s->err, sizeof s->err, "%d ticks are in flight: call pve_host_wait first", inflight);
+        return PVE_ESTATE;
+    }
+    int32_t rc = async_setup(s);
+    if (rc != PVE_OK) return rc;
+    const size_t nv = (size_t)s->cfg.n_envs * s->cfg.veh_cap;
+    const int slot = (int)(s->a_seq % PVE_ASYNC_SLOTS);
+    /* rows of this tick: unknown (-1) when the previous tick came through here -- its kernel sends the sums home and
+     * async_copy_out picks them up; otherwise the synchronous query */
+    int64_t A = -1;
+    if (inflight == 0 || s->next_total >= 0) {
+        A = pve_next_agent_total(s, stream_);
+        if (A < 0) return (int32_t)A;
+    }
+    /* actions: DMA on the copy-in stream, after the kernel that last read this buffer */
+    RT_CHECK(s, cudaStreamWaitEvent(s->s_in, s->a_k[slot], 0));
+    RT_CHECK(s, cudaMemcpyAsync(s->a_act[slot], actions_host, sizeof(float) * nv, cudaMemcpyHostToDevice, s->s_in));
+    RT_CHECK(s, cudaEventRecord(s->a_in[slot], s->s_in));
+    /* the kernel, after its actions have arrived and after the copy-out that last read these output buffers */
+    RT_CHECK(s, cudaStreamWaitEvent(stream, s->a_in[slot], 0));
+    RT_CHECK(s, cudaStreamWaitEvent(stream, s->a_done[slot], 0));
+    /* ... and after the count kernel of two ticks ago, whose input this kernel clears */
+    RT_CHECK(s, cudaStreamWaitEvent(stream, s->a_cnt[(slot + 1) % PVE_ASYNC_SLOTS], 0));
+    rc = launch_step(s, s->a_act[slot], *out_dev, stream);
+    if (rc != PVE_OK) return rc;
+    s->next_total = -1;
+    RT_CHECK(s, cudaEventRecord(s->a_k[slot], stream));
+    /* the NEXT tick's row count goes home behind the kernel, on its own stream */
+    RT_CHECK(s, cudaStreamWaitEvent(s->s_cnt, s->a_k[slot], 0));
+    pve_total_kernel<<<1, 32, 0, s->s_cnt>>>(s->st.gs_read, s->n_groups, s->a_total + slot);
+    RT_CHECK(s, cudaGetLastError());
+    RT_CHECK(s, cudaEventRecord(s->a_cnt[slot], s->s_cnt));
+    s->a_rows[slot] = A;
+    s->a_odev[slot] = *out_dev; s->a_ohost[slot] = *out_host; s->a_mask[slot] = copy_mask;
+    s->a_seq += 1;
+    /* the copy-out of the tick before this one: its row count arrived a whole tick ago, so nothing blocks here and
+     * the GPU already has this tick's kernel queued */
+    if (s->a_copied < s->a_seq - 1) {
+        rc = async_copy_out(s, s->a_seq - 2);
+        if (rc != PVE_OK) return rc;
+    }
+    return PVE_OK;
+#endif
+}
+
+int64_t pve_host_wait(pve_scene *s) {
+    if (!s) return PVE_EINVAL;
+#ifdef PVE_HOST_EMULATION
+    return PVE_ESTATE;
+#else
+    if (s->a_seq <= s->a_waited) { snprintf(s->err, sizeof s->err, "no tick in flight"); return PVE_ESTATE; }
+    while (s->a_copied <= s->a_waited) {                                      /* the newest tick: enqueue its copy-out now */
+        int32_t rc = async_copy_out(s, s->a_copied);
+        if (rc != PVE_OK) return rc;
+    }
+    const int slot = (int)(s->a_waited % PVE_ASYNC_SLOTS);                    /* the oldest one */
+    RT_CHECK(s, cudaEventSynchronize(s->a_done[slot]));
+    s->a_waited += 1;
+    return s->a_rows[slot];
+#endif
 }
 
 int32_t pve_set_state(pve_scene *s, const pve_state_view *in, void *stream_) {

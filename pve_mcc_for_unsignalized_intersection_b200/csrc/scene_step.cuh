@@ -1102,6 +1102,14 @@ PVE_DEV void pve_step_block(const PveParams &P, const PveState &S, const pve_out
                 if (O.cpv) O.cpv[obase + g] = cpv[g];
                 if (O.status) O.status[obase + g] = status[g];
                 if (O.jerk_sum) O.jerk_sum[obase + g] = (float)sjs[k];
+                if (O.packed) {                                                  /* pve_agent_record */
+                    const uint32_t c8 = cpv[g] > 255 ? 255u : (uint32_t)cpv[g];
+                    pve_v4 rec;
+                    rec.x = pve_fbits(rew[g]); rec.y = (uint32_t)suid[k];
+                    rec.z = (uint32_t)lane_of[k] | ((uint32_t)(k - lane_off[lane_of[k]]) << 8) | ((uint32_t)status[g] << 16) | (c8 << 24);
+                    rec.w = pve_fbits((float)sjs[k]);
+                    ((pve_v4 *)O.packed)[obase + g] = rec;
+                }
             }
             if (!((spk[k] >> 24) & PVE_F_CONTROL) || del[k]) continue;
             int t = g, len = 0;

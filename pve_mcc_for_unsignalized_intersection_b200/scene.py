@@ -24,18 +24,24 @@ class StepOutputs:
     reused by the next ``step`` call.
     """
 
-    def __init__(self, B, out_cap, device, neighbour_sources=False):
+    def __init__(self, B, out_cap, device, neighbour_sources=False, records_only=False):
         z = lambda *s, dt: torch.zeros(*s, dtype=dt, device=device)
-        self.agent_offset = z(B + 1, dt=torch.int32)
+        e = lambda *s, dt: None
+        per_agent = e if records_only else z                       # records_only: the 16-byte records replace them
+        # agent_offset and the three per-intersection counters share one allocation (one DMA on the host path)
+        self._small = z(4 * B + 1, dt=torch.int32)
+        self.agent_offset = self._small[:B + 1]
         self.obs = z(out_cap, OBS_H, OBS_W, dt=torch.float32)       # re_state
-        self.reward = z(out_cap, dt=torch.float32)
-        self.ids = z(out_cap, 4, dt=torch.int32)                   # env, lane, j, uid
-        self.cpv = z(out_cap, dt=torch.int32)                      # collisions_per_veh[:, 0]
-        self.status = z(out_cap, dt=torch.uint8)                   # ST_DONE | ST_REMOVED | ST_FINISHED
-        self.jerk_sum = z(out_cap, dt=torch.float32)
-        self.env_collisions = z(B, dt=torch.int32)                 # `collisions`
-        self.env_lock = z(B, dt=torch.int32)                       # `lock`
-        self.env_removed = z(B, dt=torch.int32)
+        self.reward = per_agent(out_cap, dt=torch.float32)
+        self.ids = per_agent(out_cap, 4, dt=torch.int32)           # env, lane, j, uid
+        self.cpv = per_agent(out_cap, dt=torch.int32)              # collisions_per_veh[:, 0]
+        self.status = per_agent(out_cap, dt=torch.uint8)           # ST_DONE | ST_REMOVED | ST_FINISHED
+        self.jerk_sum = per_agent(out_cap, dt=torch.float32)
+        self.env_collisions = self._small[B + 1:2 * B + 1]         # `collisions`
+        self.env_lock = self._small[2 * B + 1:3 * B + 1]           # `lock`
+        self.env_removed = self._small[3 * B + 1:4 * B + 1]
+        # pve_agent_record[out_cap]: reward, uid, lane, j, status, cpv, jerk_sum of a row in 16 bytes (the host path)
+        self.packed = z(out_cap, 4, dt=torch.int32) if records_only else None
         # optional: where each of the 7 observation rows was copied from (include/pve_mcc.h, pve_outputs.nbr_src):
         # -1 zero row; g' = row 0 of agent g' of the same intersection this tick; 0x4000 | k = last tick's row of slot k
         self.nbr_src = z(out_cap, 8, dt=torch.int16) if neighbour_sources else None
@@ -44,12 +50,33 @@ class StepOutputs:
     FIELDS = ("agent_offset", "obs", "reward", "ids", "cpv", "status", "jerk_sum",
               "env_collisions", "env_lock", "env_removed")
 
+    def pin(self):
+        """Move the (CPU) buffers to pinned memory, keeping agent_offset / env_* in one allocation."""
+        B = self.env_lock.shape[0]
+        self._small = self._small.pin_memory()
+        self.agent_offset = self._small[:B + 1]
+        self.env_collisions = self._small[B + 1:2 * B + 1]
+        self.env_lock = self._small[2 * B + 1:3 * B + 1]
+        self.env_removed = self._small[3 * B + 1:4 * B + 1]
+        for f in ("obs", "reward", "ids", "cpv", "status", "jerk_sum", "packed"):
+            if getattr(self, f) is not None:
+                setattr(self, f, getattr(self, f).pin_memory())
+        return self
+
     def native(self):
         o = N.PveOutputs()
         for f in self.FIELDS:
-            setattr(o, f, getattr(self, f).data_ptr())
+            t = getattr(self, f)
+            setattr(o, f, t.data_ptr() if t is not None else None)
         o.nbr_src = self.nbr_src.data_ptr() if self.nbr_src is not None else None
+        o.packed = self.packed.data_ptr() if self.packed is not None else None
         return o
+
+    def records(self, n=None):
+        """Host buffers only: the agent records as a numpy structured array (``_native.RECORD_DTYPE``: reward, uid,
+        lane, j, status, cpv, jerk_sum), a view of the pinned memory."""
+        n = self._n if n is None else n
+        return self.packed.numpy().view(N.RECORD_DTYPE).reshape(-1)[:n]
 
     @property
     def n_agents(self):
@@ -175,8 +202,7 @@ class BatchedScene:
         """Pinned host mirrors of the output arrays for ``step_host``."""
         host = StepOutputs(self.B, self.out_cap, "cpu")
         if pinned and self.device.type == "cuda":
-            for f in StepOutputs.FIELDS:
-                setattr(host, f, getattr(host, f).pin_memory())
+            host.pin()
         return host
 
     def step_host(self, actions_host, host_out, copy_obs=False):
@@ -195,6 +221,35 @@ class BatchedScene:
         host_out._n = n
         self.out._n = n
         return n
+
+    def make_async_buffers(self):
+        """Three (device, pinned host) output pairs for ``step_host_async``: consecutive ticks take them in turn."""
+        pairs = []
+        for _ in range(3):
+            dev = StepOutputs(self.B, self.out_cap, self.device, records_only=True)
+            host = StepOutputs(self.B, self.out_cap, "cpu", records_only=True).pin()
+            pairs.append((dev, host, dev.native(), host.native()))      # the ctypes views are built once
+        return pairs
+
+    def step_host_async(self, actions_host, pair, copy_obs=False):
+        """Enqueue one tick through host buffers without waiting (``pve_step_host_async``): actions by DMA from the
+        pinned ``actions_host``, agent records / offsets / per-intersection counters (and the observations with
+        ``copy_obs``) by DMA into ``pair[1]`` while later ticks already run.  At most three ticks may be in flight;
+        ``host_wait()`` returns the row count of the oldest one once its host buffers are complete."""
+        assert actions_host.dtype == torch.float32 and actions_host.is_contiguous() and actions_host.is_pinned()
+        assert actions_host.shape == (self.B, self.veh_cap)
+        dev, host, dev_native, host_native = pair
+        self._check(self.lib.pve_step_host_async(self._h, actions_host.data_ptr(), C.byref(dev_native),
+                                                 C.byref(host_native), 2 if copy_obs else 0, self._stream()))
+        self._async_q = getattr(self, "_async_q", []) + [host]
+
+    def host_wait(self):
+        n = int(self.lib.pve_host_wait(self._h))
+        if n < 0:
+            self._check(n)
+        host = self._async_q.pop(0)
+        host._n = n
+        return n, host
 
     def next_agent_total(self):
         return int(self.lib.pve_next_agent_total(self._h, self._stream()))
