@@ -294,7 +294,7 @@ def committed_traffic():
         return None, None
     try:
         val = json.load(open(caps[-1]))["derived"]["dram_traffic_bytes_per_launch"]
-        sha = subprocess.run(["git", "-C", ROOT, "log", "-n", "1", "--format=%h", "--", caps[-1]], stdout=subprocess.PIPE,
+        sha = subprocess.run(["git", "-C", ROOT, "log", "-n", "1", "--format=%h", "--", caps[-1]], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL,
                              text=True).stdout.strip() or None
         return val, {"source": os.path.relpath(caps[-1], ROOT), "commit": sha,
                      "note": "NOT measured in this run: value of a committed ncu capture of an earlier build"}

@@ -84,6 +84,7 @@ struct pve_scene {
     int64_t next_total;          /* rows of the next tick if known, else -1 */
     int profiling;               /* record events around the step and scan kernels */
     size_t smem_pad;             /* experiment knob (env PVE_SMEM_PAD): extra dynamic shared memory per CTA */
+    int exp_no_obs;
     int host_zerocopy;           /* pve_step_host reads/writes pinned host buffers in place (env PVE_HOST_ZEROCOPY=0: staged copies) */
 #ifndef PVE_HOST_EMULATION
     cudaEvent_t ev[3];
@@ -449,8 +450,10 @@ static cudaError_t launch_one(pve_scene *s, const float *actions, const pve_outp
 }
 #endif
 
-static int32_t launch_step(pve_scene *s, const float *actions, const pve_outputs &O, pve_stream_t stream) {
+static int32_t launch_step(pve_scene *s, const float *actions, const pve_outputs &O_in, pve_stream_t stream) {
     const int VCc = s->prm.VC, ACc = s->prm.AC;
+    pve_outputs O = O_in;
+    if (s->exp_no_obs) O.obs = nullptr;          /* experiment knob (env PVE_EXPERIMENT_NO_OBS): what the observation traffic costs */
 #ifndef PVE_HOST_EMULATION
     if (s->cfg.n_envs >= 1024) {                 /* small batches fit in one wave: order is irrelevant */
         if (s->order_age < 0 || s->order_age >= 32) {
@@ -614,6 +617,7 @@ int32_t pve_create(const pve_config *cfg, int32_t device, pve_scene **out) {
     if (const char *d = getenv("PVE_DUAL")) s->dual = s->dual && atoi(d) != 0;
 #endif
     if (const char *pad = getenv("PVE_SMEM_PAD")) s->smem_pad = (size_t)atoi(pad);
+    s->exp_no_obs = getenv("PVE_EXPERIMENT_NO_OBS") != nullptr;
     s->host_zerocopy = 1;
     if (const char *zc = getenv("PVE_HOST_ZEROCOPY")) s->host_zerocopy = atoi(zc);
     if (s->threads != 64 && s->threads != 96 && s->threads != 128 && s->threads != 256 && s->threads != 512) {

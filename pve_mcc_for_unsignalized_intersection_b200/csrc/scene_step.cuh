@@ -390,6 +390,7 @@ PVE_DEV void pve_warp0_sums(const float *x, const uint8_t *fin, const double *js
             s2 += __shfl_xor_sync(0xffffffffu, s2, d);
         }
         if (tid == 0) { out3[0] = s0; out3[1] = s1; out3[2] = s2; }
+        __syncwarp();                                    /* lanes of warp 0 read out3 next (phase K) */
     }
 #else
     double a0 = 0, a1 = 0, a2 = 0;
@@ -1253,13 +1254,15 @@ PVE_DEV void pve_step_block(const PveParams &P, const PveState &S, const pve_out
             }
         }
         if (tid >= 32 && tid < 32 + PVE_HDR_BYTES / 16) ((pve_v4 *)(S.hdr + b))[tid - 32] = ((const pve_v4 *)hdr)[tid - 32];
-        if (tid == 0) {
+        /* the scalar tail of the tick on two different warps: the last team thread publishes the counts, the class
+         * of the next tick and the per-intersection outputs; lanes 0-9 of warp 0 add one statistic each */
+        if (tid == NS - 1) {
             S.n_ctrl_next[b] = hdr->n_ctrl; S.n_veh[b] = hdr->n_veh;
             PVE_RED_ADD(&S.gs_acc[b >> PVE_GROUP_SHIFT], hdr->n_ctrl);         /* next tick's group sums */
             if ((b & ((1 << PVE_GROUP_SHIFT) - 1)) == 0) S.gs_zero[b >> PVE_GROUP_SHIFT] = 0;
             if (S.klass_next) {      /* next tick: vehicles stepped + arrivals already due must fit the small class */
                 int due = 0;
-#pragma unroll 1
+#pragma unroll
                 for (int i = 0; i < PVE_NLANE; ++i) due += (hdr->tick + 1 >= hdr->next_spawn[i]) ? 1 : 0;
                 const int big = (hdr->n_veh + due > S.small_vc || hdr->n_ctrl + due > S.small_ac) ? 1 : 0;
                 S.klass_next[b] = (uint8_t)big;
@@ -1273,18 +1276,16 @@ PVE_DEV void pve_step_block(const PveParams &P, const PveState &S, const pve_out
             if (O.env_collisions) O.env_collisions[b] = misc[M_COLL];
             if (O.env_lock) O.env_lock[b] = misc[M_LOCK];
             if (O.env_removed) O.env_removed[b] = misc[M_NREM];
-            /* per-intersection running statistics (end-of-rollout reduction, MAIN:407-415) */
-            double *st = S.stats + (size_t)b * PVE_NSTAT;
-            PVE_RED_ADD(&st[PVE_STAT_AGENT], (double)A);
-            PVE_RED_ADD(&st[PVE_STAT_VEH], (double)V);
-            PVE_RED_ADD(&st[PVE_STAT_COLL], (double)misc[M_COLLAG]);
-            PVE_RED_ADD(&st[PVE_STAT_LOCK], (double)misc[M_LOCK]);
-            PVE_RED_ADD(&st[PVE_STAT_JERK], dsum[2]);
-            PVE_RED_ADD(&st[PVE_STAT_RSUM], dsum[0]);
-            PVE_RED_ADD(&st[PVE_STAT_RSQ], dsum[1]);
-            PVE_RED_ADD(&st[PVE_STAT_REMOVED], (double)misc[M_NREM]);
-            PVE_RED_ADD(&st[PVE_STAT_STEPS], 1.0);
-            PVE_RED_ADD(&st[PVE_STAT_Q5U], (double)misc[M_Q5U]);
+        }
+        if (tid < PVE_NSTAT) {
+            /* per-intersection running statistics (end-of-rollout reduction, MAIN:407-415); dsum: pve_warp0_sums */
+            static_assert(PVE_STAT_AGENT == 0 && PVE_STAT_VEH == 1 && PVE_STAT_COLL == 2 && PVE_STAT_LOCK == 3 && PVE_STAT_JERK == 4 &&
+                          PVE_STAT_RSUM == 5 && PVE_STAT_RSQ == 6 && PVE_STAT_REMOVED == 7 && PVE_STAT_STEPS == 8 && PVE_STAT_Q5U == 9,
+                          "statistic order");
+            const int iv = tid == 0 ? A : tid == 1 ? V : tid == 2 ? misc[M_COLLAG] : tid == 3 ? misc[M_LOCK]
+                         : tid == 7 ? misc[M_NREM] : tid == 8 ? 1 : misc[M_Q5U];
+            const double val = tid == 4 ? dsum[2] : tid == 5 ? dsum[0] : tid == 6 ? dsum[1] : (double)iv;
+            PVE_RED_ADD(&S.stats[(size_t)b * PVE_NSTAT + tid], val);
         }
     PVE_END_TID_NOSYNC
 

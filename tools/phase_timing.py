@@ -25,8 +25,11 @@ lib = os.path.join(out_dir, "libpve_mcc_timing.so")
 subprocess.check_call([find_nvcc()] + NVCC_FLAGS + ["-DPVE_PHASE_TIMING", "-I", INCLUDE, "-I", CSRC,
                                                     os.path.join(CSRC, "pve_mcc.cu"), "-o", lib])
 threads = int(sys.argv[1]) if len(sys.argv) > 1 else 128
+veh_cap = int(sys.argv[2]) if len(sys.argv) > 2 else 128
+agent_cap = int(sys.argv[3]) if len(sys.argv) > 3 else 96
 B = 4096
-scene = BatchedScene(B, SceneConfig(vm=6), device="cuda:0", threads=threads, _library=lib)
+scene = BatchedScene(B, SceneConfig(vm=6, zero_uncontrolled_actions=True), veh_cap=veh_cap, agent_cap=agent_cap, device="cuda:0",
+                     threads=threads, _library=lib)
 scene.reset(synthetic_arrivals(B, 1000, 120.0, seed=1000), warmup=True)
 acts = [(torch.rand(B, scene.veh_cap, device="cuda") * 6 - 3).contiguous() for _ in range(8)]
 for t in range(420):
