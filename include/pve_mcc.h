@@ -200,6 +200,11 @@ const pve_veh_meta *pve_meta_dev(const pve_scene *s);
 const pve_env_header *pve_hdr_dev(const pve_scene *s);
 
 int32_t pve_stats(pve_scene *s, pve_counters *out_dev, void *stream);
+/* the same statistics PER INTERSECTION, as the step kernel accumulates them on the device: double [B][PVE_ENV_NSTAT] in
+ * the order agent_steps, vehicle_steps, collided_agent_steps (MAIN:569-571), lock_events (MAIN:568), passed_jerk_sum
+ * (MAIN:567), reward_sum, reward_sq_sum, removed, env_steps, q5_undefined.  Valid after the stream has drained. */
+#define PVE_ENV_NSTAT 10
+const double *pve_env_stats_dev(const pve_scene *s);
 
 /* measurement aids: CUDA events around the step kernel and the offset scan of the last pve_step
  * (pve_kernel_ms waits for them), launch geometry, struct size for binding checks */

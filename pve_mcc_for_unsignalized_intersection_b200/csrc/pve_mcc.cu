@@ -1042,6 +1042,8 @@ int32_t pve_get_state(pve_scene *s, const pve_state_view *out, void *stream_) {
 const float *pve_row0_dev(const pve_scene *s) { return s ? s->st.row0[s->phase] : nullptr; }
 const pve_veh_meta *pve_meta_dev(const pve_scene *s) { return s ? s->st.meta : nullptr; }
 const pve_env_header *pve_hdr_dev(const pve_scene *s) { return s ? s->st.hdr : nullptr; }
+const double *pve_env_stats_dev(const pve_scene *s) { return s ? s->st.stats : nullptr; }
+static_assert(PVE_ENV_NSTAT == PVE_NSTAT, "per-intersection statistics");
 int64_t pve_smem_bytes(const pve_scene *s) { return s ? (int64_t)s->smem_bytes : 0; }
 int32_t pve_threads(const pve_scene *s) { return s ? s->threads : 0; }
 int32_t pve_launch_info(const pve_scene *s, int32_t out[8]) {

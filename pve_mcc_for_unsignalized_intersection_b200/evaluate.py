@@ -59,24 +59,22 @@ def evaluate_tables(tables, weights, ticks=36000, vm=5, collision_thr=2, device=
     scene.reset(stack_tables(tables), warmup=True)
     dev = scene.device
     acts = torch.empty(B, scene.veh_cap, dtype=torch.float32, device=dev)
-    coll = torch.zeros(B, dtype=torch.int64, device=dev)
-    lock = torch.zeros(B, dtype=torch.int64, device=dev)
-    jerk = torch.zeros(B, dtype=torch.float64, device=dev)
-    zero_i = torch.zeros(1, dtype=torch.int64, device=dev)
-    zero_f = torch.zeros(1, dtype=torch.float64, device=dev)
+    # the tallies of main.py:567-571 (jerks of finished vehicles, lock events, agents with collision > 0) are kept per
+    # intersection by the step kernel itself (pve_env_stats_dev): the loop is two launches per tick and never
+    # synchronises; the sticky overflow counter is looked at every 2000 ticks so that a run that left the capacity class
+    # stops early
     for i in range(ticks):
         actor.act(scene, out=acts)                                   # main.py:557-565
-        out = scene.step(acts)                                       # main.py:566 (+ delete_vehicle, 575)
-        n = out.n_agents
-        off = out.agent_offset.long()
-        hit = torch.cat([zero_i, (out.cpv[:n] > 0).long().cumsum(0)])
-        coll += hit[off[1:]] - hit[off[:-1]]                         # main.py:569-571
-        fin = (out.status[:n] & N.ST_FINISHED) != 0
-        js = torch.cat([zero_f, (out.jerk_sum[:n].double() * fin).cumsum(0)])
-        jerk += js[off[1:]] - js[off[:-1]]                           # main.py:567 (jerks of finished vehicles)
-        lock += out.env_lock.long()                                  # main.py:568
+        scene.step(acts)                                             # main.py:566 (+ delete_vehicle, 575)
+        if i % 2000 == 1999 and scene.stats()["overflow"] != 0:
+            break
         if progress and i % 1000 == 0:
-            progress(i, scene, coll, lock)
+            progress(i, scene)
+    es = scene.env_stats().cpu().numpy()
+    names = list(scene.ENV_STAT_NAMES)
+    coll = es[:, names.index("collided_agent_steps")]
+    lock = es[:, names.index("lock_events")]
+    jerk = es[:, names.index("passed_jerk_sum")]
     st = scene.get_state()
     if int(st["overflow"].sum()) != 0:
         raise N.NativeError("capacity class %d/%d overflowed during the evaluation; rerun with larger caps"

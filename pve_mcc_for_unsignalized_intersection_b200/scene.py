@@ -322,6 +322,14 @@ class BatchedScene:
         self._check(self.lib.pve_stats(self._h, self._counters.data_ptr(), self._stream()))
         return self._counters
 
+    ENV_STAT_NAMES = ("agent_steps", "vehicle_steps", "collided_agent_steps", "lock_events", "passed_jerk_sum", "reward_sum",
+                      "reward_sq_sum", "removed", "env_steps", "q5_undefined")
+
+    def env_stats(self):
+        """The statistics per intersection (``pve_env_stats_dev``): float64 ``[B, 10]`` device view in the order of
+        ``ENV_STAT_NAMES``; accumulated by the step kernel, so an evaluation loop needs no per-tick tallies."""
+        return self._wrap(self.lib.pve_env_stats_dev(self._h), (self.B, len(self.ENV_STAT_NAMES)), torch.float64, "<f8")
+
     def stats(self):
         t = self.stats_tensor().cpu().numpy()
         return dict(zip(N.COUNTER_NAMES, t.tolist()))
