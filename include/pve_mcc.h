@@ -72,7 +72,15 @@ typedef struct pve_config {
      * what the reference driver does on the host (`else: action = 0`, MAIN:401-405), for callers that fill every
      * slot without reading the control flags back.  0: actions are used as given (step() semantics, TIS:1502) */
     int32_t zero_uncontrolled;
-    int32_t reserved0;
+    /* 0 or 12: the 12-lane intersection (everything above).  4: the single-lane-per-approach intersection of the
+     * reference's lane_num = 4 branch (TIS:51-83) -- SURVEY.md 8(f) row N3: lane_in / lane_len / remove_p above are then
+     * those of TIS:53-55 / 341-342, the vd_* and rot_* tables are unused and the n4_* constants below apply.  Lanes 4..11
+     * of every [..][12] array (spawn ticks, header) are unused.  Vehicles carry their `intention` in bits 5-6 of the
+     * flags byte of pve_veh_meta.packed; the 4th value of every observation quad is the ROUTE (direction[lane][intention]). */
+    int32_t lane_num;
+    double n4_T[3][7], n4_C[3][7];   /* get_virtual_distance (TIS:453-531): member iff p1 - T > 0, vd = |p1 - T| + C;
+                                      * first index = ego route % 3, second = position of the other route in lane2lane */
+    double n4_rw[3];                 /* get_state rewrite (TIS:1304-1316): (alpha' - alpha) 3 cw, alpha' 3 cw, alpha 3 cw */
 } pve_config;
 
 /* Per-intersection header as stored on the device (little endian, 144 bytes). */

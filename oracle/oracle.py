@@ -99,13 +99,14 @@ def empty_state(B, cap):
 
 
 def valid_rows(arrive):
-    """Rows usable per lane: the strictly ascending prefix (zero padding ends the table)."""
+    """Rows usable per lane: the positive, non-decreasing prefix (zero padding ends the table; equal consecutive times
+    are two arrivals, spawned on consecutive ticks as TIS:379 does)."""
     arr = np.asarray(arrive, dtype=np.float64)
     K = arr.shape[-2]
     if K == 0:
         return np.zeros(arr.shape[:-2] + (NLANE,), np.int32)
-    bad = np.zeros(arr.shape, dtype=bool)
-    bad[..., 1:, :] = arr[..., 1:, :] <= arr[..., :-1, :]
+    bad = arr <= 0
+    bad[..., 1:, :] |= arr[..., 1:, :] < arr[..., :-1, :]
     bad = np.logical_or.accumulate(bad, axis=-2)
     return (~bad).sum(axis=-2).astype(np.int32)
 

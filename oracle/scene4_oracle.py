@@ -68,12 +68,12 @@ class Scene4Oracle:
     def reset(self, arrive, warmup=True):
         """TIS:195-220.  ``arrive``: [K][4] seconds."""
         self.arr = [[float(x) for x in row] for row in arrive]
-        # rows usable per lane: the strictly ascending prefix (zero padding ends a table; the reference would go on
+        # rows usable per lane: the positive, non-decreasing prefix (zero padding ends a table; the reference would go on
         # spawning one vehicle per tick and then raise IndexError, SURVEY.md Q10)
         self.kvalid = []
         for i in range(NL):
             k = 0
-            while k < len(self.arr) and (k == 0 or self.arr[k][i] > self.arr[k - 1][i]):
+            while k < len(self.arr) and self.arr[k][i] > 0 and (k == 0 or self.arr[k][i] >= self.arr[k - 1][i]):
                 k += 1
             self.kvalid.append(k)
         self.time, self.tick = 0, 0                      # TIS:196 (an int that becomes a float on the first += 0.1)

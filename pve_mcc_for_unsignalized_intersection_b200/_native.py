@@ -134,9 +134,12 @@ def pack_state(st, B, cap):
     meta["uid"] = st["uid"]
     flags = st["flags"].astype(np.uint32) & 7
     lock_a = (st["lock_a"].astype(np.int32) + 1).astype(np.uint32) & 3
+    intention = (st["intention"].astype(np.uint32) & 3) if "intention" in st else np.uint32(0)      # lane_num = 4 only
     meta["packed"] = (np.minimum(st["step"], 0xFFFF).astype(np.uint32)
                       | (np.minimum(st["collision"], 255).astype(np.uint32) << 16)
-                      | ((flags | (lock_a << 3)) << 24))
+                      | ((flags | (lock_a << 3) | (intention << 5)) << 24))
+    if "intention_re" in st:
+        hdr["pad_"][:, 0] = np.asarray(st["intention_re"]) % 3
     out = {"hdr": hdr, "meta": meta,
            "row0": np.ascontiguousarray(st["row0"], dtype=np.float32)}
     for k in ("p", "v", "a", "jerk_sum"):
@@ -162,11 +165,13 @@ def unpack_state(dev, B, cap):
         "uid": meta["uid"].astype(np.int32),
         "seq_in_lane": np.full((B, cap), -1, np.int32),      # logging-only field, not kept on device
         "flags": (fl & 7).astype(np.uint8), "lock_a": (((fl >> 3) & 3).astype(np.int32) - 1).astype(np.int8),
+        "intention": ((fl >> 5) & 3).astype(np.uint8),            # lane_num = 4: TIS:387; 0 on the 12-lane path
+        "intention_re": hdr["pad_"][:, 0].astype(np.int32),       # lane_num = 4: intention_re % 3
         "row0": dev["row0"],
     }
     # zero the dead slots so that states compare equal
     live = np.arange(cap)[None, :] < st["n_veh"][:, None]
-    for k in ("p", "v", "a", "jerk_sum", "collision", "step", "uid", "flags", "lock_a"):
+    for k in ("p", "v", "a", "jerk_sum", "collision", "step", "uid", "flags", "lock_a", "intention"):
         st[k] = np.where(live, st[k], 0).astype(st[k].dtype)
     st["row0"] = np.where(live[:, :, None], st["row0"], 0).astype(np.float32)
     return st

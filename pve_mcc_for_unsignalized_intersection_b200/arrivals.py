@@ -30,13 +30,16 @@ def reference_clock(n_ticks, delta_t=0.1):
 def to_spawn_ticks(arrive_time, delta_t=0.1, max_tick=None):
     """Convert arrival seconds ``[..., K, 12]`` to int32 spawn ticks of the same shape.
 
-    A zero-padded tail (first entry of a lane that is not larger than its predecessor) and
-    everything after it maps to ``NEVER``.  The reference would instead spawn one vehicle per
-    tick from the padding and then raise ``IndexError`` at row ``K``; no shipped
-    run reaches that point, and "table exhausted = no more arrivals" is the defined behaviour here.
+    The zero-padded tail of a lane -- its first entry that is not positive, or smaller than its predecessor -- and
+    everything after it maps to ``NEVER``.  The reference would instead spawn one vehicle per tick from the padding and
+    then raise ``IndexError`` at row ``K``; no shipped run reaches that point, and "table exhausted = no
+    more arrivals" is the defined behaviour here.  Two EQUAL consecutive arrival times are valid arrivals: the reference
+    spawns them on consecutive ticks (one vehicle per lane and tick, TIS:379), and so does the device.
+
+    The last dimension is the number of lanes of the table: 12, or 4 for the 4-lane intersection (``lane_num=4``).
     """
     arr = np.asarray(arrive_time, dtype=np.float64)
-    assert arr.shape[-1] == NLANE, arr.shape
+    assert arr.shape[-1] in (NLANE, 4), arr.shape
     K = arr.shape[-2]
     if max_tick is None:
         finite_max = float(arr.max()) if arr.size else 0.0
@@ -47,11 +50,11 @@ def to_spawn_ticks(arrive_time, delta_t=0.1, max_tick=None):
     ticks = np.minimum(ticks, int(NEVER))
     ticks[ticks > max_tick] = int(NEVER)
     # padding: once a lane stops ascending, it never spawns again
+    bad = arr <= 0
     if K > 1:
-        bad = arr[..., 1:, :] <= arr[..., :-1, :]
-        bad = np.logical_or.accumulate(bad, axis=-2)
-        tail = ticks[..., 1:, :]
-        tail[bad] = int(NEVER)
+        bad[..., 1:, :] |= arr[..., 1:, :] < arr[..., :-1, :]
+    bad = np.logical_or.accumulate(bad, axis=-2)
+    ticks[bad] = int(NEVER)
     return ticks.astype(np.int32)
 
 

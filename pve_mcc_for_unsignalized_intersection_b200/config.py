@@ -34,7 +34,8 @@ class PveConfig(C.Structure):
         ("remove_p", C.c_double), ("lane_cw", C.c_double),
         ("vd_a1", (C.c_double * 4) * 2), ("vd_a2", (C.c_double * 4) * 2), ("vd_b", (C.c_double * 4) * 2),
         ("rot_cos", C.c_double * 4), ("rot_sin", C.c_double * 4),
-        ("zero_uncontrolled", C.c_int32), ("reserved0", C.c_int32),
+        ("zero_uncontrolled", C.c_int32), ("lane_num", C.c_int32),
+        ("n4_T", (C.c_double * 7) * 3), ("n4_C", (C.c_double * 7) * 3), ("n4_rw", C.c_double * 3),
     ]
 
 
@@ -62,25 +63,54 @@ class SceneConfig:
     zero_uncontrolled_actions: bool = False
 
     def __post_init__(self):
-        if self.lane_num != 12:
-            raise NotImplementedError("only the 12-lane intersection is implemented (lane_num=%r)" % self.lane_num)
+        if self.lane_num not in (12, 4):
+            raise NotImplementedError("lane_num must be 12 or 4 (lane_num=%r; the 8-lane branch draws intentions from an "
+                                      "unseeded RNG, TIS:382/390, and is not built)" % self.lane_num)
         if self.o_agent_num != 6:
             raise NotImplementedError("o_agent_num must be 6 (28-wide observation rows)")
 
     # ---- derived geometry -----------------------------------------------------------------
     def lane_len(self):
         cw = self.lane_cw
+        if self.lane_num == 4:
+            return [3.1415 / 2 * 3 * cw, 4 * cw, 3.1415 / 2 * cw]                 # TIS:53-55
         return [3.1415 / 2 * 7 * cw, 12 * cw, 3.1415 / 2 * cw]                    # TIS:149-151
 
     def lane_in(self):
+        if self.lane_num == 4:
+            return self.dis_ctl - 2 * self.lane_cw                               # TIS:53
         return self.dis_ctl - 6 * self.lane_cw                                   # TIS:149
+
+    def four_lane_tables(self):
+        """``lane_num=4``: ``get_virtual_distance`` (TIS:453-531) as ``(T, C)`` -- member iff ``p1 - T > 0``,
+        ``vd = abs(p1 - T) + C`` -- indexed ``[ego route % 3][position in lane2lane[ego route]]``, and the three
+        constants of the ``get_state`` rewrite (TIS:1304-1316); every expression keeps the reference's association."""
+        cw = self.lane_cw
+        alpha = math.atan((4 - math.sqrt(2)) / (4 + math.sqrt(2)))               # TIS:79
+        alpha_ = math.atan((4 + math.sqrt(2)) / (4 - math.sqrt(2)))              # TIS:80
+        beta = math.atan(2 / math.sqrt(5))                                       # TIS:81
+        beta_ = math.atan(math.sqrt(5) / 2)                                      # TIS:82
+        gama = math.atan(1 / 2 * math.sqrt(2))                                   # TIS:83
+        T = [[4 * cw - 3 * cw * math.cos(gama), (1.5 * 3.1415) * cw * (alpha_ / (0.5 * 3.1415)),      # TIS:456, 478
+              1.5 * 3.1415 * cw * beta / (0.5 * 3.1415), 1.5 * 3.1415 * cw * beta_ / (0.5 * 3.1415),  # TIS:468, 473
+              3 * cw * math.cos(gama), 0.0, 0.0],                                                   # TIS:483, 488, 493
+             [cw, 1.5 * 3.1415 * cw * gama / (0.5 * 3.1415),                                          # TIS:499, 504
+              1.5 * 3.1415 * cw * (0.5 * 3.1415 - gama) / (0.5 * 3.1415), 3 * cw, 0.0, 0.0, 0.0],     # TIS:509, 514
+             [0.0] * 7]
+        Cc = [[3 * cw * (0.5 * 3.1415 - gama), (1.5 * 3.1415) * cw * (alpha / (0.5 * 3.1415)),        # TIS:458, 480
+               1.5 * 3.1415 * cw * beta_ / (0.5 * 3.1415), 1.5 * 3.1415 * cw * beta / (0.5 * 3.1415),  # TIS:470, 475
+               1.5 * 3.1415 * cw * (gama / (0.5 * 3.1415)), 0.0, 0.0],                               # TIS:485
+              [3 * cw, 3 * cw * math.cos(gama), 4 * cw - 3 * cw * math.cos(gama), cw, 0.0, 0.0, 0.0],  # TIS:501-516
+              [0.0] * 7]
+        rw = [(alpha_ - alpha) * 3 * cw, alpha_ * 3 * cw, alpha * 3 * cw]         # TIS:1304, 1309, 1316
+        return T, Cc, rw
 
     def spawn_p(self, lane):
         m = lane % 3                                                             # TIS:393-394
         return sum([self.lane_in(), self.lane_len()[m]])                         # TIS:395
 
     def remove_p(self):
-        return -self.dis_ctl + int((self.lane_num + 1) / 2) * self.lane_cw       # TIS:341-342
+        return -self.dis_ctl + int((self.lane_num + 1) / 2) * self.lane_cw       # TIS:341-342 (lane_num 12: -135, 4: -145)
 
     def angles(self):
         cw = self.lane_cw
@@ -138,4 +168,12 @@ class SceneConfig:
         for k in range(4):
             c.rot_cos[k], c.rot_sin[k] = cs[k], sn[k]
         c.zero_uncontrolled = int(bool(self.zero_uncontrolled_actions))
+        c.lane_num = int(self.lane_num)
+        if self.lane_num == 4:
+            T, Cc, rw = self.four_lane_tables()
+            for r in range(3):
+                for k in range(7):
+                    c.n4_T[r][k], c.n4_C[r][k] = T[r][k], Cc[r][k]
+            for k in range(3):
+                c.n4_rw[k] = rw[k]
         return c

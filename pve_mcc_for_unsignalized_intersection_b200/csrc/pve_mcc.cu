@@ -19,6 +19,7 @@
 #include <new>
 
 #include "scene_step.cuh"
+#include "scene_step4.cuh"
 #include "actor_mma.cuh"
 #include "nstep.cuh"
 #include "critic_mma.cuh"
@@ -55,6 +56,10 @@ struct pve_scene {
     int n_groups;
     int32_t *n_ctrl_buf[2];      /* ping-pong with `phase` */
     int32_t *order;              /* busiest-first CTA order */
+    /* lane_num = 4 (row N3): its own kernel, one warp per intersection; dense output offsets from a scan kernel */
+    int lane_num;
+    Pve4Params prm4;
+    int64_t *off4;               /* [B + 1] */
     /* dual mode (default class, default CTA size): two concurrent kernels per tick, see PveState::klass */
     int dual;
     uint8_t *klass_buf[2];       /* ping-pong with `phase` */
@@ -196,6 +201,34 @@ __global__ void pve_classify_kernel(PveState S, int B) {
     const int big = (h->n_veh + due > S.small_vc || h->n_ctrl + due > S.small_ac) ? 1 : 0;
     S.klass_next[b] = (uint8_t)big;
     if (big) S.big_list_next[atomicAdd(S.big_cnt_next, 1)] = b;
+}
+
+/* ---- lane_num = 4 (scene_step4.cuh): one warp per intersection, PVE4_WARPS intersections per CTA ---------------- */
+#define PVE4_WARPS 4
+__global__ void __launch_bounds__(32 * PVE4_WARPS)
+pve4_step_kernel(const Pve4Params P, const PveState S, const pve_outputs O, const int32_t *spawn_tick, const float *actions,
+                 const int64_t *off4) {
+    extern __shared__ __align__(16) unsigned char pve_smem[];
+    const int b = (int)blockIdx.x * PVE4_WARPS + (int)(threadIdx.x >> 5);
+    if (b >= P.B) return;
+    Pve4Smem &M = ((Pve4Smem *)pve_smem)[threadIdx.x >> 5];
+    pve4_step_block(P, S, O, spawn_tick, actions, b, M, off4[b]);
+}
+
+/* exclusive prefix of the agent counts -> first output row of every intersection (one CTA; B is small on this path) */
+__global__ void __launch_bounds__(1024)
+pve4_offsets_kernel(const int32_t *__restrict__ n_ctrl, int64_t *__restrict__ off, int B) {
+    __shared__ int64_t part[1024];
+    const int tid = threadIdx.x, per = (B + 1023) / 1024;
+    const int lo = tid * per, hi = min(B, lo + per);
+    int64_t s = 0;
+    for (int b = lo; b < hi; ++b) s += n_ctrl[b];
+    part[tid] = s;
+    __syncthreads();
+    if (tid == 0) { int64_t run = 0; for (int t = 0; t < 1024; ++t) { const int64_t c = part[t]; part[t] = run; run += c; } off[B] = run; }
+    __syncthreads();
+    int64_t run = part[tid];
+    for (int b = lo; b < hi; ++b) { off[b] = run; run += n_ctrl[b]; }
 }
 
 /* order[i] = intersections sorted by their agent count, descending (counting sort, one CTA) */
@@ -450,9 +483,46 @@ static cudaError_t launch_one(pve_scene *s, const float *actions, const pve_outp
 }
 #endif
 
+/* lane_num = 4: offsets, the step, and the group sums that pve_next_agent_total reads */
+static int32_t launch_step4(pve_scene *s, const float *actions, const pve_outputs &O, pve_stream_t stream) {
+    const int B = s->cfg.n_envs;
+#ifndef PVE_HOST_EMULATION
+    static bool attr_set[16] = {false};
+    const size_t smem = sizeof(Pve4Smem) * PVE4_WARPS;
+    if (!attr_set[s->device & 15]) {
+        RT_CHECK(s, cudaFuncSetAttribute(pve4_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_set[s->device & 15] = true;
+    }
+    if (s->profiling) RT_CHECK(s, cudaEventRecord(s->ev[0], stream));
+    pve4_offsets_kernel<<<1, 1024, 0, stream>>>(s->st.n_ctrl, s->off4, B);
+    RT_CHECK(s, cudaGetLastError());
+    pve4_step_kernel<<<(B + PVE4_WARPS - 1) / PVE4_WARPS, 32 * PVE4_WARPS, smem, stream>>>(s->prm4, s->st, O, s->spawn_tick, actions, s->off4);
+    RT_CHECK(s, cudaGetLastError());
+    if (s->profiling) RT_CHECK(s, cudaEventRecord(s->ev[1], stream));
+    const int G = s->n_groups;
+    pve_gsum_kernel<<<(G + 127) / 128, 128, 0, stream>>>(s->st.n_ctrl, s->gsum, s->gsum + G, s->gsum + 2 * (size_t)G, B, G);
+    RT_CHECK(s, cudaGetLastError());
+#else
+    (void)stream;
+    int64_t run = 0;
+    for (int b = 0; b < B; ++b) { s->off4[b] = run; run += s->st.n_ctrl[b]; }
+    s->off4[B] = run;
+    Pve4Smem *M = new (std::nothrow) Pve4Smem;
+    if (!M) return PVE_ENOMEM;
+    for (int b = 0; b < B; ++b) {
+        memset(M, 0xA5, sizeof *M);           /* poison: catches reads of unwritten shared memory */
+        pve4_step_block(s->prm4, s->st, O, s->spawn_tick, actions, b, *M, s->off4[b]);
+    }
+    delete M;
+    emul_gsum(s->st.n_ctrl, s->gsum, s->gsum + s->n_groups, s->gsum + 2 * (size_t)s->n_groups, B, s->n_groups);
+#endif
+    return PVE_OK;
+}
+
 static int32_t launch_step(pve_scene *s, const float *actions, const pve_outputs &O_in, pve_stream_t stream) {
     const int VCc = s->prm.VC, ACc = s->prm.AC;
     pve_outputs O = O_in;
+    if (s->lane_num == 4) return launch_step4(s, actions, O, stream);
     if (s->exp_no_obs) O.obs = nullptr;          /* experiment knob (env PVE_EXPERIMENT_NO_OBS): what the observation traffic costs */
 #ifndef PVE_HOST_EMULATION
     if (s->cfg.n_envs >= 1024) {                 /* small batches fit in one wave: order is irrelevant */
@@ -567,7 +637,7 @@ void pve_destroy(pve_scene *s) {
     rt_free(s->st.hdr); rt_free(s->st.p); rt_free(s->st.v); rt_free(s->st.a); rt_free(s->st.js);
     rt_free(s->st.meta); rt_free(s->st.row0[0]); rt_free(s->st.row0[1]);
     rt_free(s->n_ctrl_buf[0]); rt_free(s->n_ctrl_buf[1]); rt_free(s->st.n_veh); rt_free(s->st.stats); rt_free(s->gsum); rt_free(s->order);
-    rt_free(s->actions_dev); rt_free(s->counters_dev);
+    rt_free(s->actions_dev); rt_free(s->counters_dev); rt_free(s->off4);
     rt_host_free(s->pinned_i32); rt_host_free(s->pinned_gs);
     rt_free(s->klass_buf[0]); rt_free(s->klass_buf[1]); rt_free(s->big_list_buf[0]); rt_free(s->big_list_buf[1]);
     rt_free(s->big_cnt3);
@@ -605,6 +675,12 @@ int32_t pve_create(const pve_config *cfg, int32_t device, pve_scene **out) {
                  B, cfg->veh_cap, cfg->agent_cap);
         return PVE_EINVAL;
     }
+    s->lane_num = (cfg->lane_num == 4) ? 4 : 12;
+    if (cfg->lane_num != 0 && cfg->lane_num != 12 && cfg->lane_num != 4) {
+        snprintf(s->err, sizeof s->err, "lane_num must be 12 or 4 (got %d)", cfg->lane_num);
+        return PVE_EINVAL;
+    }
+    if (s->lane_num == 4 && VC < PVE4_LC) { VC = 128; AC = AC < 96 ? 96 : AC; s->smem_bytes = sizeof(Pve4Smem); }
     s->cfg.veh_cap = VC;          /* rounded up to the capacity class; see pve_veh_cap() */
     s->cfg.agent_cap = AC;
     /* default CTA size: 128 threads for the small classes (V ~ 76 vehicles per intersection), 512 for the large ones
@@ -613,7 +689,7 @@ int32_t pve_create(const pve_config *cfg, int32_t device, pve_scene **out) {
     s->threads = cfg->threads == 0 ? (VC >= 384 ? 512 : 128) : cfg->threads;
 #ifndef PVE_HOST_EMULATION
     /* dual mode for the default class with the default CTA size (env PVE_DUAL=0 turns it off) */
-    s->dual = (cfg->threads == 0 && VC == 128) ? 1 : 0;
+    s->dual = (cfg->threads == 0 && VC == 128 && s->lane_num == 12) ? 1 : 0;
     if (const char *d = getenv("PVE_DUAL")) s->dual = s->dual && atoi(d) != 0;
 #endif
     if (const char *pad = getenv("PVE_SMEM_PAD")) s->smem_pad = (size_t)atoi(pad);
@@ -647,6 +723,29 @@ int32_t pve_create(const pve_config *cfg, int32_t device, pve_scene **out) {
             return PVE_EINVAL;
         }
     }
+    if (s->lane_num == 4) {
+        static const int8_t kDir4[PVE4_NL][3] = {{6, 7, 8}, {0, 1, 2}, {9, 10, 11}, {3, 4, 5}};                  /* TIS:73-78 */
+        static const int8_t kL2L4[PVE4_ND][7] = {                                                                /* TIS:58-71 */
+            {10, 6, 9, 3, 7, 4, 8}, {10, 6, 3, 4, 9, 5, -1}, {6, 10, -1, -1, -1, -1, -1},
+            {1, 9, 0, 6, 10, 7, 11}, {1, 9, 6, 7, 0, 8, -1}, {9, 1, -1, -1, -1, -1, -1},
+            {4, 0, 3, 9, 1, 10, 2}, {4, 0, 9, 10, 3, 11, -1}, {0, 4, -1, -1, -1, -1, -1},
+            {7, 3, 6, 0, 4, 1, 5}, {7, 3, 0, 1, 6, 2, -1}, {3, 7, -1, -1, -1, -1, -1}};
+        Pve4Params &Q = s->prm4;
+        memset(&Q, 0, sizeof Q);
+        Q.dt = cfg->dt; Q.dt2 = cfg->dt2; Q.vm = cfg->vm; Q.vM = cfg->vM; Q.am = cfg->am; Q.aM = cfg->aM; Q.v0 = cfg->v0;
+        Q.thr = cfg->collision_thr; Q.lane_in = cfg->lane_in; Q.remove_p = cfg->remove_p; Q.cw = cfg->lane_cw;
+        Q.abs_am = fabs(cfg->am); Q.two_abs_am = 2 * fabs(cfg->am); Q.aspan = (double)(cfg->aM - cfg->am);
+        for (int m = 0; m < 3; ++m) Q.L[m] = cfg->lane_len[m];
+        memcpy(Q.T, cfg->n4_T, sizeof Q.T); memcpy(Q.C, cfg->n4_C, sizeof Q.C);
+        Q.rw_k = cfg->n4_rw[0]; Q.rw_a = cfg->n4_rw[1]; Q.rw_b = cfg->n4_rw[2];
+        memcpy(Q.dir, kDir4, sizeof Q.dir);
+        memset(Q.l2l_pos, -1, sizeof Q.l2l_pos);
+        for (int d = 0; d < PVE4_ND; ++d) {
+            for (int k = 0; k < 7; ++k) if (kL2L4[d][k] >= 0) Q.l2l_pos[d][kL2L4[d][k]] = (int8_t)k;
+            Q.l2l_1[d] = kL2L4[d][1];
+        }
+        Q.B = B; Q.VC = VC; Q.K = 0; Q.zero_unctl = cfg->zero_uncontrolled ? 1 : 0; Q.out_cap = cfg->out_cap;
+    }
     P.B = B; P.VC = VC; P.AC = AC; P.K = 0; P.out_cap = cfg->out_cap;
     s->st.small_vc = 0; s->st.small_ac = 0;
     P.zero_unctl = cfg->zero_uncontrolled ? 1 : 0;
@@ -668,6 +767,7 @@ int32_t pve_create(const pve_config *cfg, int32_t device, pve_scene **out) {
     RT_CHECK(s, rt_alloc((void **)&s->st.n_veh, sizeof(int32_t) * (size_t)B));
     RT_CHECK(s, rt_alloc((void **)&s->st.stats, sizeof(double) * (size_t)B * PVE_NSTAT));
     RT_CHECK(s, rt_alloc((void **)&s->order, sizeof(int32_t) * (size_t)B));
+    if (s->lane_num == 4) RT_CHECK(s, rt_alloc((void **)&s->off4, sizeof(int64_t) * ((size_t)B + 1)));
     s->order_age = -1;
 #ifndef PVE_HOST_EMULATION
     if (s->dual) {
@@ -702,6 +802,7 @@ int32_t pve_reset(pve_scene *s, const int32_t *spawn_tick_dev, int32_t K, int32_
     const size_t nv = (size_t)B * s->cfg.veh_cap;
     s->spawn_tick = spawn_tick_dev;
     s->prm.K = spawn_tick_dev ? K : 0;
+    s->prm4.K = s->prm.K;
     s->phase = 0;
     s->rot = 0;
     s->order_age = -1;

@@ -509,7 +509,7 @@ PVE_DEV void pve_world_xy(const PveParams &P, double p, int lane, double *x, dou
  * TIS:293-320 reward of an agent: p, v, jerk/dt of the ego; vd0, v0 = virtual position and speed of its
  * nearest neighbour (has_nb false: none)
  * ------------------------------------------------------------------------------------------- */
-PVE_DEV float pve_reward(const PveParams &P, double p, double v, double jr, bool has_nb, double vd0, double v0) {
+PVE_DEV float pve_reward(double vm, double aspan, double p, double v, double jr, bool has_nb, double vd0, double v0) {
     /* The three transcendental terms are evaluated unconditionally on safe arguments and selected afterwards: in a
      * warp some agent needs each of them anyway, and without branches their dependent chains (division -> exp ->
      * division; log) overlap instead of running one after the other. */
@@ -528,7 +528,7 @@ PVE_DEV float pve_reward(const PveParams &P, double p, double v, double jr, bool
     double r_ = use_t ? term_t : 0.0;
     r_ -= jr * jr * (3.0 / 3600.0);                                              /* TIS:316 */
     r_ += use_d ? term_d : 0.0;
-    r_ += (v - P.vm) * (2.0 / P.aspan);                                          /* TIS:319 */
+    r_ += (v - vm) * (2.0 / aspan);                                              /* TIS:319 */
     return (float)fmin(20.0, fmax(-20.0, r_));                                   /* TIS:320 */
 }
 
@@ -981,7 +981,7 @@ PVE_DEV void pve_step_block(const PveParams &P, const PveState &S, const pve_out
             {
                 const bool has_nb = nb0 != 0xFFFF;
                 const double jr = (sa[k] - a_old) / P.dt;                        /* TIS:1522, 316 */
-                rew[g] = pve_reward(P, pe, sv[k], jr, has_nb, S_[x0], has_nb ? sv[nb0] : 0.0);
+                rew[g] = pve_reward(P.vm, P.aspan, pe, sv[k], jr, has_nb, S_[x0], has_nb ? sv[nb0] : 0.0);
             }
         }
         if (tid < PVE_OBS_W / 4) ((pve_v4 *)(row0 + (size_t)AC * PVE_OBS_W))[tid] = pve_pack4(0.f, 0.f, 0.f, 0.f);

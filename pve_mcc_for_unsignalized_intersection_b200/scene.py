@@ -182,6 +182,10 @@ class BatchedScene:
                 ticks = np.broadcast_to(ticks, (self.B,) + ticks.shape[1:])
         else:
             ticks = np.asarray(spawn_ticks, dtype=np.int32)
+        if self.cfg.lane_num == 4:
+            assert ticks.shape[2] == 4, "lane_num=4 takes arrival tables with 4 columns, got %r" % (ticks.shape,)
+            never = np.full(ticks.shape[:2] + (NLANE - 4,), 2**31 - 1, dtype=np.int32)      # lanes 4..11 do not exist
+            ticks = np.concatenate([ticks, never], axis=2)
         assert ticks.shape[0] == self.B and ticks.shape[2] == NLANE, ticks.shape
         assert ticks.shape[1] < 65536, "arrival tables are limited to 65535 rows per lane"
         self._spawn = torch.from_numpy(np.ascontiguousarray(ticks)).to(self.device)
