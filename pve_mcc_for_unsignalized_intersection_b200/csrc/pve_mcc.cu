@@ -711,6 +711,9 @@ int32_t pve_create(const pve_config *cfg, int32_t device, pve_scene **out) {
     memcpy(P.vd_a1, cfg->vd_a1, sizeof P.vd_a1); memcpy(P.vd_a2, cfg->vd_a2, sizeof P.vd_a2);
     memcpy(P.vd_b, cfg->vd_b, sizeof P.vd_b);
     memcpy(P.rot_cos, cfg->rot_cos, sizeof P.rot_cos); memcpy(P.rot_sin, cfg->rot_sin, sizeof P.rot_sin);
+    P.f_cw = (float)P.lane_cw; P.f_thr = (float)P.thr;
+    for (int m = 0; m < 3; ++m) { P.f_len[m] = (float)P.lane_len[m]; P.f_rq[m] = (float)(3.141593 / 2 / P.lane_len[m]); }   /* TIS:1259 */
+    for (int k = 0; k < 4; ++k) { P.f_rc[k] = (float)P.rot_cos[k]; P.f_rs[k] = (float)P.rot_sin[k]; }
     memcpy(P.l2l, kLane2Lane, sizeof P.l2l);
     memset(P.rev_dir, -1, sizeof P.rev_dir);
     for (int L = 0; L < PVE_NLANE; ++L) {

@@ -84,6 +84,8 @@ struct PveParams {
     double spawn_p[3];
     double vd_a1[2][4], vd_a2[2][4], vd_b[2][4];
     double rot_cos[4], rot_sin[4];
+    float f_cw, f_thr, f_len[3], f_rq[3];   /* float copies for the collision pre-screen; f_rq[m] = 3.141593 / 2 / lane_len[m] */
+    float f_rc[4], f_rs[4];
     int8_t l2l[PVE_NLANE][4];      /* lane2lane, TIS:153-166 */
     int8_t rev_dir[PVE_NLANE][4];  /* directions d whose lane2lane[d] contains this lane ... */
     int8_t rev_k[PVE_NLANE][4];    /* ... and its position k there */
@@ -432,7 +434,7 @@ PVE_DEV void pve_move_rows(const PveRowJob &J, int first_warp) {
      * bank groups, no conflicts whatever rows the four quarters hold -- and a warp stores 448 contiguous
      * bytes.  The row's gather code is read once per row (a broadcast); the source is read from shared
      * memory unless the code says "last tick's buffer", in which case a predicated global load overrides
-     * it.  Four rows are in flight per lane. */
+     * it. */
     const int t = (int)threadIdx.x - first_warp * 32;
     const int piece = t & 7;
     if (piece == 7) return;
@@ -443,24 +445,36 @@ PVE_DEV void pve_move_rows(const PveRowJob &J, int first_warp) {
     int row = t >> 3;
     pve_v4 *PVE_RESTRICT dst = J.oblk + piece + row * 7;
     const uint16_t *sc = J.srcc + row;
-    for (; row + 3 * RSTEP < n_rows; row += 4 * RSTEP, dst += 4 * RSTEP * 7, sc += 4 * RSTEP) {      /* four full steps */
-        pve_v4 val[4];
+    /* PVE_MOVER_DEPTH rows in flight per lane: about half of the rows come from last tick's buffer (an L2 hit), and the
+     * loop pays one such round trip per iteration whatever the depth */
+#ifndef PVE_MOVER_DEPTH
+#define PVE_MOVER_DEPTH 8
+#endif
+    constexpr int D = PVE_MOVER_DEPTH;
+    const uint32_t rows_sa = (uint32_t)__cvta_generic_to_shared(rows);
+#pragma unroll 1
+    for (; row < n_rows; row += D * RSTEP, dst += D * RSTEP * 7, sc += D * RSTEP) {
+        pve_v4 val[D];
+        /* predicated loads written out: left to the compiler, "row in range ? (last tick's buffer ? global : shared)"
+         * becomes divergent branches around every load, and the quarters of a warp (different rows) take them apart */
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            const uint32_t code = sc[u * RSTEP];
+        for (int u = 0; u < D; ++u) {
+            const bool ok = row + u * RSTEP < n_rows;
+            const uint32_t code = ok ? (uint32_t)sc[u * RSTEP] : 0u;
             const uint32_t src = code & 0x7FFFu;
-            if (code & PVE_SRC_PREV) val[u] = prev[src]; else val[u] = rows[src];
+            const uint32_t sel = ok ? (code >> 15) : 2u;              /* 0: shared, 1: global, 2: no row */
+            asm volatile("{\n\t.reg .pred pg, ps;\n\t"
+                         "setp.eq.u32 pg, %6, 1;\n\t"
+                         "setp.eq.u32 ps, %6, 0;\n\t"
+                         "@pg ld.global.v4.u32 {%0, %1, %2, %3}, [%4];\n\t"
+                         "@ps ld.shared.v4.u32 {%0, %1, %2, %3}, [%5];\n\t}"
+                         : "=r"(val[u].x), "=r"(val[u].y), "=r"(val[u].z), "=r"(val[u].w)
+                         : "l"(prev + src), "r"(rows_sa + src * 16u), "r"(sel));
         }
 #pragma unroll
-        for (int u = 0; u < 4; ++u) dst[u * RSTEP * 7] = val[u];
+        for (int u = 0; u < D; ++u)
+            if (row + u * RSTEP < n_rows) dst[u * RSTEP * 7] = val[u];
     }
-#pragma unroll
-    for (int u = 0; u < 3; ++u)                                                                     /* the tail */
-        if (row + u * RSTEP < n_rows) {
-            const uint32_t code = sc[u * RSTEP];
-            const uint32_t src = code & 0x7FFFu;
-            dst[u * RSTEP * 7] = (code & PVE_SRC_PREV) ? prev[src] : rows[src];
-        }
 #else
     (void)first_warp;
     for (int it = 0; it < J.A * PVE_OBS_H; ++it) {
@@ -503,6 +517,52 @@ PVE_DEV void pve_world_xy(const PveParams &P, double p, int lane, double *x, dou
     const double c = P.rot_cos[lane / 3], s = P.rot_sin[lane / 3];              /* TIS:1251 */
     *x = tx * c - ty * s;                                                       /* TIS:1287 */
     *y = ty * c + tx * s;                                                       /* TIS:1288 */
+}
+
+/* The same in float32 (sin / cos by the special-function unit): a pre-screen for the collision test.  The error of a
+ * coordinate is below 1e-4 m (|coordinates| < 200 m, |sin| error 5e-7 on a radius of 26 m; the two sides of every
+ * branch of get_p meet continuously, so a branch taken differently in float32 costs no more than that); phase G3
+ * repeats the test in float64 (pve_world_xy) whenever the float32 distance is within PVE_XY_MARGIN of the threshold,
+ * so every decision is the float64 one. */
+#define PVE_XY_MARGIN 0.02f
+PVE_DEV void pve_world_xy_f32(const PveParams &P, double p, int lane, float *x, float *y) {
+    const float cw = P.f_cw, pf = (float)p;
+    const int m = lane % 3;
+    float tx, ty;
+    if (m == 1) {
+        tx = pf - 6 * cw; ty = 3 * cw;
+    } else {
+        const float L = P.f_len[m];
+        if (pf > L) {
+            tx = pf - L + 6 * cw; ty = (m == 0) ? cw : 5 * cw;
+        } else if (pf > 0) {
+            const float r_a = (L - pf) * P.f_rq[m];
+            float sn, cs;
+#ifdef __CUDACC__
+            __sincosf(r_a, &sn, &cs);
+#else
+            sn = sinf(r_a); cs = cosf(r_a);
+#endif
+            if (m == 0) { tx = 6 * cw - (7 * cw) * sn; ty = -6 * cw + (7 * cw) * cs; }
+            else        { tx = 6 * cw - cw * sn;       ty = 6 * cw - cw * cs; }
+        } else if (m == 0) {
+            tx = -cw; ty = -6 * cw + pf;
+        } else {
+            tx = 5 * cw; ty = 6 * cw - pf;
+        }
+    }
+    const float c = P.f_rc[lane / 3], s = P.f_rs[lane / 3];
+    *x = tx * c - ty * s;
+    *y = ty * c + tx * s;
+}
+/* the exact test of phase G3 for the rare pair the pre-screen cannot decide (a rolled loop: one copy of the float64
+ * geometry in the instruction stream, in a branch that is almost never fetched) */
+PVE_DEV bool pve_collide_exact(const PveParams &P, double p0, int lane0, double p1, int lane1) {
+    double x[2], y[2];
+#pragma unroll 1
+    for (int w = 0; w < 2; ++w) pve_world_xy(P, w ? p1 : p0, w ? lane1 : lane0, &x[w], &y[w]);
+    const double dx = x[1] - x[0], dy = y[1] - y[0];
+    return sqrt(dx * dx + dy * dy) < P.thr;                                      /* TIS:322-334 */
 }
 
 /* ---------------------------------------------------------------------------------------------
@@ -555,7 +615,8 @@ PVE_DEV void pve_step_block(const PveParams &P, const PveState &S, const pve_out
     double *const epos = (double *)(smem + L::EPOS), *const spos = (double *)(smem + L::SPOS);
     uint16_t *const eidx = (uint16_t *)(smem + L::EIDX), *const sidx = (uint16_t *)(smem + L::SIDX);
     float *const row0 = (float *)(smem + L::ROW0);
-    double *const xy = (double *)(smem + L::XY);
+    float *const xyf = (float *)(smem + L::XY);              /* float2[AC], phases G1-G3 */
+    double *const vdis = (double *)(smem + L::XY), *const rsort = vdis + AC;   /* phases H-J: vir_dis of every agent, sorted ring distances */
     double *const dsum = (double *)(smem + L::DSUM);
     float *const rew = (float *)(smem + L::REW);
     int32_t *const suid = (int32_t *)(smem + L::SUID);
@@ -990,7 +1051,7 @@ PVE_DEV void pve_step_block(const PveParams &P, const PveState &S, const pve_out
 #pragma unroll 1
             for (int g = tid - NS; g < A; g += NT - NS) {
                 const int k = vidx[g];
-                pve_world_xy(P, sp[k], lane_of[k], &xy[2 * g], &xy[2 * g + 1]);
+                pve_world_xy_f32(P, sp[k], lane_of[k], &xyf[2 * g], &xyf[2 * g + 1]);
             }
     PVE_END_TID
 
@@ -1015,7 +1076,7 @@ PVE_DEV void pve_step_block(const PveParams &P, const PveState &S, const pve_out
 #pragma unroll 1
         for (int g = tid; g < A; g += NS) {
             const int k = vidx[g];
-            pve_world_xy(P, sp[k], lane_of[k], &xy[2 * g], &xy[2 * g + 1]);
+            pve_world_xy_f32(P, sp[k], lane_of[k], &xyf[2 * g], &xyf[2 * g + 1]);
         }
     PVE_END_TEAM
     }
@@ -1027,8 +1088,14 @@ PVE_DEV void pve_step_block(const PveParams &P, const PveState &S, const pve_out
             const int k0 = nn0[g];
             if (k0 != 0xFFFF) {
                 const int g0 = acnt[k0];
-                const double dx = xy[2 * g0] - xy[2 * g], dy = xy[2 * g0 + 1] - xy[2 * g + 1];
-                if (sqrt(dx * dx + dy * dy) < P.thr) {
+                const float dx = xyf[2 * g0] - xyf[2 * g], dy = xyf[2 * g0 + 1] - xyf[2 * g + 1];
+                const float dist = sqrtf(dx * dx + dy * dy);
+                bool coll = dist < P.f_thr;
+                if (fabsf(dist - P.f_thr) < PVE_XY_MARGIN) {                     /* too close to call in float32 */
+                    const int k = vidx[g];
+                    coll = pve_collide_exact(P, sp[k], lane_of[k], sp[k0], lane_of[k0]);
+                }
+                if (coll) {
                     hit[g] = 1;
                     PVE_ATOMIC_ADD(&inct[g0], 1);                                /* TIS:334 */
                     if (g < g0) PVE_ATOMIC_ADD(&incb[g0], 1);                    /* Q4 */
@@ -1049,6 +1116,7 @@ PVE_DEV void pve_step_block(const PveParams &P, const PveState &S, const pve_out
             uint32_t fl = pk >> 24;
             const double p = sp[k];
             if (g >= 0) {
+                vdis[g] = pve_vir_dis(spos, arank, g);                           /* TIS:1349-1354; read by the ring members in phase I */
                 cpv[g] = rep;                                                    /* TIS:337-339 */
                 if (rep > 0) { PVE_ATOMIC_ADD(&misc[M_COLL], rep); PVE_ATOMIC_ADD(&misc[M_COLLAG], 1); }
             }
@@ -1112,6 +1180,7 @@ PVE_DEV void pve_step_block(const PveParams &P, const PveState &S, const pve_out
                     ((pve_v4 *)O.packed)[obase + g] = rec;
                 }
             }
+            inct[g] = 0;                                                         /* from here on: ring length, set for the ring's reporter */
             if (!((spk[k] >> 24) & PVE_F_CONTROL) || del[k]) continue;
             int t = g, len = 0;
 #pragma unroll 1
@@ -1121,43 +1190,49 @@ PVE_DEV void pve_step_block(const PveParams &P, const PveState &S, const pve_out
             }
             if (len == 0) continue;
             slock[k] = 1;                                                        /* TIS:1482 */
-            int mn = g;
+            /* record_.sort() (TIS:1492) orders the ring's [vir_dis, follower, header] records; follower ids are
+             * unique, so (vir_dis, follower agent index) is the whole key.  Every member of the ring walks it once and
+             * finds its own rank and the ring's first member in (lane, j) order, mn (the reporter: TIS:365-370 calls
+             * check_lock for it first); then it deposits its vir_dis where the reporter, walking the ring from itself,
+             * meets the values in sorted order: at the member `rank` hops after mn. */
+            const double dg = vdis[g];
+            int mn = g, hmn = 0, rank = 0;
             t = g;
 #pragma unroll 1
-            for (int hop = 0; hop < len; ++hop) { t = hdra[t]; mn = t < mn ? t : mn; }
-            if (mn != g) continue;          /* the first member in (lane, j) order reports the ring */
-            PVE_ATOMIC_ADD(&misc[M_LOCK], 1);
-            /* record_.sort() (TIS:1492) orders the ring's [vir_dis, follower, header] records; follower
-             * ids are unique, so (vir_dis, follower agent index) is the whole key.  Walk the ring once
-             * per output position instead of materialising the list. */
-            double last_d = -1.0e300, sum = 0, first_d = 0;
-            int last_o = -1, first_o = -1;
-#pragma unroll 1
-            for (int x = 0; x < len; ++x) {
-                double best_d = 1.0e300;
-                int best_o = 0x7FFFFFFF;
-                t = g;
-#pragma unroll 1
-                for (int hop = 0; hop < len; ++hop) {
-                    const double dd = pve_vir_dis(spos, arank, t);
-                    const bool after = dd > last_d || (dd == last_d && t > last_o);
-                    const bool better = dd < best_d || (dd == best_d && t < best_o);
-                    if (after && better) { best_d = dd; best_o = t; }
-                    t = hdra[t];
-                }
-                sum = sum + best_d;                                              /* TIS:1495 sum(dis) */
-                if (x == 0) { first_d = best_d; first_o = best_o; }
-                last_d = best_d; last_o = best_o;
+            for (int hop = 1; hop < len; ++hop) {
+                t = hdra[t];
+                const double dd = vdis[t];
+                rank += (dd < dg || (dd == dg && t < g)) ? 1 : 0;
+                if (t < mn) { mn = t; hmn = hop; }
             }
-            if (first_d < P.thr || sum / (double)len < P.thr + 3) {              /* TIS:1495 */
-                slocka[vidx[first_o]] = 1;                                       /* TIS:1496 */
-                slocka[vidx[hdra[first_o]]] = -1;                                /* TIS:1497 */
-            }
+            int tgt = hmn + rank;
+            tgt = tgt >= len ? tgt - len : tgt;
+            t = g;
+#pragma unroll 1
+            for (int hop = 0; hop < tgt; ++hop) t = hdra[t];
+            rsort[t] = dg;
+            if (rank == 0) nn0[mn] = (uint16_t)g;                                /* record_[0]'s follower */
+            if (mn == g) { inct[g] = len; PVE_ATOMIC_ADD(&misc[M_LOCK], 1); }
         }
     PVE_END_TEAM
 
     /* ---- J: arrivals (TIS:378-433) and header, one lane of warp 0 per traffic lane -------------- */
     PVE_FOR_TEAM(tid)
+        /* the reporter of every ring: sum(dis) over the sorted records and the unlock rule, TIS:1495-1497 */
+#pragma unroll 1
+        for (int g = tid; g < A; g += NS) {
+            const int len = inct[g];
+            if (len == 0) continue;
+            double sum = 0;
+            int t = g;
+#pragma unroll 1
+            for (int hop = 0; hop < len; ++hop) { sum = sum + rsort[t]; t = hdra[t]; }
+            if (rsort[g] < P.thr || sum / (double)len < P.thr + 3) {             /* TIS:1495 */
+                const int first_o = nn0[g];
+                slocka[vidx[first_o]] = 1;                                       /* TIS:1496 */
+                slocka[vidx[hdra[first_o]]] = -1;                                /* TIS:1497 */
+            }
+        }
         if (tid < 32) {
             const int i = tid < PVE_NLANE ? tid : 0;
             const int tick = hdr->tick + 1;                                      /* TIS:223 */
