@@ -61,7 +61,7 @@ struct pve_scene {
     Pve4Params prm4;
     int64_t *off4;               /* [B + 1] */
     /* dual mode (default class, default CTA size): two concurrent kernels per tick, see PveState::klass */
-    int dual;
+    int dual, dual_pdl;
     uint8_t *klass_buf[2];       /* ping-pong with `phase` */
     int32_t *big_list_buf[2];
     int32_t *big_cnt3;           /* [3], rotates with `rot` */
@@ -167,6 +167,9 @@ pve_step_kernel(const PveParams P, const PveState S, const pve_outputs O, const 
     /* dual mode: intersections of the big kernel are skipped (pve_step_block tests klass[b] after it has issued its
      * first loads, so the test costs no extra memory round trip) */
     pve_step_block<NT, VC, AC, SRC>(P, S, O, spawn_tick, actions, phase, b, pve_smem, S.klass);
+    /* dual mode launches this grid as the programmatic dependent of the big kernel (same stream, started while the
+     * big kernel runs): it may not complete before that one has (no-op for an ordinary launch) */
+    asm volatile("griddepcontrol.wait;" ::: "memory");
 }
 
 /* dual mode: the intersections that do not fit the small class, a few per tick */
@@ -175,6 +178,7 @@ __global__ void __launch_bounds__(NT, PveResident<VC, AC>::blocks(NT))
 pve_step_big_kernel(const PveParams P, const PveState S, const pve_outputs O, const int32_t *spawn_tick,
                     const float *actions, const int phase) {
     extern __shared__ __align__(16) unsigned char pve_smem[];
+    asm volatile("griddepcontrol.launch_dependents;");      /* the small kernel shares nothing with this one: start it now */
     const int n = *S.big_cnt;
     for (int i = (int)blockIdx.x; i < n; i += (int)gridDim.x) {
         pve_step_block<NT, VC, AC, SRC>(P, S, O, spawn_tick, actions, phase, S.big_list[i], pve_smem, nullptr);
@@ -446,9 +450,13 @@ static cudaError_t launch_variant(pve_scene *s, const float *actions, const pve_
 }
 /* dual mode: the small kernel (96 threads, class PVE_SMALL_VC / PVE_SMALL_AC: more intersections resident per SM) on
  * the caller's stream and, concurrently on the side stream, the big kernel for the intersections that do not fit */
+#ifndef PVE_SMALL_VC
 #define PVE_SMALL_VC 96
 #define PVE_SMALL_AC 64
+#endif
+#ifndef PVE_SMALL_NT
 #define PVE_SMALL_NT 96
+#endif
 template <int VC, int AC, bool SRC>
 static cudaError_t launch_dual(pve_scene *s, const float *actions, const pve_outputs &O, pve_stream_t stream) {
     static bool attr_set[16] = {false};
@@ -463,9 +471,28 @@ static cudaError_t launch_dual(pve_scene *s, const float *actions, const pve_out
         if (e != cudaSuccess) return e;
         attr_set[dev] = true;
     }
+    const int big_grid = s->cfg.n_envs < 148 ? s->cfg.n_envs : 148;
+    if (s->dual_pdl) {
+        /* Experiment (env PVE_DUAL_PDL=1), measured slower than the fork / join over the side stream (0.0816 vs 0.0774 ms
+         * per tick): one stream, no events: the big kernel first, the small kernel as its programmatic dependent -- it
+         * starts when every CTA of the big kernel has executed griddepcontrol.launch_dependents and waits for the big
+         * kernel's completion only at its own end (griddepcontrol.wait), so the stream's next kernel is ordered after
+         * both. */
+        pve_step_big_kernel<128, VC, AC, SRC><<<big_grid, 128, smem_big, stream>>>(s->prm, s->st, O, s->spawn_tick, actions, s->phase);
+        if ((e = cudaGetLastError()) != cudaSuccess) return e;
+        cudaLaunchConfig_t cfg;
+        memset(&cfg, 0, sizeof cfg);
+        cfg.gridDim = dim3((unsigned)s->cfg.n_envs); cfg.blockDim = dim3(PVE_SMALL_NT);
+        cfg.dynamicSmemBytes = smem_small + s->smem_pad; cfg.stream = stream;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        at[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = at; cfg.numAttrs = 1;
+        const int32_t *sp_arg = s->spawn_tick;
+        return cudaLaunchKernelEx(&cfg, pve_step_kernel<PVE_SMALL_NT, PVE_SMALL_VC, PVE_SMALL_AC, SRC>, s->prm, s->st, O, sp_arg, actions, (int)s->phase);
+    }
     if ((e = cudaEventRecord(s->ev_fork, stream)) != cudaSuccess) return e;
     if ((e = cudaStreamWaitEvent(s->side, s->ev_fork, 0)) != cudaSuccess) return e;
-    const int big_grid = s->cfg.n_envs < 148 ? s->cfg.n_envs : 148;
     pve_step_big_kernel<128, VC, AC, SRC><<<big_grid, 128, smem_big, s->side>>>(s->prm, s->st, O, s->spawn_tick, actions, s->phase);
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
     if ((e = cudaEventRecord(s->ev_join, s->side)) != cudaSuccess) return e;
@@ -691,6 +718,8 @@ int32_t pve_create(const pve_config *cfg, int32_t device, pve_scene **out) {
     /* dual mode for the default class with the default CTA size (env PVE_DUAL=0 turns it off) */
     s->dual = (cfg->threads == 0 && VC == 128 && s->lane_num == 12) ? 1 : 0;
     if (const char *d = getenv("PVE_DUAL")) s->dual = s->dual && atoi(d) != 0;
+    s->dual_pdl = 0;      /* experiment knob: 1 = one stream, the small kernel as the big kernel's programmatic dependent */
+    if (const char *d = getenv("PVE_DUAL_PDL")) s->dual_pdl = atoi(d) != 0;
 #endif
     if (const char *pad = getenv("PVE_SMEM_PAD")) s->smem_pad = (size_t)atoi(pad);
     s->exp_no_obs = getenv("PVE_EXPERIMENT_NO_OBS") != nullptr;
