@@ -67,6 +67,10 @@ def parse():
                          "loop's n-step return folding and replay writer (main.py:243-266) on the GPU every tick")
     ap.add_argument("--veh-cap", type=int, default=VEH_CAP, help="capacity class of the run (vehicle slots per intersection)")
     ap.add_argument("--agent-cap", type=int, default=AGENT_CAP, help="capacity class of the run (agents per intersection)")
+    ap.add_argument("--out-rows-per-env", type=int, default=0,
+                    help="size the dense output arrays for this many agent rows per intersection instead of agent_cap (very "
+                         "large batches: the outputs are dense, so the mean count plus a margin is enough; rows that do not "
+                         "fit raise `overflow`, which discards the run)")
     ap.add_argument("--traffic-child", action="store_true", help=argparse.SUPPRESS)      # run under ncu by measure_traffic()
     ap.add_argument("--no-traffic", action="store_true", help="skip the ncu child that measures roofline.traffic")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -419,7 +423,8 @@ def graft_arm(args, rank, world, local_rank, veh_cap, agent_cap):
     scene = BatchedScene(B, SceneConfig(vm=5 if (stress or rollout) else VM, zero_uncontrolled_actions=True,
                                         lane_num=4 if args.workload == "lane4" else 12),
                          veh_cap=veh_cap, agent_cap=agent_cap, device=dev, threads=args.threads,
-                         neighbour_sources=args.workload == "train")
+                         neighbour_sources=args.workload == "train",
+                         out_cap=B * args.out_rows_per_env if args.out_rows_per_env else None)
     scene.reset(tabs, warmup=True)
     actor = None
     if rollout:

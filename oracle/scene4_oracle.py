@@ -38,13 +38,17 @@ class Veh:
 
 
 class Scene4Oracle:
+    # geometry tables as class attributes: oracle/scene8_oracle.py derives the 8-lane scene from this class
+    NL, ND, NTYPE = NL, ND, 3
+    DIRECTION, LANE2LANE = DIRECTION, LANE2LANE
+
     def __init__(self, vm=5, collision_thr=2, dis_ctl=150, deltaT=0.1, vM=13, am=-3, aM=3, v0=10, lane_cw=2.5):
         self.vm, self.vM, self.am, self.aM, self.v0, self.dt, self.cw = vm, vM, am, aM, v0, deltaT, lane_cw
         self.thr, self.dis_ctl = collision_thr, dis_ctl
         cw = lane_cw
         self.lane_in = dis_ctl - 2 * cw                                                      # TIS:53
         self.L = [3.1415 / 2 * 3 * cw, 4 * cw, 3.1415 / 2 * cw]                               # TIS:53-55
-        self.remove_p = -dis_ctl + int((NL + 1) / 2) * cw                                    # TIS:341-342
+        self.remove_p = -dis_ctl + int((self.NL + 1) / 2) * cw                                    # TIS:341-342
         alpha = math.atan((4 - math.sqrt(2)) / (4 + math.sqrt(2)))                           # TIS:79
         alpha_ = math.atan((4 + math.sqrt(2)) / (4 - math.sqrt(2)))                          # TIS:80
         beta = math.atan(2 / math.sqrt(5))                                                   # TIS:81
@@ -71,23 +75,23 @@ class Scene4Oracle:
         # rows usable per lane: the positive, non-decreasing prefix (zero padding ends a table; the reference would go on
         # spawning one vehicle per tick and then raise IndexError)
         self.kvalid = []
-        for i in range(NL):
+        for i in range(self.NL):
             k = 0
             while k < len(self.arr) and self.arr[k][i] > 0 and (k == 0 or self.arr[k][i] >= self.arr[k - 1][i]):
                 k += 1
             self.kvalid.append(k)
         self.time, self.tick = 0, 0                      # TIS:196 (an int that becomes a float on the first += 0.1)
-        self.lanes = [[] for _ in range(NL)]
-        self.veh_rec = [0] * NL
+        self.lanes = [[] for _ in range(self.NL)]
+        self.veh_rec = [0] * self.NL
         self.id_seq = self.passed = self.passed_steps = self.intention_re = 0
-        self.vlist = [[] for _ in range(ND)]             # virtual_lane_4: entries [pos, lane, j, v, tag]
+        self.vlist = [[] for _ in range(self.ND)]             # virtual_lane_4: entries [pos, lane, j, v, tag]
         self.agents = []                                 # self.virtual_lane: [p, lane, j, intention]
         if warmup:
-            while not any(self.lanes) and any(self.veh_rec[i] < self.kvalid[i] for i in range(NL)):      # TIS:214-220
+            while not any(self.lanes) and any(self.veh_rec[i] < self.kvalid[i] for i in range(self.NL)):      # TIS:214-220
                 self._scene_update()
 
     def control_mask(self):
-        return [v.control for i in range(NL) for v in self.lanes[i]]
+        return [v.control for i in range(self.NL) for v in self.lanes[i]]
 
     # ------------------------------------------------------------------------------------------------------------
     def _move(self, i, j, act):
@@ -122,8 +126,8 @@ class Scene4Oracle:
     # ------------------------------------------------------------------------------------------------------------
     def _vd(self, other_route, ego_route, p1):
         """TIS:453-531: the other vehicle's place on the ego route's virtual lane, or None."""
-        r = ego_route % 3
-        k = LANE2LANE[ego_route].index(other_route)
+        r = ego_route % self.NTYPE
+        k = self.LANE2LANE[ego_route].index(other_route)
         delta = p1 - self.T[r][k]
         if delta > 0:
             return abs(delta) + self.C[r][k] if self.T[r][k] != 0.0 or self.C[r][k] != 0.0 else p1
@@ -161,8 +165,8 @@ class Scene4Oracle:
         ori = self.vlist[route]
         new = [e[:] for e in ori]
         idx = next(k for k, e in enumerate(ori) if e[1] == i and e[2] == j)
-        if route % 3 == 0:                                                                    # TIS:1301-1319
-            tag = LANE2LANE[route][1]
+        if self.NL == 4 and route % 3 == 0:                                                   # TIS:1301-1319
+            tag = self.LANE2LANE[route][1]
             k3 = 3 * self.cw
             for s, e in enumerate(ori):
                 if e[4] == tag:
@@ -211,21 +215,23 @@ class Scene4Oracle:
         self.tick += 1
         out = {"ids": [], "uid": [], "obs": [], "reward": [], "cpv": [], "nn": [], "jerks": [], "collisions": 0, "lock": 0}
         dele = []
-        for i in range(NL):
+        for i in range(self.NL):
             if self.lanes[i]:                                                                 # TIS:234
-                for m, route in enumerate(DIRECTION[i]):
+                for m, route in enumerate(self.DIRECTION[i]):
+                    if route == -1:                                                           # TIS:236-237 (lane_num = 8)
+                        continue
                     lst = []
                     for p, l, jj, it in self.agents:                                          # TIS:240-270
                         car = self.lanes[l][jj]
                         if l == i:
-                            if DIRECTION[l][it] == route:
+                            if self.DIRECTION[l][it] == route:
                                 lst.append([p, l, jj, car.v, route])
                             elif car.p - self.L[car.intention] > 0:                           # TIS:252-258
                                 lst.append([car.p - self.L[car.intention] + self.L[m], l, jj, car.v, route])
-                        elif DIRECTION[l][it] in LANE2LANE[route]:
-                            vd = self._vd(DIRECTION[l][it], route, p)
+                        elif self.DIRECTION[l][it] in self.LANE2LANE[route]:
+                            vd = self._vd(self.DIRECTION[l][it], route, p)
                             if vd is not None:
-                                lst.append([vd, l, jj, car.v, DIRECTION[l][it]])
+                                lst.append([vd, l, jj, car.v, self.DIRECTION[l][it]])
                     lst.sort(key=lambda e: e[0])                                              # TIS:271 (stable)
                     self.vlist[route] = lst
                     for j, me in enumerate(self.lanes[i]):
@@ -279,7 +285,7 @@ class Scene4Oracle:
                             self.passed_steps += me.step
             self._spawn(i)                                                                    # TIS:361
         self.agents = []                                                                      # TIS:364
-        for i in range(NL):                                                                   # TIS:365-370
+        for i in range(self.NL):                                                                   # TIS:365-370
             for j, me in enumerate(self.lanes[i]):
                 if me.control and not me.lock and self._check_lock(i, j):
                     out["lock"] += 1
@@ -293,9 +299,8 @@ class Scene4Oracle:
         """TIS:378-433."""
         if self.veh_rec[i] < self.kvalid[i] and self.time >= self.arr[self.veh_rec[i]][i]:
             v = Veh()
-            v.intention = self.intention_re % 3                                               # TIS:387
-            self.intention_re += 1
-            v.route = DIRECTION[i][v.intention]
+            v.intention = self._draw_intention(i)
+            v.route = self.DIRECTION[i][v.intention]
             v.p = sum([self.lane_in, self.L[v.intention]])                                    # TIS:395
             v.v, v.a, v.jerk, v.jerk_sum = self.v0, 0, 0, 0
             v.collision = v.step = 0
@@ -304,6 +309,11 @@ class Scene4Oracle:
             self.lanes[i].append(v)
             self.veh_rec[i] += 1
             self.id_seq += 1
+
+    def _draw_intention(self, i):
+        it = self.intention_re % 3                                                            # TIS:387
+        self.intention_re += 1                                                                # TIS:388
+        return it
 
     def _check_lock(self, i, j):
         """TIS:1469-1499."""
@@ -333,7 +343,7 @@ class Scene4Oracle:
     def step(self, actions):
         """One tick as main.py:398-407 + 441 drives it: ``actions`` per vehicle in (lane, j) order."""
         k = 0
-        for i in range(NL):
+        for i in range(self.NL):
             for j in range(len(self.lanes[i])):
                 self._move(i, j, float(actions[k]))
                 k += 1
@@ -344,7 +354,7 @@ class Scene4Oracle:
         return out
 
     def snapshot(self):
-        vs = [v for i in range(NL) for v in self.lanes[i]]
+        vs = [v for i in range(self.NL) for v in self.lanes[i]]
         s = {k: [getattr(v, k) for v in vs] for k in ("p", "v", "a", "jerk_sum", "collision", "step", "uid", "control",
                                                       "finish", "lock", "lock_a", "intention")}
         s["row0"] = [list(v.row0) for v in vs]

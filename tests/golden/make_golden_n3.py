@@ -1,5 +1,5 @@
-"""Mint the golden rollouts of the 4-lane intersection by RUNNING THE REFERENCE SCENE
-with ``lane_num=4`` (build container only: needs /root/reference):
+"""Mint the golden rollouts of the 4-lane and 8-lane intersections by RUNNING THE
+REFERENCE SCENE with ``lane_num=4`` / ``lane_num=8`` (build container only: needs /root/reference):
 
     python tests/golden/make_golden_n3.py
 
@@ -9,6 +9,11 @@ done / removed / the six neighbours of every agent, the scalar outputs, a SHA-25
 observations every ``OBS_EVERY`` ticks) and the whole post-tick state (vehicles incl. their intention, per-lane counts,
 the heads of the twelve virtual lanes, the spawn counter ``intention_re``).  Layout as tests/golden/make_golden.py:
 ragged arrays concatenated along axis 0 with ``<name>__off`` offsets.
+
+``lane_num=8`` draws every new vehicle's intention with ``random.seed(); random.randint(0, 1)`` (TIS:382, 390), i.e. from
+OS entropy: those rollouts (``rollout8_*.npz``) run with ``random.seed`` disabled and ``random.randint`` returning
+``draws[k][i]`` for the k-th arrival of lane i -- a seeded table stored in the file; nothing else of the reference is
+touched.
 """
 import hashlib
 import os
@@ -25,7 +30,7 @@ from ref_harness import load_reference, ref_args  # noqa: E402
 from pve_mcc_for_unsignalized_intersection_b200.arrivals import synthetic_arrivals  # noqa: E402
 
 OBS_EVERY = 20
-NL, ND = 4, 12
+NL, ND = 4, 12          # rebound by rollout() for the 8-lane scene
 
 
 def snapshot(env, ticks):
@@ -46,9 +51,17 @@ def snapshot(env, ticks):
     return s
 
 
-def rollout(mod, name, table, n_ticks, policy, vm, seed, collision_thr=2):
+def rollout(mod, name, table, n_ticks, policy, vm, seed, collision_thr=2, lane_num=4):
+    global NL, ND
+    NL, ND = (4, 12) if lane_num == 4 else (8, 16)
     rng = np.random.RandomState(seed)
     nn_log = []
+    draws = rng.randint(0, 2, size=(len(table), NL)).astype(np.uint8) if lane_num == 8 else None
+    ctx = [0, 0]
+    saved = (mod.random.seed, mod.random.randint)
+    if lane_num == 8:
+        mod.random.seed = lambda *a: None
+        mod.random.randint = lambda a, b: int(draws[ctx[1]][ctx[0]])
 
     class Counted(mod.TrafficInteraction):
         n_updates = 0
@@ -61,6 +74,10 @@ def rollout(mod, name, table, n_ticks, policy, vm, seed, collision_thr=2):
             out = super().get_state(i, j, vl, direction)
             nn_log.append([list(c) for c in self.closer_cars])
             return out
+
+        def add_new_veh(self, i):
+            ctx[0], ctx[1] = i, self.veh_rec[i]
+            return super().add_new_veh(i)
 
     env = Counted(np.asarray(table, np.float64), 150, ref_args(collision_thr), vm=vm, lane_num=NL)
     rag, obs_full, obs_ticks, sha = Ragged(), Ragged(), [], []
@@ -115,8 +132,11 @@ def rollout(mod, name, table, n_ticks, policy, vm, seed, collision_thr=2):
         n_rows += A
         max_v = max(max_v, len(post["p"]))
         assert int(post["veh_rec"].max()) < len(table) - 1, "arrival table too short for the rollout"
+    mod.random.seed, mod.random.randint = saved
     data = {"table": np.asarray(table, np.float64), "vm": np.float64(vm), "collision_thr": np.float64(collision_thr),
             "lane_num": np.int64(NL), "n_ticks": np.int64(n_ticks), "obs_sha256": np.stack(sha), "obs_ticks": np.array(obs_ticks, np.int64)}
+    if draws is not None:
+        data["draws"] = draws
     for k, v in init.items():
         data["init_" + k] = v
     data.update(rag.pack())
@@ -125,15 +145,15 @@ def rollout(mod, name, table, n_ticks, policy, vm, seed, collision_thr=2):
         data["t_" + k] = np.array(v, np.int64)
     for k, v in envs.items():
         data["t_" + k] = np.stack(v).astype(np.int32)
-    path = os.path.join(HERE, "rollout4_%s.npz" % name)
+    path = os.path.join(HERE, "rollout%d_%s.npz" % (lane_num, name))
     np.savez_compressed(path, **data)
     print("%-18s ticks=%d agent rows=%d max_V=%d collisions=%d locks=%d passed=%d  %.0f KB" % (
         name, n_ticks, n_rows, max_v, sum(scal["collisions"]), sum(scal["lock"]), scal["passed_veh"][-1], os.path.getsize(path) / 1024))
 
 
-def mat4(density, rows):
+def mat4(density, rows, lanes=4):
     arr = scio.loadmat("/root/reference/data/test/arvTimeNewVeh_new_%d_12.mat" % density)["arvTimeNewVeh"]
-    return np.ascontiguousarray(arr[:rows, :NL].astype(np.float64))
+    return np.ascontiguousarray(arr[:rows, :lanes].astype(np.float64))
 
 
 SPECS = {
@@ -144,8 +164,17 @@ SPECS = {
     "mat1200_thr3": (lambda: mat4(1200, 60), 420, "uniform", 5, 35, 3.0),
 }
 
+SPECS8 = {
+    "mat1000_vm5": (lambda: mat4(1000, 60, 8), 600, "uniform", 5, 41, 2),
+    "mat1200_vm6": (lambda: mat4(1200, 60, 8), 500, "mixed", 6, 42, 2),
+    "mat400_vm5": (lambda: mat4(400, 30, 8), 600, "uniform", 5, 43, 2),
+    "synth1800_brake": (lambda: synthetic_arrivals(1, 1800, 60.0, seed=9)[0][:, :8].copy(), 420, "brake", 5, 44, 2),
+    "mat1200_thr3": (lambda: mat4(1200, 60, 8), 420, "uniform", 5, 45, 3.0),
+}
+
 if __name__ == "__main__":
     mod = load_reference()
-    for name, (table, ticks, policy, vm, seed, thr) in SPECS.items():
-        if len(sys.argv) < 2 or name in sys.argv[1:]:
-            rollout(mod, name, table(), ticks, policy, vm, seed, thr)
+    for lanes, specs in ((4, SPECS), (8, SPECS8)):
+        for name, (table, ticks, policy, vm, seed, thr) in specs.items():
+            if len(sys.argv) < 2 or ("%d:%s" % (lanes, name)) in sys.argv[1:] or (lanes == 4 and name in sys.argv[1:]):
+                rollout(mod, name, table(), ticks, policy, vm, seed, thr, lane_num=lanes)

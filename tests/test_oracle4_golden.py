@@ -8,20 +8,31 @@ import pytest
 
 from golden_io import GOLDEN, Ragged
 from oracle.scene4_oracle import Scene4Oracle
+from oracle.scene8_oracle import Scene8Oracle
 
 ROLLOUTS4 = ["mat1000_vm5", "mat1200_vm6", "mat400_vm5", "synth1800_brake", "mat1200_thr3"]
+ROLLOUTS8 = ROLLOUTS4          # rollout8_*.npz: lane_num = 8, intentions from the recorded draw table
 
 
-def load4(name):
-    z = dict(np.load(os.path.join(GOLDEN, "rollout4_%s.npz" % name)))
+def load4(name, lanes=4):
+    z = dict(np.load(os.path.join(GOLDEN, "rollout%d_%s.npz" % (lanes, name))))
     return z, Ragged(z)
 
 
+@pytest.mark.parametrize("name", ROLLOUTS8)
+def test_oracle8_reproduces_the_reference_rollout(name):
+    test_oracle4_reproduces_the_reference_rollout(name, lanes=8)
+
+
 @pytest.mark.parametrize("name", ROLLOUTS4)
-def test_oracle4_reproduces_the_reference_rollout(name):
-    z, r = load4(name)
-    o = Scene4Oracle(vm=float(z["vm"]), collision_thr=float(z["collision_thr"]))
-    o.reset(z["table"], warmup=True)
+def test_oracle4_reproduces_the_reference_rollout(name, lanes=4):
+    z, r = load4(name, lanes)
+    if lanes == 4:
+        o = Scene4Oracle(vm=float(z["vm"]), collision_thr=float(z["collision_thr"]))
+        o.reset(z["table"], warmup=True)
+    else:
+        o = Scene8Oracle(vm=float(z["vm"]), collision_thr=float(z["collision_thr"]))
+        o.reset(z["table"], z["draws"], warmup=True)
     s = o.snapshot()
     assert s["tick"] == int(z["init_tick"]) and s["lane_n"] == z["init_lane_n"].tolist() and s["p"] == z["init_p"].tolist()
     obs_at = {int(t): k for k, t in enumerate(z["obs_ticks"])}
