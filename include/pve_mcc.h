@@ -72,15 +72,19 @@ typedef struct pve_config {
      * what the reference driver does on the host (`else: action = 0`, MAIN:401-405), for callers that fill every
      * slot without reading the control flags back.  0: actions are used as given (step() semantics, TIS:1502) */
     int32_t zero_uncontrolled;
-    /* 0 or 12: the 12-lane intersection (everything above).  4: the single-lane-per-approach intersection of the
-     * reference's lane_num = 4 branch (TIS:51-83) -- SURVEY.md 8(f) row N3: lane_in / lane_len / remove_p above are then
-     * those of TIS:53-55 / 341-342, the vd_* and rot_* tables are unused and the n4_* constants below apply.  Lanes 4..11
-     * of every [..][12] array (spawn ticks, header) are unused.  Vehicles carry their `intention` in bits 5-6 of the
-     * flags byte of pve_veh_meta.packed; the 4th value of every observation quad is the ROUTE (direction[lane][intention]). */
+    /* 0 or 12: the 12-lane intersection (everything above).  4 / 8: the one- / two-lanes-per-approach intersections of
+     * the reference's lane_num = 4 and lane_num = 8 branches (TIS:66-99, 100-145) -- SURVEY.md 8(f) row N3: lane_in /
+     * lane_len / remove_p above are then those of TIS:53-55 / 101-103 and TIS:341-342, the vd_* and rot_* tables are unused
+     * and the n4_* constants below apply.  Lanes 4..11 (8..11) of every [..][12] array (spawn ticks, header) are unused.
+     * Vehicles carry their `intention` in bits 5-6 of the flags byte of pve_veh_meta.packed; the 4th value of every
+     * observation quad is the ROUTE (direction[lane][intention]).  lane_num = 8 draws every new vehicle's intention at
+     * random in the reference (TIS:382, 390); here the draws are an input, see pve_set_intention_draws. */
     int32_t lane_num;
-    double n4_T[3][7], n4_C[3][7];   /* get_virtual_distance (TIS:453-531): member iff p1 - T > 0, vd = |p1 - T| + C;
-                                      * first index = ego route % 3, second = position of the other route in lane2lane */
-    double n4_rw[3];                 /* get_state rewrite (TIS:1304-1316): (alpha' - alpha) 3 cw, alpha' 3 cw, alpha 3 cw */
+    double n4_T[4][7], n4_C[4][7], n4_C2[4][7];
+                                     /* get_virtual_distance (TIS:453-531 / 537-660): member iff p1 - T > 0,
+                                      * vd = (|p1 - T| + C) - C2; first index = ego route % 3 (lane_num 4) or % 4 (lane_num 8),
+                                      * second = position of the other route in lane2lane */
+    double n4_rw[3];                 /* get_state rewrite (TIS:1304-1316, lane_num 4): (alpha' - alpha) 3 cw, alpha' 3 cw, alpha 3 cw */
 } pve_config;
 
 /* Per-intersection header as stored on the device (little endian, 144 bytes). */
@@ -170,6 +174,11 @@ const char *pve_last_error(const pve_scene *s);
  * the host from the arrival tables; borrowed, must outlive the rollout.
  * warmup != 0 advances every intersection to its first arrival like TIS:214-220. */
 int32_t pve_reset(pve_scene *s, const int32_t *spawn_tick_dev, int32_t K, int32_t warmup, void *stream);
+
+/* lane_num = 8 only, before pve_reset: draws_dev uint8 [B][K][12], draws_dev[b][k][i] in {0, 1} = what the reference's
+ * `random.randint(0, 1)` returns for the k-th arrival of lane i (TIS:390: intention = self.intention[i][draw]); K and the
+ * layout are those of the spawn table handed to the next pve_reset.  Borrowed, must outlive the rollout. */
+int32_t pve_set_intention_draws(pve_scene *s, const uint8_t *draws_dev);
 
 /* step(i, j, a) for every vehicle (TIS:1501, MAIN:398-406) + scene_update() (TIS:222) +
  * delete_vehicle() (TIS:435).  actions_dev: float [B][veh_cap]. */

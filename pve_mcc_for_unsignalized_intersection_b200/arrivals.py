@@ -36,10 +36,10 @@ def to_spawn_ticks(arrive_time, delta_t=0.1, max_tick=None):
     more arrivals" is the defined behaviour here.  Two EQUAL consecutive arrival times are valid arrivals: the reference
     spawns them on consecutive ticks (one vehicle per lane and tick, TIS:379), and so does the device.
 
-    The last dimension is the number of lanes of the table: 12, or 4 for the 4-lane intersection (``lane_num=4``).
+    The last dimension is the number of lanes of the table: 12, or 8 / 4 for the 8- and 4-lane intersections (``lane_num``).
     """
     arr = np.asarray(arrive_time, dtype=np.float64)
-    assert arr.shape[-1] in (NLANE, 4), arr.shape
+    assert arr.shape[-1] in (NLANE, 8, 4), arr.shape
     K = arr.shape[-2]
     if max_tick is None:
         finite_max = float(arr.max()) if arr.size else 0.0

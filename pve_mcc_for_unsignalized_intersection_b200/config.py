@@ -35,7 +35,8 @@ class PveConfig(C.Structure):
         ("vd_a1", (C.c_double * 4) * 2), ("vd_a2", (C.c_double * 4) * 2), ("vd_b", (C.c_double * 4) * 2),
         ("rot_cos", C.c_double * 4), ("rot_sin", C.c_double * 4),
         ("zero_uncontrolled", C.c_int32), ("lane_num", C.c_int32),
-        ("n4_T", (C.c_double * 7) * 3), ("n4_C", (C.c_double * 7) * 3), ("n4_rw", C.c_double * 3),
+        ("n4_T", (C.c_double * 7) * 4), ("n4_C", (C.c_double * 7) * 4), ("n4_C2", (C.c_double * 7) * 4),
+        ("n4_rw", C.c_double * 3),
     ]
 
 
@@ -63,9 +64,9 @@ class SceneConfig:
     zero_uncontrolled_actions: bool = False
 
     def __post_init__(self):
-        if self.lane_num not in (12, 4):
-            raise NotImplementedError("lane_num must be 12 or 4 (lane_num=%r; the 8-lane branch draws intentions from an "
-                                      "unseeded RNG, TIS:382/390, and is not built)" % self.lane_num)
+        if self.lane_num not in (12, 8, 4):
+            raise NotImplementedError("lane_num must be 12, 8 or 4 (lane_num=%r: the reference's T-junction branch dies in "
+                                      "its constructor, direction_num is never set)" % self.lane_num)
         if self.o_agent_num != 6:
             raise NotImplementedError("o_agent_num must be 6 (28-wide observation rows)")
 
@@ -74,11 +75,15 @@ class SceneConfig:
         cw = self.lane_cw
         if self.lane_num == 4:
             return [3.1415 / 2 * 3 * cw, 4 * cw, 3.1415 / 2 * cw]                 # TIS:53-55
+        if self.lane_num == 8:
+            return [3.1415 / 2 * 5 * cw, 8 * cw, 3.1415 / 2 * cw]                 # TIS:101-103
         return [3.1415 / 2 * 7 * cw, 12 * cw, 3.1415 / 2 * cw]                    # TIS:149-151
 
     def lane_in(self):
         if self.lane_num == 4:
             return self.dis_ctl - 2 * self.lane_cw                               # TIS:53
+        if self.lane_num == 8:
+            return self.dis_ctl - 4 * self.lane_cw                               # TIS:101
         return self.dis_ctl - 6 * self.lane_cw                                   # TIS:149
 
     def four_lane_tables(self):
@@ -105,12 +110,30 @@ class SceneConfig:
         rw = [(alpha_ - alpha) * 3 * cw, alpha_ * 3 * cw, alpha * 3 * cw]         # TIS:1304, 1309, 1316
         return T, Cc, rw
 
+    def eight_lane_tables(self):
+        """``lane_num=8``: ``get_virtual_distance`` (TIS:537-660) as ``(T, C, C2)`` -- member iff ``p1 - T > 0``,
+        ``vd = (abs(p1 - T) + C) - C2`` -- indexed ``[ego route % 4][position in lane2lane[ego route]]``; every expression
+        keeps the reference's association (``C2`` exists for TIS:638: ``abs(d) + 8 cw - sqrt(24) cw``)."""
+        cw = self.lane_cw
+        s24 = math.sqrt(24)
+        T = [[8 * cw - s24 * cw, math.atan(3 / 4) * 5 * cw, 4 * cw, math.atan(4 / 3) * 5 * cw, 4 * cw, s24 * cw, 0.0],      # TIS:542-576
+             [3 * cw, 3 * cw, math.atan(3 / 4) * 5 * cw, math.atan(4 / 3) * 5 * cw, 5 * cw, 5 * cw, 0.0],                   # TIS:581-615
+             [cw, cw, math.atan(1 / s24) * 5 * cw, math.atan(s24) * 5 * cw, 7 * cw, 7 * cw, 0.0],                           # TIS:621-655
+             [0.0] * 7]                                                                                                    # TIS:658
+        Cc = [[math.atan(s24) * 5 * cw, math.atan(4 / 3) * 5 * cw, math.atan(4 / 3) * 5 * cw, math.atan(3 / 4) * 5 * cw,
+               math.atan(3 / 4) * 5 * cw, math.atan(1 / s24) * 5 * cw, 0.0],
+              [7 * cw, 5 * cw, 4 * cw, 4 * cw, 3 * cw, cw, 0.0],
+              [7 * cw, 5 * cw, s24 * cw, 8 * cw, 3 * cw, cw, 0.0],
+              [0.0] * 7]
+        C2 = [[0.0] * 7, [0.0] * 7, [0.0, 0.0, 0.0, s24 * cw, 0.0, 0.0, 0.0], [0.0] * 7]
+        return T, Cc, C2
+
     def spawn_p(self, lane):
         m = lane % 3                                                             # TIS:393-394
         return sum([self.lane_in(), self.lane_len()[m]])                         # TIS:395
 
     def remove_p(self):
-        return -self.dis_ctl + int((self.lane_num + 1) / 2) * self.lane_cw       # TIS:341-342 (lane_num 12: -135, 4: -145)
+        return -self.dis_ctl + int((self.lane_num + 1) / 2) * self.lane_cw       # TIS:341-342 (lane_num 12: -135, 8: -140, 4: -145)
 
     def angles(self):
         cw = self.lane_cw
@@ -176,4 +199,9 @@ class SceneConfig:
                     c.n4_T[r][k], c.n4_C[r][k] = T[r][k], Cc[r][k]
             for k in range(3):
                 c.n4_rw[k] = rw[k]
+        elif self.lane_num == 8:
+            T, Cc, C2 = self.eight_lane_tables()
+            for r in range(4):
+                for k in range(7):
+                    c.n4_T[r][k], c.n4_C[r][k], c.n4_C2[r][k] = T[r][k], Cc[r][k], C2[r][k]
         return c

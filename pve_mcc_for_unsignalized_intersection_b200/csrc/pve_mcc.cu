@@ -59,6 +59,7 @@ struct pve_scene {
     /* lane_num = 4 (row N3): its own kernel, one warp per intersection; dense output offsets from a scan kernel */
     int lane_num;
     Pve4Params prm4;
+    const uint8_t *draws;        /* lane_num = 8: intention draws [B][K][12] (borrowed, pve_set_intention_draws) */
     int64_t *off4;               /* [B + 1] */
     /* dual mode (default class, default CTA size): two concurrent kernels per tick, see PveState::klass */
     int dual, dual_pdl;
@@ -207,16 +208,17 @@ __global__ void pve_classify_kernel(PveState S, int B) {
     if (big) S.big_list_next[atomicAdd(S.big_cnt_next, 1)] = b;
 }
 
-/* ---- lane_num = 4 (scene_step4.cuh): one warp per intersection, PVE4_WARPS intersections per CTA ---------------- */
+/* ---- lane_num = 4 / 8 (scene_step4.cuh): one warp per intersection, PVE4_WARPS intersections per CTA -------------- */
 #define PVE4_WARPS 4
+template <int NLN>
 __global__ void __launch_bounds__(32 * PVE4_WARPS)
-pve4_step_kernel(const Pve4Params P, const PveState S, const pve_outputs O, const int32_t *spawn_tick, const float *actions,
-                 const int64_t *off4) {
+pve4_step_kernel(const Pve4Params P, const PveState S, const pve_outputs O, const int32_t *spawn_tick, const uint8_t *draws,
+                 const float *actions, const int64_t *off4) {
     extern __shared__ __align__(16) unsigned char pve_smem[];
     const int b = (int)blockIdx.x * PVE4_WARPS + (int)(threadIdx.x >> 5);
     if (b >= P.B) return;
     Pve4Smem &M = ((Pve4Smem *)pve_smem)[threadIdx.x >> 5];
-    pve4_step_block(P, S, O, spawn_tick, actions, b, M, off4[b]);
+    pve4_step_block<NLN>(P, S, O, spawn_tick, draws, actions, b, M, off4[b]);
 }
 
 /* exclusive prefix of the agent counts -> first output row of every intersection (one CTA; B is small on this path) */
@@ -510,20 +512,24 @@ static cudaError_t launch_one(pve_scene *s, const float *actions, const pve_outp
 }
 #endif
 
-/* lane_num = 4: offsets, the step, and the group sums that pve_next_agent_total reads */
+/* lane_num = 4 / 8: offsets, the step, and the group sums that pve_next_agent_total reads */
 static int32_t launch_step4(pve_scene *s, const float *actions, const pve_outputs &O, pve_stream_t stream) {
     const int B = s->cfg.n_envs;
 #ifndef PVE_HOST_EMULATION
     static bool attr_set[16] = {false};
     const size_t smem = sizeof(Pve4Smem) * PVE4_WARPS;
     if (!attr_set[s->device & 15]) {
-        RT_CHECK(s, cudaFuncSetAttribute(pve4_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        RT_CHECK(s, cudaFuncSetAttribute(pve4_step_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        RT_CHECK(s, cudaFuncSetAttribute(pve4_step_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr_set[s->device & 15] = true;
     }
     if (s->profiling) RT_CHECK(s, cudaEventRecord(s->ev[0], stream));
     pve4_offsets_kernel<<<1, 1024, 0, stream>>>(s->st.n_ctrl, s->off4, B);
     RT_CHECK(s, cudaGetLastError());
-    pve4_step_kernel<<<(B + PVE4_WARPS - 1) / PVE4_WARPS, 32 * PVE4_WARPS, smem, stream>>>(s->prm4, s->st, O, s->spawn_tick, actions, s->off4);
+    if (s->lane_num == 4)
+        pve4_step_kernel<4><<<(B + PVE4_WARPS - 1) / PVE4_WARPS, 32 * PVE4_WARPS, smem, stream>>>(s->prm4, s->st, O, s->spawn_tick, nullptr, actions, s->off4);
+    else
+        pve4_step_kernel<8><<<(B + PVE4_WARPS - 1) / PVE4_WARPS, 32 * PVE4_WARPS, smem, stream>>>(s->prm4, s->st, O, s->spawn_tick, s->draws, actions, s->off4);
     RT_CHECK(s, cudaGetLastError());
     if (s->profiling) RT_CHECK(s, cudaEventRecord(s->ev[1], stream));
     const int G = s->n_groups;
@@ -538,7 +544,8 @@ static int32_t launch_step4(pve_scene *s, const float *actions, const pve_output
     if (!M) return PVE_ENOMEM;
     for (int b = 0; b < B; ++b) {
         memset(M, 0xA5, sizeof *M);           /* poison: catches reads of unwritten shared memory */
-        pve4_step_block(s->prm4, s->st, O, s->spawn_tick, actions, b, *M, s->off4[b]);
+        if (s->lane_num == 4) pve4_step_block<4>(s->prm4, s->st, O, s->spawn_tick, nullptr, actions, b, *M, s->off4[b]);
+        else pve4_step_block<8>(s->prm4, s->st, O, s->spawn_tick, s->draws, actions, b, *M, s->off4[b]);
     }
     delete M;
     emul_gsum(s->st.n_ctrl, s->gsum, s->gsum + s->n_groups, s->gsum + 2 * (size_t)s->n_groups, B, s->n_groups);
@@ -549,7 +556,7 @@ static int32_t launch_step4(pve_scene *s, const float *actions, const pve_output
 static int32_t launch_step(pve_scene *s, const float *actions, const pve_outputs &O_in, pve_stream_t stream) {
     const int VCc = s->prm.VC, ACc = s->prm.AC;
     pve_outputs O = O_in;
-    if (s->lane_num == 4) return launch_step4(s, actions, O, stream);
+    if (s->lane_num != 12) return launch_step4(s, actions, O, stream);
     if (s->exp_no_obs) O.obs = nullptr;          /* experiment knob (env PVE_EXPERIMENT_NO_OBS): what the observation traffic costs */
 #ifndef PVE_HOST_EMULATION
     if (s->cfg.n_envs >= 1024) {                 /* small batches fit in one wave: order is irrelevant */
@@ -702,12 +709,18 @@ int32_t pve_create(const pve_config *cfg, int32_t device, pve_scene **out) {
                  B, cfg->veh_cap, cfg->agent_cap);
         return PVE_EINVAL;
     }
-    s->lane_num = (cfg->lane_num == 4) ? 4 : 12;
-    if (cfg->lane_num != 0 && cfg->lane_num != 12 && cfg->lane_num != 4) {
-        snprintf(s->err, sizeof s->err, "lane_num must be 12 or 4 (got %d)", cfg->lane_num);
+    s->lane_num = (cfg->lane_num == 4 || cfg->lane_num == 8) ? cfg->lane_num : 12;
+    if (cfg->lane_num != 0 && cfg->lane_num != 12 && cfg->lane_num != 4 && cfg->lane_num != 8) {
+        snprintf(s->err, sizeof s->err, "lane_num must be 12, 8 or 4 (got %d)", cfg->lane_num);
         return PVE_EINVAL;
     }
-    if (s->lane_num == 4 && VC < PVE4_LC) { VC = 128; AC = AC < 96 ? 96 : AC; s->smem_bytes = sizeof(Pve4Smem); }
+    if (s->lane_num != 12) {
+        if (VC > PVE4_LC) {
+            snprintf(s->err, sizeof s->err, "lane_num = %d holds at most %d vehicles per intersection", s->lane_num, PVE4_LC);
+            return PVE_EINVAL;
+        }
+        VC = 128; AC = AC < 96 ? 96 : AC; s->smem_bytes = sizeof(Pve4Smem);
+    }
     s->cfg.veh_cap = VC;          /* rounded up to the capacity class; see pve_veh_cap() */
     s->cfg.agent_cap = AC;
     /* default CTA size: 128 threads for the small classes (V ~ 76 vehicles per intersection), 512 for the large ones
@@ -755,27 +768,43 @@ int32_t pve_create(const pve_config *cfg, int32_t device, pve_scene **out) {
             return PVE_EINVAL;
         }
     }
-    if (s->lane_num == 4) {
+    if (s->lane_num != 12) {
         static const int8_t kDir4[PVE4_NL][3] = {{6, 7, 8}, {0, 1, 2}, {9, 10, 11}, {3, 4, 5}};                  /* TIS:73-78 */
         static const int8_t kL2L4[PVE4_ND][7] = {                                                                /* TIS:58-71 */
             {10, 6, 9, 3, 7, 4, 8}, {10, 6, 3, 4, 9, 5, -1}, {6, 10, -1, -1, -1, -1, -1},
             {1, 9, 0, 6, 10, 7, 11}, {1, 9, 6, 7, 0, 8, -1}, {9, 1, -1, -1, -1, -1, -1},
             {4, 0, 3, 9, 1, 10, 2}, {4, 0, 9, 10, 3, 11, -1}, {0, 4, -1, -1, -1, -1, -1},
             {7, 3, 6, 0, 4, 1, 5}, {7, 3, 0, 1, 6, 2, -1}, {3, 7, -1, -1, -1, -1, -1}};
+        static const int8_t kDir8[PVE4_MAXNL][3] = {{0, 1, -1}, {-1, 2, 3}, {4, 5, -1}, {-1, 6, 7},             /* TIS:136-145 */
+                                                    {8, 9, -1}, {-1, 10, 11}, {12, 13, -1}, {-1, 14, 15}};
+        static const int8_t kL2L8[PVE4_MAXND][7] = {                                                             /* TIS:107-123 */
+            {14, 4, 13, 12, 9, 10, 5}, {14, 13, 8, 4, 5, 6, 12}, {14, 13, 8, 4, 5, 6, 7}, {14, -1, -1, -1, -1, -1, -1},
+            {2, 8, 1, 0, 13, 14, 9}, {2, 1, 12, 8, 9, 10, 0}, {2, 1, 12, 8, 9, 10, 11}, {2, -1, -1, -1, -1, -1, -1},
+            {6, 12, 5, 4, 1, 2, 13}, {6, 5, 0, 12, 13, 14, 4}, {6, 5, 0, 12, 13, 14, 15}, {6, -1, -1, -1, -1, -1, -1},
+            {10, 0, 9, 8, 5, 6, 1}, {10, 9, 4, 0, 1, 2, 8}, {10, 9, 4, 0, 1, 2, 3}, {10, -1, -1, -1, -1, -1, -1}};
+        const bool four = s->lane_num == 4;
+        const int nl = four ? PVE4_NL : PVE4_MAXNL, nd = four ? PVE4_ND : PVE4_MAXND;
         Pve4Params &Q = s->prm4;
         memset(&Q, 0, sizeof Q);
         Q.dt = cfg->dt; Q.dt2 = cfg->dt2; Q.vm = cfg->vm; Q.vM = cfg->vM; Q.am = cfg->am; Q.aM = cfg->aM; Q.v0 = cfg->v0;
         Q.thr = cfg->collision_thr; Q.lane_in = cfg->lane_in; Q.remove_p = cfg->remove_p; Q.cw = cfg->lane_cw;
         Q.abs_am = fabs(cfg->am); Q.two_abs_am = 2 * fabs(cfg->am); Q.aspan = (double)(cfg->aM - cfg->am);
         for (int m = 0; m < 3; ++m) Q.L[m] = cfg->lane_len[m];
-        memcpy(Q.T, cfg->n4_T, sizeof Q.T); memcpy(Q.C, cfg->n4_C, sizeof Q.C);
+        memcpy(Q.T, cfg->n4_T, sizeof Q.T); memcpy(Q.C, cfg->n4_C, sizeof Q.C); memcpy(Q.C2, cfg->n4_C2, sizeof Q.C2);
         Q.rw_k = cfg->n4_rw[0]; Q.rw_a = cfg->n4_rw[1]; Q.rw_b = cfg->n4_rw[2];
-        memcpy(Q.dir, kDir4, sizeof Q.dir);
+        memset(Q.dir, -1, sizeof Q.dir);
+        for (int i = 0; i < nl; ++i) for (int m = 0; m < 3; ++m) Q.dir[i][m] = four ? kDir4[i][m] : kDir8[i][m];
         memset(Q.l2l_pos, -1, sizeof Q.l2l_pos);
-        for (int d = 0; d < PVE4_ND; ++d) {
-            for (int k = 0; k < 7; ++k) if (kL2L4[d][k] >= 0) Q.l2l_pos[d][kL2L4[d][k]] = (int8_t)k;
-            Q.l2l_1[d] = kL2L4[d][1];
+        for (int d = 0; d < nd; ++d) {
+            for (int k = 0; k < 7; ++k) {
+                const int r = four ? kL2L4[d][k] : kL2L8[d][k];
+                if (r >= 0) Q.l2l_pos[d][r] = (int8_t)k;
+            }
+            Q.l2l_1[d] = four ? kL2L4[d][1] : kL2L8[d][1];
         }
+        for (int i = 0; i < PVE4_MAXNL; ++i) { Q.int8[i][0] = (int8_t)((i & 1) ? 1 : 0); Q.int8[i][1] = (int8_t)((i & 1) ? 2 : 1); }   /* TIS:125-134 */
+        Q.ntype = four ? 3 : 4;
+        for (int i = 0; i < nl; ++i) if (i == 2 || i == 5 || i == 8 || i == 11) Q.am_mask |= 1 << i;             /* TIS:1519 */
         Q.B = B; Q.VC = VC; Q.K = 0; Q.zero_unctl = cfg->zero_uncontrolled ? 1 : 0; Q.out_cap = cfg->out_cap;
     }
     P.B = B; P.VC = VC; P.AC = AC; P.K = 0; P.out_cap = cfg->out_cap;
@@ -799,7 +828,7 @@ int32_t pve_create(const pve_config *cfg, int32_t device, pve_scene **out) {
     RT_CHECK(s, rt_alloc((void **)&s->st.n_veh, sizeof(int32_t) * (size_t)B));
     RT_CHECK(s, rt_alloc((void **)&s->st.stats, sizeof(double) * (size_t)B * PVE_NSTAT));
     RT_CHECK(s, rt_alloc((void **)&s->order, sizeof(int32_t) * (size_t)B));
-    if (s->lane_num == 4) RT_CHECK(s, rt_alloc((void **)&s->off4, sizeof(int64_t) * ((size_t)B + 1)));
+    if (s->lane_num != 12) RT_CHECK(s, rt_alloc((void **)&s->off4, sizeof(int64_t) * ((size_t)B + 1)));
     s->order_age = -1;
 #ifndef PVE_HOST_EMULATION
     if (s->dual) {
@@ -827,8 +856,19 @@ int32_t pve_create(const pve_config *cfg, int32_t device, pve_scene **out) {
     return pve_reset(s, nullptr, 0, 0, nullptr);
 }
 
+int32_t pve_set_intention_draws(pve_scene *s, const uint8_t *draws_dev) {
+    if (!s) return PVE_EINVAL;
+    s->draws = draws_dev;
+    return PVE_OK;
+}
+
 int32_t pve_reset(pve_scene *s, const int32_t *spawn_tick_dev, int32_t K, int32_t warmup, void *stream_) {
     if (!s) return PVE_EINVAL;
+    if (s->lane_num == 8 && spawn_tick_dev && K > 0 && !s->draws) {
+        snprintf(s->err, sizeof s->err, "lane_num = 8: call pve_set_intention_draws before pve_reset (TIS:390 draws every new "
+                                        "vehicle's intention at random; the draws are an input here)");
+        return PVE_EINVAL;
+    }
     pve_stream_t stream = (pve_stream_t)stream_;
     const int B = s->cfg.n_envs;
     const size_t nv = (size_t)B * s->cfg.veh_cap;

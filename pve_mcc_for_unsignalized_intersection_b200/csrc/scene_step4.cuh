@@ -1,5 +1,10 @@
 /*
- * scene_step4.cuh -- one tick of one 4-lane intersection (lane_num = 4), executed by one WARP.
+ * scene_step4.cuh -- one tick of one 4-lane or 8-lane intersection (lane_num = 4 / 8), executed by one WARP.
+ *
+ * lane_num = 8 (two lanes per approach, 16 routes; TIS:100-145, 537-660, 1061-1249) runs the same control flow -- the
+ * reference's scene_update is one loop for every lane_num != 12 -- with its own tables (Pve4Params), its own get_p
+ * (pve8_world_xy), no get_state rewrite, `-1` routes skipped (TIS:236-237) and the intention of a new vehicle taken from
+ * a table of draws (the reference calls random.seed() and random.randint(0, 1), TIS:382, 390: an input here).
  *
  * Replaces, for lane_num = 4, the reference's step() x V (traffic_interaction_scene.py "TIS" 1501-1539),
  * scene_update() (TIS:222-376) with get_virtual_distance (TIS:453-531), get_p (TIS:896-1062), get_state incl. its
@@ -27,6 +32,8 @@
 
 #define PVE4_NL 4
 #define PVE4_ND 12
+#define PVE4_MAXNL 8           /* lane_num = 8 */
+#define PVE4_MAXND 16
 #define PVE4_LC 128            /* list capacity (entries of one virtual lane) == vehicle slots staged per intersection */
 
 #ifdef __CUDACC__
@@ -42,11 +49,15 @@
 struct Pve4Params {
     double dt, dt2, vm, vM, am, aM, v0, thr, lane_in, remove_p, cw, abs_am, two_abs_am, aspan;
     double L[3];
-    double T[3][7], C[3][7];           /* get_virtual_distance: member iff p1 - T > 0; vd = |p1 - T| + C (T = C = 0: vd = p1) */
-    double rw_k, rw_a, rw_b;           /* get_state rewrite: (alpha' - alpha) 3 cw, alpha' 3 cw, alpha 3 cw (TIS:1304-1316) */
-    int8_t dir[PVE4_NL][3];            /* direction[lane][intention], TIS:73-78 */
-    int8_t l2l_pos[PVE4_ND][PVE4_ND];  /* position of route r in lane2lane[route] (TIS:58-71) or -1 */
-    int8_t l2l_1[PVE4_ND];             /* lane2lane[route][1]: the route whose entries get_state rewrites */
+    double T[4][7], C[4][7], C2[4][7]; /* get_virtual_distance: member iff p1 - T > 0; vd = (|p1 - T| + C) - C2 (T = C = 0: vd = p1);
+                                        * first index: route % ntype */
+    double rw_k, rw_a, rw_b;           /* get_state rewrite (lane_num = 4): (alpha' - alpha) 3 cw, alpha' 3 cw, alpha 3 cw (TIS:1304-1316) */
+    int8_t dir[PVE4_MAXNL][3];         /* direction[lane][intention], TIS:73-78 / 136-145 (-1: no such route) */
+    int8_t l2l_pos[PVE4_MAXND][PVE4_MAXND];  /* position of route r in lane2lane[route] (TIS:58-71 / 107-123) or -1 */
+    int8_t l2l_1[PVE4_MAXND];          /* lane2lane[route][1]: the route whose entries get_state rewrites (lane_num = 4) */
+    int8_t int8[PVE4_MAXNL][2];        /* lane_num = 8: intention[lane][draw], TIS:125-134 */
+    int32_t ntype;                     /* 3 (lane_num = 4) or 4 (lane_num = 8) */
+    int32_t am_mask;                   /* lanes of `i in [2, 5, 8, 11]`, TIS:1519 */
     int32_t B, VC, K, zero_unctl;
     int64_t out_cap;
 };
@@ -65,9 +76,9 @@ struct alignas(16) Pve4Smem {
         done_row[PVE4_LC], fin_now[PVE4_LC], ltag[PVE4_LC], tmem[PVE4_LC], ttag[PVE4_LC];
     int8_t lock_a[PVE4_LC];
     int32_t misc[16];                              /* see P4M_* */
-    int32_t spawn[PVE4_NL], spawn_int[PVE4_NL], spawn_uid[PVE4_NL];
+    int32_t spawn[PVE4_MAXNL], spawn_int[PVE4_MAXNL], spawn_uid[PVE4_MAXNL];
     int16_t nbr[8];
-    int32_t lane_off[PVE4_NL + 1];
+    int32_t lane_off[PVE4_MAXNL + 1];
 };
 enum { P4M_NA = 0, P4M_N, P4M_IDX, P4M_GOUT, P4M_COLL, P4M_LOCK, P4M_NREM, P4M_PASSED, P4M_PSTEP, P4M_Q5U, P4M_COLLAG, P4M_NSPAWN,
        P4M_NCTRL, P4M_SURV };
@@ -120,11 +131,81 @@ PVE_DEV void pve4_world_xy(const Pve4Params &P, double p, int i, int m, double *
     }
 }
 
+/* TIS:1061-1249 get_p for lane_num = 8 (yaw is never read): even lanes turn left (m = 0) or go straight (m = 1), odd
+ * lanes go straight or turn right (m = 2); a = i / 2 is the approach */
+PVE_DEV void pve8_world_xy(const Pve4Params &P, double p, int i, int m, double *x, double *y) {
+    const double cw = P.cw, a4 = 4 * cw;
+    const int a = i >> 1;
+    double u = 0, w = 0;         /* the pair before the approach's orientation is applied */
+    int kind = 0;                /* how (u, w) maps to (x, y) for the four approaches */
+    if ((i & 1) == 0) {
+        if (m == 1) { u = p - a4; w = 1 * cw; kind = 0; }                                          /* TIS:1082-1085 ... */
+        else if (p > P.L[0]) { u = p - P.L[0] + a4; w = 1 * cw; kind = 1; }                        /* TIS:1066-1069 ... */
+        else if (p > 0) {
+            const double b = p / (5 * cw);                                                         /* TIS:1071 */
+            double s, c;
+#ifdef __CUDACC__
+            sincos(b, &s, &c);
+#else
+            s = sin(b); c = cos(b);
+#endif
+            s = s * 5 * cw; c = c * 5 * cw;
+            /* TIS:1072-1075, 1119-1122, 1166-1169, 1213-1216 */
+            if (a == 0) { *x = -1 * (c - a4); *y = -1 * (a4 - s); } else if (a == 1) { *x = -1 * (s - a4); *y = 1 * (a4 - c); }
+            else if (a == 2) { *x = 1 * (c - a4); *y = 1 * (a4 - s); } else { *x = 1 * (s - a4); *y = -1 * (a4 - c); }
+            return;
+        } else {                                                                                   /* TIS:1078-1079 ... */
+            const double q = -1 * p + a4;
+            if (a == 0) { *x = -1 * cw; *y = -1 * q; } else if (a == 1) { *x = 1 * q; *y = -1 * cw; }
+            else if (a == 2) { *x = cw; *y = q; } else { *x = -1 * q; *y = 1 * cw; }
+            return;
+        }
+        if (kind == 0) {
+            if (a == 0) { *x = u; *y = w; } else if (a == 1) { *x = -1 * cw; *y = u; }
+            else if (a == 2) { *x = -1 * p + a4; *y = -1 * cw; } else { *x = 1 * cw; *y = -1 * p + a4; }
+        } else {
+            if (a == 0) { *x = 1 * u; *y = w; } else if (a == 1) { *x = -1 * cw; *y = 1 * u; }
+            else if (a == 2) { *x = -1 * u; *y = -1 * cw; } else { *x = 1 * cw; *y = -1 * u; }
+        }
+        return;
+    }
+    if (m == 1) {                                                                                  /* TIS:1088-1091 ... */
+        if (a == 0) { *x = p - a4; *y = 3 * cw; } else if (a == 1) { *x = -3 * cw; *y = p - a4; }
+        else if (a == 2) { *x = -1 * p + a4; *y = -3 * cw; } else { *x = 3 * cw; *y = -1 * p + a4; }
+        return;
+    }
+    if (p > P.L[2]) {                                                                              /* TIS:1094-1097 ... */
+        u = p - P.L[2] + a4;
+        if (a == 0) { *x = 1 * u; *y = 3 * cw; } else if (a == 1) { *x = -3 * cw; *y = 1 * u; }
+        else if (a == 2) { *x = -1 * u; *y = -3 * cw; } else { *x = 3 * cw; *y = -1 * u; }
+        return;
+    }
+    if (p > 0) {
+        const double b = p / cw;                                                                   /* TIS:1099 */
+        double s, c;
+#ifdef __CUDACC__
+        sincos(b, &s, &c);
+#else
+        s = sin(b); c = cos(b);
+#endif
+        s = s * cw; c = c * cw;
+        /* TIS:1100-1103, 1147-1150, 1194-1197, 1241-1244 */
+        if (a == 0) { *x = 1 * (a4 - c); *y = 1 * (a4 - s); } else if (a == 1) { *x = -1 * (a4 - s); *y = 1 * (a4 - c); }
+        else if (a == 2) { *x = -1 * (a4 - c); *y = -1 * (a4 - s); } else { *x = 1 * (a4 - s); *y = -1 * (a4 - c); }
+        return;
+    }
+    w = -1 * p + a4;                                                                               /* TIS:1106-1107 ... */
+    if (a == 0) { *x = 3 * cw; *y = w; } else if (a == 1) { *x = -1 * w; *y = 3 * cw; }
+    else if (a == 2) { *x = -3 * cw; *y = -1 * w; } else { *x = w; *y = -3 * cw; }
+}
+
 /* one tick of intersection b.  rows_cur: the stored rows (indexed by the vehicle slots of the tick's start, rewritten at
  * the end for the next tick); rows_new: scratch for the rows computed this tick (same indexing). */
+template <int NLN>      /* lane_num: 4 or 8 */
 PVE_DEV void pve4_step_block(const Pve4Params &P, const PveState &S, const pve_outputs &O,
-                             const int32_t *PVE_RESTRICT spawn_tick, const float *PVE_RESTRICT actions,
-                             const int b, Pve4Smem &M, const int64_t obase) {
+                             const int32_t *PVE_RESTRICT spawn_tick, const uint8_t *PVE_RESTRICT draws,
+                             const float *PVE_RESTRICT actions, const int b, Pve4Smem &M, const int64_t obase) {
+    constexpr int PVE4_NLX = NLN;
     const size_t vbase = (size_t)b * (size_t)P.VC;
     float *const rows_cur = S.row0[0] + vbase * PVE_OBS_W;
     float *const rows_new = S.row0[1] + vbase * PVE_OBS_W;
@@ -134,12 +215,12 @@ PVE_DEV void pve4_step_block(const Pve4Params &P, const PveState &S, const pve_o
     P4_SYNC;
     P4_ONE {
         int o = 0;
-        for (int i = 0; i < PVE4_NL; ++i) { M.lane_off[i] = o; o += M.h.lane_n[i]; }
-        M.lane_off[PVE4_NL] = o;
+        for (int i = 0; i < PVE4_NLX; ++i) { M.lane_off[i] = o; o += M.h.lane_n[i]; }
+        M.lane_off[PVE4_NLX] = o;
         for (int q = 0; q < 16; ++q) M.misc[q] = 0;
     }
     P4_SYNC;
-    const int V = M.lane_off[PVE4_NL];
+    const int V = M.lane_off[PVE4_NLX];
     P4_PAR(k, V) {
         M.p[k] = S.p[vbase + k]; M.v[k] = S.v[vbase + k]; M.a[k] = S.a[vbase + k]; M.js[k] = S.js[vbase + k];
         const pve_veh_meta mt = S.meta[vbase + k];
@@ -151,7 +232,7 @@ PVE_DEV void pve4_step_block(const Pve4Params &P, const PveState &S, const pve_o
         M.lock[k] = (fl & PVE_F_LOCK) ? 1 : 0; M.lock_a[k] = (int8_t)((int)((fl >> 3) & 3u) - 1);
         M.intent[k] = (uint8_t)((fl >> 5) & 3u);
         int i = 0;
-        for (int q = 1; q < PVE4_NL; ++q) if (k >= M.lane_off[q]) i = q;
+        for (int q = 1; q < PVE4_NLX; ++q) if (k >= M.lane_off[q]) i = q;
         M.lane_of[k] = (uint8_t)i;
         M.hdr[k] = -1; M.virdis[k] = 100.0; M.del[k] = 0; M.jerk[k] = 0.0; M.done_row[k] = 0; M.fin_now[k] = 0;
     }
@@ -159,7 +240,7 @@ PVE_DEV void pve4_step_block(const Pve4Params &P, const PveState &S, const pve_o
 
     /* ---- step() for every vehicle: one lane of the warp per physical lane, its vehicles in order (the rear-end rule
      *      reads the already stepped leader, TIS:1509-1516) ---------------------------------------------------------- */
-    P4_PAR(i, PVE4_NL) {
+    P4_PAR(i, PVE4_NLX) {
         for (int k = M.lane_off[i]; k < M.lane_off[i + 1]; ++k) {
             const int j = k - M.lane_off[i];
             const double act = (P.zero_unctl && !M.ctl[k]) ? 0.0 : (double)actions[vbase + k];
@@ -172,7 +253,7 @@ PVE_DEV void pve4_step_block(const Pve4Params &P, const PveState &S, const pve_o
                 if (M.p[k] - M.p[k - 1] < d_safe) ta = P.am;
             }
             if (M.h.head_lane[i] == i && M.h.head_j[i] == j) ta = P.aM;                           /* TIS:1517: virtual_lane_4[i], the LANE index */
-            if (i == 2) ta = P.aM;                                                                /* TIS:1519: `i in [2, 5, 8, 11]` */
+            if ((P.am_mask >> i) & 1) ta = P.aM;                                                  /* TIS:1519: `i in [2, 5, 8, 11]` */
             ta = fmin(P.aM, fmax(P.am, ta));                                                      /* TIS:1521 */
             M.jerk[k] = ta - M.a[k];
             M.a[k] = ta;
@@ -194,10 +275,11 @@ PVE_DEV void pve4_step_block(const Pve4Params &P, const PveState &S, const pve_o
     const bool out_ok = obase + NA <= P.out_cap;
 
     /* ---- scene_update: lane by lane, route by route, vehicle by vehicle (TIS:233-361) ---------------------------------- */
-    for (int i = 0; i < PVE4_NL; ++i) {
+    for (int i = 0; i < PVE4_NLX; ++i) {
         if (M.lane_off[i + 1] == M.lane_off[i]) continue;                                         /* TIS:234 */
         for (int m = 0; m < 3; ++m) {
             const int route = P.dir[i][m];
+            if (route < 0) continue;                                                              /* TIS:236-237 (lane_num = 8) */
             /* membership and virtual position of every controlled vehicle (TIS:240-270) */
             P4_PAR(g, NA) {
                 const int k = M.agent[g], l = M.lane_of[k], it = M.intent[k];
@@ -210,10 +292,10 @@ PVE_DEV void pve4_step_block(const Pve4Params &P, const PveState &S, const pve_o
                 } else {
                     const int kk = P.l2l_pos[route][r];
                     if (kk >= 0) {                                                                /* TIS:259-270, 453-531 */
-                        const int ty = route % 3;
+                        const int ty = route % P.ntype;
                         const double T = P.T[ty][kk], C = P.C[ty][kk];
                         const double delta = M.p[k] - T;
-                        if (delta > 0) { mem = 1; tag = r; pos = (T == 0.0 && C == 0.0) ? M.p[k] : fabs(delta) + C; }
+                        if (delta > 0) { mem = 1; tag = r; pos = (T == 0.0 && C == 0.0) ? M.p[k] : (fabs(delta) + C) - P.C2[ty][kk]; }
                     }
                 }
                 M.tmem[g] = (uint8_t)mem; M.ttag[g] = (uint8_t)tag; M.tpos[g] = pos;
@@ -236,8 +318,10 @@ PVE_DEV void pve4_step_block(const Pve4Params &P, const PveState &S, const pve_o
             P4_SYNC;
             const int n = M.misc[P4M_N];
             P4_ONE {      /* virtual_lane_4[route][0], read by next tick's step() (the rewrite below keeps the list order) */
-                if (n > 0) { const int kh = M.lslot[0]; M.h.head_lane[route] = (int8_t)M.lane_of[kh]; M.h.head_j[route] = (uint8_t)(kh - M.lane_off[M.lane_of[kh]]); }
-                else { M.h.head_lane[route] = -1; M.h.head_j[route] = 0; }
+                if (route < PVE_NLANE) {      /* (lane_num = 8 has 16 routes; step() reads the heads of routes 0-7 only) */
+                    if (n > 0) { const int kh = M.lslot[0]; M.h.head_lane[route] = (int8_t)M.lane_of[kh]; M.h.head_j[route] = (uint8_t)(kh - M.lane_off[M.lane_of[kh]]); }
+                    else { M.h.head_lane[route] = -1; M.h.head_j[route] = 0; }
+                }
             }
             /* the vehicles of this route, in lane order */
             for (int k = M.lane_off[i]; k < M.lane_off[i + 1]; ++k) {
@@ -248,7 +332,7 @@ PVE_DEV void pve4_step_block(const Pve4Params &P, const PveState &S, const pve_o
                     P4_SYNC;
                     const int idx = M.misc[P4M_IDX];
                     const double ego0 = M.lpos[idx];
-                    if (route % 3 == 0) {                                                         /* TIS:1301-1319: the rewrite, kept for later agents */
+                    if (NLN == 4 && route % 3 == 0) {                                             /* TIS:1301-1319: the rewrite, kept for later agents */
                         const int tag = P.l2l_1[route];
                         P4_PAR(s, n) {
                             if (M.ltag[s] == tag) {
@@ -323,8 +407,13 @@ PVE_DEV void pve4_step_block(const Pve4Params &P, const PveState &S, const pve_o
                         M.js[k] += fabs(M.jerk[k] / P.dt);                                        /* TIS:321 */
                         if (s0 >= 0) {                                                            /* TIS:322-334 */
                             double x0, y0, x1, y1;
-                            pve4_world_xy(P, M.p[k], i, m, &x0, &y0);
-                            pve4_world_xy(P, M.p[k0], M.lane_of[k0], M.intent[k0], &x1, &y1);
+                            if (NLN == 4) {
+                                pve4_world_xy(P, M.p[k], i, m, &x0, &y0);
+                                pve4_world_xy(P, M.p[k0], M.lane_of[k0], M.intent[k0], &x1, &y1);
+                            } else {
+                                pve8_world_xy(P, M.p[k], i, m, &x0, &y0);
+                                pve8_world_xy(P, M.p[k0], M.lane_of[k0], M.intent[k0], &x1, &y1);
+                            }
                             const double dx = x1 - x0, dy = y1 - y0;
                             if (sqrt(dx * dx + dy * dy) < P.thr) { M.coll[k] += 1; M.coll[k0] += 1; }
                         }
@@ -364,15 +453,20 @@ PVE_DEV void pve4_step_block(const Pve4Params &P, const PveState &S, const pve_o
         int surv = 0, nctrl = 0;
         for (int k = 0; k < V; ++k) if (!M.del[k]) { ++surv; nctrl += M.ctl[k]; }
         int granted = 0, pos = 0, k = 0;
-        for (int i = 0; i < PVE4_NL; ++i) {
+        for (int i = 0; i < PVE4_NLX; ++i) {
             int cnt = 0;
             for (; k < M.lane_off[i + 1]; ++k) if (!M.del[k]) { M.newpos[k] = (uint16_t)pos++; ++cnt; }
             M.spawn[i] = 0;
             if (tick >= M.h.next_spawn[i] && cnt < 255) {                                         /* TIS:379 */
                 if (surv + granted < P.VC && surv + granted < PVE4_LC) {
                     M.spawn[i] = 1 + pos;                         /* slot + 1 */
-                    M.spawn_int[i] = M.h.pad_[0] % 3;             /* TIS:387: intention_re % 3 */
-                    M.h.pad_[0] = (uint8_t)((M.h.pad_[0] + 1) % 3);
+                    if (NLN == 4) {
+                        M.spawn_int[i] = M.h.pad_[0] % 3;         /* TIS:387: intention_re % 3 */
+                        M.h.pad_[0] = (uint8_t)((M.h.pad_[0] + 1) % 3);
+                    } else {                                      /* TIS:390: intention[i][random.randint(0, 1)], the draw is an input */
+                        const int dr = draws ? (int)(draws[((size_t)b * P.K + M.h.veh_rec[i]) * PVE_NLANE + i] & 1) : 0;
+                        M.spawn_int[i] = P.int8[i][dr];
+                    }
                     M.spawn_uid[i] = M.h.id_seq + granted;        /* TIS:433 */
                     ++pos; ++cnt; ++granted;
                     const int rec = (int)M.h.veh_rec[i] + 1;      /* TIS:430 */
@@ -476,7 +570,7 @@ PVE_DEV void pve4_step_block(const Pve4Params &P, const PveState &S, const pve_o
                 for (int c = 0; c < PVE_OBS_W; ++c) rows_cur[(size_t)M.newpos[k] * PVE_OBS_W + c] = rows_new[(size_t)k * PVE_OBS_W + c];
         }
     }
-    P4_PAR(i, PVE4_NL) {
+    P4_PAR(i, PVE4_NLX) {
         if (M.spawn[i]) {                                                                         /* TIS:395-427 */
             const int np = M.spawn[i] - 1, it = M.spawn_int[i];
             const size_t o = vbase + (size_t)np;

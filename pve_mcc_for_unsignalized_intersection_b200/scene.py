@@ -169,10 +169,14 @@ class BatchedScene:
                 "small_smem_bytes": out[4]}
 
     # ---- reset: TrafficInteraction(arrive_time, ...) TIS:195-220 --------------------------
-    def reset(self, arrive_time=None, warmup=True, spawn_ticks=None):
+    def reset(self, arrive_time=None, warmup=True, spawn_ticks=None, intention_draws=None):
         """``arrive_time``: float64 seconds ``[K, 12]`` (shared) or ``[B, K, 12]`` (per intersection),
         the reference's ``arvTimeNewVeh`` table.  ``warmup`` advances each intersection to its first
-        arrival like the reference constructor (TIS:214-220)."""
+        arrival like the reference constructor (TIS:214-220).
+
+        ``lane_num=8`` only: ``intention_draws`` uint8 ``[K, 8]`` or ``[B, K, 8]``, entry ``[k][i]`` in {0, 1} = what the
+        reference's ``random.randint(0, 1)`` returns for the k-th arrival of lane ``i`` (TIS:390; the reference seeds from
+        OS entropy, so the draws are an input here).  Default: drawn with ``numpy.random.default_rng(0)``."""
         if spawn_ticks is None:
             arr = np.asarray(arrive_time, dtype=np.float64)
             if arr.ndim == 2:
@@ -182,10 +186,23 @@ class BatchedScene:
                 ticks = np.broadcast_to(ticks, (self.B,) + ticks.shape[1:])
         else:
             ticks = np.asarray(spawn_ticks, dtype=np.int32)
-        if self.cfg.lane_num == 4:
-            assert ticks.shape[2] == 4, "lane_num=4 takes arrival tables with 4 columns, got %r" % (ticks.shape,)
-            never = np.full(ticks.shape[:2] + (NLANE - 4,), 2**31 - 1, dtype=np.int32)      # lanes 4..11 do not exist
+        nl = self.cfg.lane_num
+        if nl != NLANE:
+            assert ticks.shape[2] == nl, "lane_num=%d takes arrival tables with %d columns, got %r" % (nl, nl, ticks.shape)
+            never = np.full(ticks.shape[:2] + (NLANE - nl,), 2**31 - 1, dtype=np.int32)     # lanes nl..11 do not exist
             ticks = np.concatenate([ticks, never], axis=2)
+        if nl == 8:
+            if intention_draws is None:
+                dr = np.random.default_rng(0).integers(0, 2, size=(self.B, ticks.shape[1], 8), dtype=np.uint8)
+            else:
+                dr = np.asarray(intention_draws, dtype=np.uint8)
+                if dr.ndim == 2:
+                    dr = np.broadcast_to(dr[None], (self.B,) + dr.shape)
+            assert dr.shape[0] == self.B and dr.shape[1] >= ticks.shape[1] and dr.shape[2] == 8, dr.shape
+            full = np.zeros((self.B, ticks.shape[1], NLANE), np.uint8)
+            full[:, :, :8] = dr[:, :ticks.shape[1]]
+            self._draws = torch.from_numpy(full).to(self.device)
+            self._check(self.lib.pve_set_intention_draws(self._h, self._draws.data_ptr()))
         assert ticks.shape[0] == self.B and ticks.shape[2] == NLANE, ticks.shape
         assert ticks.shape[1] < 65536, "arrival tables are limited to 65535 rows per lane"
         self._spawn = torch.from_numpy(np.ascontiguousarray(ticks)).to(self.device)

@@ -25,7 +25,7 @@ def build_emul(force=False):
             and os.path.getmtime(LIB) >= max(os.path.getmtime(f) for f in SOURCES)):
         return LIB
     os.makedirs(os.path.dirname(LIB), exist_ok=True)
-    cmd = ["/usr/bin/g++", "-x", "c++", "-std=c++17", "-O2", "-g", "-fPIC", "-shared", "-ffp-contract=off",
+    cmd = ["/usr/bin/g++", "-x", "c++", "-std=c++17", "-O2", "-g", "-fPIC", "-shared", "-ffp-contract=off", "-fno-strict-aliasing",
            "-DPVE_HOST_EMULATION", "-Wall", "-Wno-unknown-pragmas", "-I", INCLUDE, "-I", CSRC,
            SOURCES[0], "-o", LIB, "-lm"]
     res = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)

@@ -23,6 +23,17 @@ def test_free_running_lane4_matches_oracle():
     assert E.free_run4("cuda", 4, 600, 300, seed=8, vm=6) > 1500
 
 
+@pytest.mark.parametrize("name", E.ROLLOUTS8)
+def test_golden_rollout8_direct(name):
+    scene = E.run_golden("cuda", name, lanes=8)
+    assert scene.backend == "cuda-sm_100a" and scene.launch_info["dual"] is False
+
+
+def test_free_running_lane8_matches_oracle():
+    assert E.free_run4("cuda", 6, 1000, 300, seed=6, lanes=8) > 9000
+    assert E.free_run4("cuda", 4, 500, 300, seed=9, vm=6, lanes=8) > 1500
+
+
 def test_lane4_batch_of_4096_invariants_and_sampled_oracle():
     """4,096 4-lane intersections: a strided sample is compared with the oracle row by row every tick, the whole batch
     through invariants that do not depend on its size (dense offsets, vehicle conservation, counters)."""

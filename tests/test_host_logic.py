@@ -68,7 +68,16 @@ def test_config_constants_match_the_reference_values():
     np.testing.assert_allclose(T[1], [7.5, 7.750943, 19.737992, 22.5], atol=1e-6)
     np.testing.assert_allclose(Cc[1], [15, 8.060445, -5.549381, -15], atol=1e-6)
     with pytest.raises(NotImplementedError):
-        SceneConfig(lane_num=8)
+        SceneConfig(lane_num=3)          # the reference's T-junction branch dies in its own constructor
+    c8 = SceneConfig(lane_num=8)         # TIS:100-103, 341-342
+    assert c8.lane_in() == 140.0 and c8.remove_p() == -140.0
+    np.testing.assert_allclose(c8.lane_len(), [19.634375, 20.0, 3.926875], atol=1e-9)
+    from oracle.scene8_oracle import geometry8
+    lane_in, L, T, C1, C2 = geometry8(2.5)
+    T8, C8, C28 = c8.eight_lane_tables()
+    assert (lane_in, L) == (c8.lane_in(), c8.lane_len())
+    for r in range(3):
+        assert T8[r] == T[r] and C8[r] == C1[r] and C28[r] == C2[r]
     # the oracle derives the same constants independently
     from oracle.oracle import scene_params
     op = scene_params(vm=6)

@@ -1,6 +1,6 @@
-"""CPU tier, row N3: the SOURCE of the 4-lane kernel (csrc/scene_step4.cuh), compiled as a sequential emulation, against
-rollouts of the unmodified reference scene with ``lane_num=4`` (no oracle in between) and against the 4-lane oracle
-on random tables.  The same checks run on the real CUDA build in tests/test_gpu_lane4.py."""
+"""CPU tier, row N3: the SOURCE of the 4-/8-lane kernel (csrc/scene_step4.cuh), compiled as a sequential emulation, against
+rollouts of the unmodified reference scene with ``lane_num=4`` and ``lane_num=8`` (no oracle in between) and against the
+4-/8-lane oracles on random tables.  The same checks run on the real CUDA build in tests/test_gpu_lane4.py."""
 import numpy as np
 import pytest
 import torch
@@ -10,13 +10,14 @@ from pve_mcc_for_unsignalized_intersection_b200 import SceneConfig
 from pve_mcc_for_unsignalized_intersection_b200.arrivals import synthetic_arrivals
 from pve_mcc_for_unsignalized_intersection_b200.scene import BatchedScene
 from oracle.scene4_oracle import Scene4Oracle
-from test_oracle4_golden import ROLLOUTS4, load4
+from oracle.scene8_oracle import Scene8Oracle
+from test_oracle4_golden import ROLLOUTS4, ROLLOUTS8, load4
 
 BACKEND = "emul"
 
 
-def make_scene4(backend, B, vm=5, collision_thr=2):
-    cfg = SceneConfig(vm=vm, collision_thr=collision_thr, lane_num=4)
+def make_scene4(backend, B, vm=5, collision_thr=2, lanes=4):
+    cfg = SceneConfig(vm=vm, collision_thr=collision_thr, lane_num=lanes)
     if backend == "cuda":
         return BatchedScene(B, cfg, device="cuda:0")
     from emul.build_emul import build_emul
@@ -35,10 +36,13 @@ def check_state(st, snap, b, what):
     np.testing.assert_array_equal(st["flags"][b, :V], fl, err_msg=what + " flags")
 
 
-def run_golden(backend, name):
-    z, r = load4(name)
-    scene = make_scene4(backend, 1, vm=float(z["vm"]), collision_thr=float(z["collision_thr"]))
-    scene.reset(z["table"], warmup=True)
+def run_golden(backend, name, lanes=4):
+    z, r = load4(name, lanes)
+    scene = make_scene4(backend, 1, vm=float(z["vm"]), collision_thr=float(z["collision_thr"]), lanes=lanes)
+    if lanes == 4:
+        scene.reset(z["table"], warmup=True)
+    else:
+        scene.reset(z["table"], warmup=True, intention_draws=z["draws"])
     obs_at = {int(t): k for k, t in enumerate(z["obs_ticks"])}
     rows = 0
     for t in range(int(z["n_ticks"])):
@@ -64,13 +68,14 @@ def run_golden(backend, name):
         snap = {k: r["post_" + k, t] for k in ("p", "v", "a", "jerk_sum", "collision", "step", "uid", "control", "finish", "lock",
                                                 "lock_a", "intention")}
         check_state(st, snap, 0, what)
-        np.testing.assert_array_equal(st["lane_n"][0, :4], z["t_lane_n"][t], err_msg=what)
-        np.testing.assert_array_equal(st["veh_rec"][0, :4], z["t_veh_rec"][t], err_msg=what)
-        np.testing.assert_array_equal(st["head_lane"][0], z["t_head_lane"][t], err_msg=what + " head lane")
-        np.testing.assert_array_equal(st["head_j"][0], z["t_head_j"][t], err_msg=what + " head j")
+        np.testing.assert_array_equal(st["lane_n"][0, :lanes], z["t_lane_n"][t], err_msg=what)
+        np.testing.assert_array_equal(st["veh_rec"][0, :lanes], z["t_veh_rec"][t], err_msg=what)
+        # (lane_num = 8: the device keeps the heads of routes 0-11 of 16; step() reads those of routes 0-7, TIS:1517)
+        np.testing.assert_array_equal(st["head_lane"][0], z["t_head_lane"][t][:12], err_msg=what + " head lane")
+        np.testing.assert_array_equal(st["head_j"][0], z["t_head_j"][t][:12], err_msg=what + " head j")
         assert (int(st["tick"][0]), int(st["id_seq"][0]), int(st["passed_veh"][0]), int(st["passed_step_total"][0])) == (
             int(z["t_tick"][t]), int(z["t_id_seq"][t]), int(z["t_passed_veh"][t]), int(z["t_passed_step_total"][t])), what
-        assert int(st["intention_re"][0]) == int(z["t_intention_re"][t]) % 3 and int(st["overflow"][0]) == 0, what
+        assert (lanes == 8 or int(st["intention_re"][0]) == int(z["t_intention_re"][t]) % 3) and int(st["overflow"][0]) == 0, what
         rows += len(o["reward"])
     assert rows > 3000
     return scene
@@ -81,14 +86,26 @@ def test_golden_rollout4_direct(name):
     run_golden(BACKEND, name)
 
 
-def free_run4(backend, B, density, ticks, seed, vm=5):
-    """B intersections with their own tables, random actions, against B instances of the 4-lane oracle."""
-    tabs = synthetic_arrivals(B, density, ticks * 0.1 + 30.0, seed=seed)[:, :, :4].copy()
-    scene = make_scene4(backend, B, vm=vm)
-    scene.reset(tabs, warmup=True)
-    orcs = [Scene4Oracle(vm=vm) for _ in range(B)]
-    for b, o in enumerate(orcs):
-        o.reset(tabs[b], warmup=True)
+@pytest.mark.parametrize("name", ROLLOUTS8)
+def test_golden_rollout8_direct(name):
+    run_golden(BACKEND, name, lanes=8)
+
+
+def free_run4(backend, B, density, ticks, seed, vm=5, lanes=4):
+    """B intersections with their own tables, random actions, against B instances of the 4-/8-lane oracle."""
+    tabs = synthetic_arrivals(B, density, ticks * 0.1 + 30.0, seed=seed)[:, :, :lanes].copy()
+    scene = make_scene4(backend, B, vm=vm, lanes=lanes)
+    if lanes == 4:
+        scene.reset(tabs, warmup=True)
+        orcs = [Scene4Oracle(vm=vm) for _ in range(B)]
+        for b, o in enumerate(orcs):
+            o.reset(tabs[b], warmup=True)
+    else:
+        draws = np.random.RandomState(seed + 100).randint(0, 2, size=(B,) + tabs.shape[1:]).astype(np.uint8)
+        scene.reset(tabs, warmup=True, intention_draws=draws)
+        orcs = [Scene8Oracle(vm=vm) for _ in range(B)]
+        for b, o in enumerate(orcs):
+            o.reset(tabs[b], draws[b], warmup=True)
     rng = np.random.RandomState(seed)
     n = 0
     for t in range(ticks):
@@ -118,3 +135,15 @@ def free_run4(backend, B, density, ticks, seed, vm=5):
 
 def test_free_running_lane4_matches_oracle():
     assert free_run4(BACKEND, 3, 1400, 260, seed=5) > 4000
+
+
+def test_free_running_lane8_matches_oracle():
+    assert free_run4(BACKEND, 3, 1000, 260, seed=6, lanes=8) > 4000
+
+
+def test_lane8_needs_draws_at_the_c_abi():
+    """pve_reset refuses an 8-lane scene without intention draws (the reference draws them from OS entropy, TIS:382/390)."""
+    scene = make_scene4(BACKEND, 1, lanes=8)
+    ticks = torch.zeros(1, 4, 12, dtype=torch.int32) + 5
+    rc = scene.lib.pve_reset(scene._h, ticks.data_ptr(), 4, 1, None)
+    assert rc != 0 and b"pve_set_intention_draws" in scene.lib.pve_last_error(scene._h)
