@@ -61,8 +61,8 @@ def parse():
     ap.add_argument("--envs", type=int, default=ENVS_PER_GPU, help="intersections per GPU")
     ap.add_argument("--density", type=int, default=DENSITY)
     ap.add_argument("--threads", type=int, default=0, help="CTA size override (64/128/256)")
-    ap.add_argument("--workload", default="poisson", choices=["poisson", "stress", "rollout", "train", "lane4"],
-                    help="poisson: BASELINE config 2 (default); lane4: the same on the 4-lane intersection (lane_num=4, row N3); stress: config 4; rollout: config 5 = the pretrained "
+    ap.add_argument("--workload", default="poisson", choices=["poisson", "stress", "rollout", "train", "lane4", "lane8"],
+                    help="poisson: BASELINE config 2 (default); lane4 / lane8: the same on the 4-lane / 8-lane intersection (lane_num=4 / 8, row N3); stress: config 4; rollout: config 5 = the pretrained "
                          "actor evaluated on the GPU every tick + the environment step; train: rollout + the training "
                          "loop's n-step return folding and replay writer (main.py:243-266) on the GPU every tick")
     ap.add_argument("--veh-cap", type=int, default=VEH_CAP, help="capacity class of the run (vehicle slots per intersection)")
@@ -78,10 +78,16 @@ def parse():
     return ap.parse_args()
 
 
+def lanes_of(args):
+    return {"lane4": 4, "lane8": 8}.get(args.workload, 12)
+
+
 def workload_name(args):
-    if args.workload == "lane4":
-        return ("%d four-lane intersections (lane_num=4) per GPU, synthetic Poisson arrivals %d veh/h/lane, actions U(-3,3) for "
-                "controlled vehicles and 0 for uncontrolled ones (main.py:401-405), vm=%d" % (args.envs, args.density, VM))
+    if args.workload in ("lane4", "lane8"):
+        return ("%d %d-lane intersections (lane_num=%d) per GPU, synthetic Poisson arrivals %d veh/h/lane, actions U(-3,3) for "
+                "controlled vehicles and 0 for uncontrolled ones (main.py:401-405), vm=%d%s" % (
+                    args.envs, lanes_of(args), lanes_of(args), args.density, VM,
+                    ", intention draws numpy default_rng(0) (TIS:390)" if args.workload == "lane8" else ""))
     if args.workload == "stress":
         return "stress: headway 1.0 s on all 12 lanes, all-brake policy, %d intersections per GPU" % args.envs
     if args.workload == "train":
@@ -101,7 +107,7 @@ def make_tables(args, n_envs, seed, horizon_s):
     if args.workload == "stress":
         return stress_arrivals(n_envs, horizon_s)
     tabs = synthetic_arrivals(n_envs, args.density, horizon_s, seed=seed)
-    return tabs[:, :, :4].copy() if args.workload == "lane4" else tabs
+    return tabs[:, :, :lanes_of(args)].copy() if lanes_of(args) != 12 else tabs
 
 
 # ---------------------------------------------------------------------------------------------
@@ -109,7 +115,7 @@ def make_tables(args, n_envs, seed, horizon_s):
 # ---------------------------------------------------------------------------------------------
 def cpu_port_run(args, n_envs, prime, timed_steps, warmup_steps, n_threads, seed=1234):
     """Times the oracle port: `timed_steps` ticks of `n_envs` intersections after priming."""
-    if args.workload == "lane4":
+    if args.workload in ("lane4", "lane8"):
         return cpu_port_run_lane4(args, n_envs, prime, timed_steps, warmup_steps, seed)
     from oracle.oracle import OracleScene, scene_params
     horizon = (prime + warmup_steps + timed_steps) * 0.1 + 30.0
@@ -146,13 +152,20 @@ def cpu_port_run(args, n_envs, prime, timed_steps, warmup_steps, n_threads, seed
 
 
 def cpu_port_run_lane4(args, n_envs, prime, timed_steps, warmup_steps, seed):
-    """lane_num=4: the pure-Python oracle (oracle/scene4_oracle.py), one thread, a few intersections."""
+    """lane_num=4 / 8: the pure-Python oracles (oracle/scene4_oracle.py, scene8_oracle.py), one thread, a few intersections."""
     from oracle.scene4_oracle import Scene4Oracle
+    from oracle.scene8_oracle import Scene8Oracle
     n_envs, prime, timed_steps = min(n_envs, 4), min(prime, 200), min(timed_steps, 50)
     tabs = make_tables(args, n_envs, seed, (prime + warmup_steps + timed_steps) * 0.1 + 30.0)
-    orcs = [Scene4Oracle(vm=VM) for _ in range(n_envs)]
-    for o, t in zip(orcs, tabs):
-        o.reset(t, warmup=True)
+    if args.workload == "lane4":
+        orcs = [Scene4Oracle(vm=VM) for _ in range(n_envs)]
+        for o, t in zip(orcs, tabs):
+            o.reset(t, warmup=True)
+    else:
+        orcs = [Scene8Oracle(vm=VM) for _ in range(n_envs)]
+        draws = np.random.default_rng(0).integers(0, 2, size=tabs.shape, dtype=np.uint8)
+        for o, t, d in zip(orcs, tabs, draws):
+            o.reset(t, d, warmup=True)
     rng = np.random.RandomState(seed)
     agent_steps, elapsed = 0, 0.0
     for t in range(prime + warmup_steps + timed_steps):
@@ -268,7 +281,7 @@ def traffic_child(args):
     stress = args.workload == "stress"
     veh_cap, agent_cap = (384, 320) if stress else (args.veh_cap, args.agent_cap)
     scene = BatchedScene(B, SceneConfig(vm=5 if stress else VM, zero_uncontrolled_actions=True,
-                                        lane_num=4 if args.workload == "lane4" else 12), veh_cap=veh_cap,
+                                        lane_num=lanes_of(args)), veh_cap=veh_cap,
                          agent_cap=agent_cap, device=dev, threads=args.threads)
     scene.reset(make_tables(args, B, 1000, (PRIME_TICKS + 60) * 0.1 + 30.0), warmup=True)
     gen = torch.Generator(device=dev)
@@ -293,7 +306,7 @@ def measure_traffic(args, veh_cap, agent_cap):
         return None, "ncu not found"
     # launches of pve_step_kernel before the profiled one: the reset's warm-up tick + PRIME_TICKS + 4 flushed ticks
     cmd = [ncu, "--metrics", "dram__bytes_read.sum,dram__bytes_write.sum", "--clock-control", "none", "-k",
-           "regex:pve4_step_kernel" if args.workload == "lane4" else "regex:pve_step_kernel", "-s", str(PRIME_TICKS + 5), "-c", "1",
+           "regex:pve4_step_kernel" if lanes_of(args) != 12 else "regex:pve_step_kernel", "-s", str(PRIME_TICKS + 5), "-c", "1",
            "--csv", sys.executable,
            os.path.abspath(__file__), "--traffic-child", "--envs", str(args.envs), "--density", str(args.density),
            "--workload", args.workload, "--threads", str(args.threads), "--veh-cap", str(veh_cap),
@@ -421,7 +434,7 @@ def graft_arm(args, rank, world, local_rank, veh_cap, agent_cap):
     # every slot of the action tensor is filled; the library takes the action of an uncontrolled vehicle as 0, which is
     # what the reference driver feeds (main.py:401-405)
     scene = BatchedScene(B, SceneConfig(vm=5 if (stress or rollout) else VM, zero_uncontrolled_actions=True,
-                                        lane_num=4 if args.workload == "lane4" else 12),
+                                        lane_num=lanes_of(args)),
                          veh_cap=veh_cap, agent_cap=agent_cap, device=dev, threads=args.threads,
                          neighbour_sources=args.workload == "train",
                          out_cap=B * args.out_rows_per_env if args.out_rows_per_env else None)
@@ -596,7 +609,7 @@ def graft_arm(args, rank, world, local_rank, veh_cap, agent_cap):
         # DRAM bytes of one launch: measured now by a one-launch ncu child of this script (single GPU only), else the
         # value of the newest committed capture, tagged with its file and commit
         traffic, traffic_src = None, None
-        if world == 1 and not args.no_traffic and args.workload in ("poisson", "stress", "lane4"):
+        if world == 1 and not args.no_traffic and args.workload in ("poisson", "stress", "lane4", "lane8"):
             traffic, traffic_src = measure_traffic(args, veh_cap, agent_cap)
         if traffic is None and args.envs == ENVS_PER_GPU and args.workload == "poisson":
             why = traffic_src
@@ -619,7 +632,7 @@ def graft_arm(args, rank, world, local_rank, veh_cap, agent_cap):
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src,
                          "peak_source": peak_src,
-                         "kernel": "pve4_step_kernel" if args.workload == "lane4" else "pve_step_kernel",
+                         "kernel": "pve4_step_kernel" if lanes_of(args) != 12 else "pve_step_kernel",
                          "kernel_ms_per_launch": my_kern_ms / K,
                          "algorithmic_bytes_per_launch": alg_bytes / K},
             # kernels inside the timed region of `value`: one step kernel per tick (+ one actor kernel in a rollout)
@@ -628,7 +641,7 @@ def graft_arm(args, rank, world, local_rank, veh_cap, agent_cap):
             # + pve_order_kernel, launched by every 32nd step since reset (the warm-up tick inside reset is step 0)
             # per tick: the step (two concurrent kernels in dual mode; offsets + step + group sums on the 4-lane path), + the actor
             # kernel in a rollout, + target actor x 2, mark, gather, critic, plan, scan, fold in a training rollout
-            "gpu_launches": (3 * K if args.workload == "lane4" else
+            "gpu_launches": (3 * K if lanes_of(args) != 12 else
                              K * ((2 if scene.launch_info["dual"] else 1) + (1 if actor is not None else 0) + (8 if folder is not None else 0))
                              + order_launches),
             "clocks": sampler.result(),

@@ -245,7 +245,12 @@ int32_t pve_config_bytes(void);
  * vehicle at once (model_agent_maddpg.py:23-49: LN28 -> Dense64 -> LN -> ReLU -> Dense64 -> LN ->
  * ReLU -> Dense1 -> 3 tanh, fp32).  `weights_host`: PVE_ACTOR_FLOATS floats in this order:
  *   LayerNorm gamma[28], beta[28]; dense kernel[28][64], bias[64]; LayerNorm_1 gamma[64], beta[64];
- *   dense_1 kernel[64][64], bias[64]; LayerNorm_2 gamma[64], beta[64]; dense_2 kernel[64], bias[1]. */
+ *   dense_1 kernel[64][64], bias[64]; LayerNorm_2 gamma[64], beta[64]; dense_2 kernel[64], bias[1].
+ *
+ * A handle is immutable once created (weights are fixed; a new network is a new handle) and carries the work counters of
+ * its kernel: launches of ONE handle must be ordered on one stream (or by events); different handles are independent.
+ * Everything derived from the weights (packed fragments, the action of the all-zero row) is complete when
+ * pve_actor_create returns. */
 #define PVE_ACTOR_FLOATS 6393
 typedef struct pve_actor pve_actor;
 int32_t pve_actor_create(const float *weights_host, int32_t n_floats, int32_t device, pve_actor **out);

@@ -1260,6 +1260,13 @@ struct pve_actor {
     float *zero_dev;             /* [28] zeros + [1] the action of an all-zero row (a missing neighbour, TIS:1334) */
 };
 
+#ifndef PVE_HOST_EMULATION
+static cudaError_t launch_actor(pve_actor *a, const float *rows, const pve_veh_meta *meta, const int32_t *n_veh,
+                                const float *noise, float noise_scale, float *actions, int slots_per_env, int n_env,
+                                long long n_slots, pve_stream_t stream, const int32_t *limit_dev = nullptr, int limit_mult = 1,
+                                const uint8_t *mask = nullptr, int slot_step = 1);
+#endif
+
 int32_t pve_actor_create(const float *weights_host, int32_t n_floats, int32_t device, pve_actor **out) {
     if (!weights_host || !out || n_floats != PVE_ACTOR_FLOATS) return PVE_EINVAL;
 #ifdef PVE_HOST_EMULATION
@@ -1292,8 +1299,15 @@ int32_t pve_actor_create(const float *weights_host, int32_t n_floats, int32_t de
             && cudaMemcpy(a->pw_dev, packed, sizeof(uint32_t) * PVM_WORDS, cudaMemcpyHostToDevice) == cudaSuccess
             && cudaMemset(a->ticket, 0, 2 * sizeof(int)) == cudaSuccess;
     free(packed);
+    /* the action of the all-zero row of a missing neighbour (TIS:1334), once per network and finished before the handle
+     * is handed out, so that pushes on any stream may read it (the weights of a handle never change) */
+    ok = ok && cudaMalloc((void **)&a->zero_dev, 32 * sizeof(float)) == cudaSuccess
+            && cudaMemset(a->zero_dev, 0, 32 * sizeof(float)) == cudaSuccess
+            && launch_actor(a, a->zero_dev, nullptr, nullptr, nullptr, 0.f, a->zero_dev + 28, PVA_TILE, 1, 1, nullptr,
+                            nullptr, 1, nullptr, 1) == cudaSuccess
+            && cudaDeviceSynchronize() == cudaSuccess;
     if (!ok) {
-        cudaFree(a->w_dev); cudaFree(a->pw_dev); cudaFree(a->ticket); free(a);
+        cudaFree(a->w_dev); cudaFree(a->pw_dev); cudaFree(a->ticket); cudaFree(a->zero_dev); free(a);
         cudaGetLastError();
         return PVE_ECUDA;
     }
@@ -1316,8 +1330,8 @@ void pve_actor_destroy(pve_actor *a) {
 #ifndef PVE_HOST_EMULATION
 static cudaError_t launch_actor(pve_actor *a, const float *rows, const pve_veh_meta *meta, const int32_t *n_veh,
                                 const float *noise, float noise_scale, float *actions, int slots_per_env, int n_env,
-                                long long n_slots, pve_stream_t stream, const int32_t *limit_dev = nullptr, int limit_mult = 1,
-                                const uint8_t *mask = nullptr, int slot_step = 1) {
+                                long long n_slots, pve_stream_t stream, const int32_t *limit_dev, int limit_mult,
+                                const uint8_t *mask, int slot_step) {
     if (a->use_mma) {
         const int blocks = n_env < a->blocks_mma ? n_env : a->blocks_mma;
         pve_actor_mma_kernel<<<blocks, PVM_THREADS, PVM_SMEM_BYTES, stream>>>(a->pw_dev, rows, meta, n_veh, noise, noise_scale,
@@ -1587,13 +1601,7 @@ int32_t pve_nstep_push_scene(pve_nstep *f, pve_scene *s, const pve_outputs *O, d
         }
         f->scene_slots = slots;
     }
-    if (!target_actor->zero_dev) {      /* the action of the all-zero row of a missing neighbour (TIS:1334): once per network */
-        if (cudaMalloc((void **)&target_actor->zero_dev, 32 * sizeof(float)) != cudaSuccess) { cudaGetLastError(); return PVE_ENOMEM; }
-        if (cudaMemsetAsync(target_actor->zero_dev, 0, 32 * sizeof(float), stream) != cudaSuccess
-            || launch_actor(target_actor, target_actor->zero_dev, nullptr, nullptr, nullptr, 0.f, target_actor->zero_dev + 28,
-                            PVA_TILE, 1, 1, stream) != cudaSuccess)
-            return PVE_ECUDA;
-    }
+    if (!target_actor->zero_dev) return PVE_ESTATE;      /* computed by pve_actor_create */
     const int32_t *n_rows_dev = O->agent_offset + B;
     const long long rows7 = f->out_cap * PVE_OBS_H;
     if (rows7 > 0x7fffffffLL || (long long)slots > 0x7fffffffLL) return PVE_EINVAL;

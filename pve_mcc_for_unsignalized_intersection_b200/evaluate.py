@@ -94,7 +94,8 @@ def batch_test(model_dir, data_dir, out_path=None, densities=DENSITIES, lane_num
     """main.py:543-583: every ``arvTimeNewVeh_new_<density>_<lane_num>.mat`` of ``data_dir`` with the checkpoint
     of ``model_dir``; writes the reference's ``*_batch_test_result_12_v1.txt`` lines to ``out_path``."""
     if lane_num != NLANE:
-        raise NotImplementedError("only the 12-lane intersection is built (SURVEY.md section 8, row N3 is open)")
+        raise NotImplementedError("batch_test evaluates the shipped 12-lane checkpoint on the 12-lane arrival files (the "
+                                  "reference ships neither for lane_num 4 / 8); use BatchedScene(SceneConfig(lane_num=...)) directly")
     weights = ActorWeights.from_checkpoint(model_dir)
     names = ["arvTimeNewVeh_new_%s_%s.mat" % (d, lane_num) for d in densities]
     tables = [load_arrivals(os.path.join(data_dir, n)) for n in names]

@@ -196,12 +196,19 @@ class NStepFolder:
             raise N.NativeError("pve_nstep_reset failed with %d" % rc)
 
     def counters(self):
-        """``num_experiences`` (replay_buffer.py:47), records added by the last push, history-slot conflicts (must
-        be 0), pushes.  Synchronises."""
+        """``num_experiences`` (replay_buffer.py:47), records added by the last push, history-slot conflicts, pushes.
+        Synchronises.  Raises if a slot conflict was ever counted (``__len__``, ``order``, ``deque`` and ``get_batch`` go
+        through here, so a corrupted memory cannot be read silently)."""
         out = (C.c_int64 * 4)()
         rc = self.lib.pve_nstep_counters(self._h, out, self._stream())
         if rc != 0:
             raise N.NativeError("pve_nstep_counters failed with %d" % rc)
+        if int(out[2]) != 0:
+            # two live vehicles of one intersection shared a history slot (uid mod uid_slots): their histories, and the
+            # replay records folded from them, are no longer the reference's -- never hand such a memory out
+            raise N.NativeError("n-step history table too small: %d slot conflicts (uid_slots must exceed the number of "
+                                "vehicles an intersection spawns during one agent's lifetime); create the folder with a "
+                                "larger uid_slots" % int(out[2]))
         return {"num_experiences": int(out[0]), "last_added": int(out[1]), "slot_conflicts": int(out[2]), "pushes": int(out[3])}
 
     def __len__(self):
