@@ -1,6 +1,6 @@
 #!/bin/bash
 # Round-2 evidence run on the GPU box: full bench, launch list, ncu --set full of the small step kernel, sanitizer.
-# Usage: tools/gpu_round2.sh [what...]   what = bench launches full stress rollout sanitizer
+# Usage: tools/gpu_round2.sh [what...]   what = bench launches full stress rollout lanes train sanitizer
 OUT=gpurun_out; mkdir -p $OUT
 WHAT=${*:-bench launches full}
 for w in $WHAT; do
@@ -18,8 +18,14 @@ stress)
   timeout 900 python bench.py --workload stress --steps 50 --warmup 5 --no-cpu-baseline > $OUT/r02_bench_stress.json 2> $OUT/r02_bench_stress.err; cut -c1-300 $OUT/r02_bench_stress.json ;;
 rollout)
   timeout 900 python bench.py --workload rollout --steps 50 --warmup 5 --no-cpu-baseline > $OUT/r02_bench_rollout.json 2> $OUT/r02_bench_rollout.err; cut -c1-300 $OUT/r02_bench_rollout.json ;;
+lanes)
+  for w in lane4 lane8; do
+    timeout 900 python bench.py --workload $w --steps 100 --warmup 5 > $OUT/r02_bench_$w.json 2> $OUT/r02_bench_$w.err; cut -c1-260 $OUT/r02_bench_$w.json
+  done ;;
+train)
+  timeout 900 python bench.py --workload train --steps 50 --warmup 5 --no-cpu-baseline --no-e2e > $OUT/r02_bench_train.json 2> $OUT/r02_bench_train.err; cut -c1-300 $OUT/r02_bench_train.json ;;
 sanitizer)
-  timeout 1500 compute-sanitizer --tool memcheck --error-exitcode 9 python -m pytest tests/test_gpu_parity_more.py -x -q -k "pipelined or two_handles or out_cap or dual" > $OUT/r02_sanitizer_memcheck.log 2>&1; echo "memcheck rc=$?"; tail -5 $OUT/r02_sanitizer_memcheck.log
+  timeout 1500 compute-sanitizer --tool memcheck --error-exitcode 9 python -m pytest tests/test_gpu_parity_more.py tests/test_gpu_lane4.py -x -q -k "pipelined or two_handles or out_cap or dual or lane8_matches or rollout8_direct" > $OUT/r02_sanitizer_memcheck.log 2>&1; echo "memcheck rc=$?"; tail -5 $OUT/r02_sanitizer_memcheck.log
   timeout 1500 compute-sanitizer --tool racecheck --error-exitcode 9 python -m pytest tests/test_gpu_parity.py -x -q -k "teacher_forced_every_tick" > $OUT/r02_sanitizer_racecheck.log 2>&1; echo "racecheck rc=$?"; tail -8 $OUT/r02_sanitizer_racecheck.log ;;
 esac
 done
