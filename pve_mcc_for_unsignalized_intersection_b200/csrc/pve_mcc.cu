@@ -23,6 +23,7 @@
 #include "actor_mma.cuh"
 #include "nstep.cuh"
 #include "critic_mma.cuh"
+#include "mlp_tc5.cuh"
 
 #ifndef PVE_HOST_EMULATION
 #include <cuda_runtime.h>
@@ -1256,7 +1257,10 @@ struct pve_actor {
     int *ticket;                 /* [2] work counter + exit counter of the kernel, zero between launches */
     int device;
     int blocks_ffma, blocks_mma; /* one resident wave of CTAs each */
-    int use_mma;                 /* default 1; env PVE_ACTOR_IMPL=ffma selects the CUDA-core kernel */
+    int use_mma;                 /* 2 = tcgen05 kernel (default), 1 = mma.sync kernel (PVE_ACTOR_IMPL=mma), 0 = CUDA cores (=ffma) */
+    uint16_t *tw_dev;            /* shared-memory image of the split weights (tcgen05 kernel) */
+    PvtVecs vecs;                /* bias / LayerNorm / last-layer vectors: a kernel parameter of the tcgen05 kernel */
+    int blocks_tc;
     float *zero_dev;             /* [28] zeros + [1] the action of an all-zero row (a missing neighbour, TIS:1334) */
 };
 
@@ -1277,13 +1281,15 @@ int32_t pve_actor_create(const float *weights_host, int32_t n_floats, int32_t de
     pve_actor *a = (pve_actor *)calloc(1, sizeof(pve_actor));
     if (!a) return PVE_ENOMEM;
     a->device = device;
-    a->use_mma = 1;
-    if (const char *impl = getenv("PVE_ACTOR_IMPL")) a->use_mma = strcmp(impl, "ffma") != 0;
+    a->use_mma = 2;
+    if (const char *impl = getenv("PVE_ACTOR_IMPL")) a->use_mma = strcmp(impl, "ffma") == 0 ? 0 : strcmp(impl, "mma") == 0 ? 1 : 2;
     int sms = 0, per_sm = 0;
     if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device) != cudaSuccess || sms <= 0) sms = 148;
     bool ok = cudaFuncSetAttribute(pve_actor_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PVA_SMEM_BYTES) == cudaSuccess
-              && cudaFuncSetAttribute(pve_actor_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PVM_SMEM_BYTES) == cudaSuccess;
+              && cudaFuncSetAttribute(pve_actor_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PVM_SMEM_BYTES) == cudaSuccess
+              && cudaFuncSetAttribute(pve_actor_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PVT_ACTOR_SMEM) == cudaSuccess;
     if (ok) {
+        a->blocks_tc = sms;                  /* one persistent CTA per SM (three groups of 128 rows + the producer warp) */
         if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pve_actor_kernel, PVA_THREADS, PVA_SMEM_BYTES) != cudaSuccess || per_sm < 1) per_sm = 1;
         a->blocks_ffma = per_sm * sms;
         if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pve_actor_mma_kernel, PVM_THREADS, PVM_SMEM_BYTES) != cudaSuccess || per_sm < 1) per_sm = 1;
@@ -1292,6 +1298,15 @@ int32_t pve_actor_create(const float *weights_host, int32_t n_floats, int32_t de
     uint32_t *packed = ok ? (uint32_t *)malloc(sizeof(uint32_t) * PVM_WORDS) : nullptr;
     ok = ok && packed;
     if (ok) pvm_pack(weights_host, packed);
+    uint16_t *image = ok ? (uint16_t *)malloc(PVT_W_BYTES) : nullptr;
+    ok = ok && image;
+    if (ok) {
+        pvt_pack(weights_host + PVA_W1, weights_host + PVA_B1, weights_host + PVA_W2, weights_host + PVA_B2, 0, image);
+        pvt_vecs_actor(weights_host, &a->vecs);
+    }
+    ok = ok && cudaMalloc((void **)&a->tw_dev, PVT_W_BYTES) == cudaSuccess
+            && cudaMemcpy(a->tw_dev, image, PVT_W_BYTES, cudaMemcpyHostToDevice) == cudaSuccess;
+    free(image);
     ok = ok && cudaMalloc((void **)&a->w_dev, sizeof(float) * PVE_ACTOR_FLOATS) == cudaSuccess
             && cudaMalloc((void **)&a->pw_dev, sizeof(uint32_t) * PVM_WORDS) == cudaSuccess
             && cudaMalloc((void **)&a->ticket, 2 * sizeof(int)) == cudaSuccess
@@ -1307,7 +1322,8 @@ int32_t pve_actor_create(const float *weights_host, int32_t n_floats, int32_t de
                             nullptr, 1, nullptr, 1) == cudaSuccess
             && cudaDeviceSynchronize() == cudaSuccess;
     if (!ok) {
-        cudaFree(a->w_dev); cudaFree(a->pw_dev); cudaFree(a->ticket); cudaFree(a->zero_dev); free(a);
+        fprintf(stderr, "pve_actor_create: %s\n", cudaGetErrorString(cudaPeekAtLastError()));
+        cudaFree(a->w_dev); cudaFree(a->pw_dev); cudaFree(a->tw_dev); cudaFree(a->ticket); cudaFree(a->zero_dev); free(a);
         cudaGetLastError();
         return PVE_ECUDA;
     }
@@ -1321,6 +1337,7 @@ void pve_actor_destroy(pve_actor *a) {
 #ifndef PVE_HOST_EMULATION
     cudaFree(a->w_dev);
     cudaFree(a->pw_dev);
+    cudaFree(a->tw_dev);
     cudaFree(a->ticket);
     cudaFree(a->zero_dev);
 #endif
@@ -1332,7 +1349,11 @@ static cudaError_t launch_actor(pve_actor *a, const float *rows, const pve_veh_m
                                 const float *noise, float noise_scale, float *actions, int slots_per_env, int n_env,
                                 long long n_slots, pve_stream_t stream, const int32_t *limit_dev, int limit_mult,
                                 const uint8_t *mask, int slot_step) {
-    if (a->use_mma) {
+    if (a->use_mma == 2) {
+        const int blocks = n_env < a->blocks_tc ? n_env : a->blocks_tc;
+        pve_actor_tc_kernel<<<blocks, PVT_THREADS_ACTOR, PVT_ACTOR_SMEM, stream>>>(a->vecs, a->tw_dev, rows, meta, n_veh, noise, noise_scale,
+                                                                                actions, slots_per_env, n_env, n_slots, a->ticket, limit_dev, limit_mult, mask, slot_step);
+    } else if (a->use_mma) {
         const int blocks = n_env < a->blocks_mma ? n_env : a->blocks_mma;
         pve_actor_mma_kernel<<<blocks, PVM_THREADS, PVM_SMEM_BYTES, stream>>>(a->pw_dev, rows, meta, n_veh, noise, noise_scale,
                                                                            actions, slots_per_env, n_env, n_slots, a->ticket, limit_dev, limit_mult, mask, slot_step);
@@ -1341,7 +1362,9 @@ static cudaError_t launch_actor(pve_actor *a, const float *rows, const pve_veh_m
         pve_actor_kernel<<<blocks, PVA_THREADS, PVA_SMEM_BYTES, stream>>>(a->w_dev, rows, meta, n_veh, noise, noise_scale,
                                                                        actions, slots_per_env, n_env, n_slots, a->ticket, limit_dev, limit_mult, mask, slot_step);
     }
-    return cudaGetLastError();
+    const cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) fprintf(stderr, "pve actor launch: %s\n", cudaGetErrorString(e));
+    return e;
 }
 #endif
 
@@ -1398,7 +1421,10 @@ struct pve_critic {
     float *w_dev;                /* flat fp32 parameters (FFMA kernel) */
     uint32_t *pw_dev;            /* split bf16 fragments + vectors (tensor-core kernel) */
     int device, blocks, blocks_mma;
-    int use_mma;                 /* default 1; env PVE_CRITIC_IMPL=ffma selects the CUDA-core kernel */
+    int use_mma;                 /* 2 = tcgen05 kernel (default), 1 = mma.sync kernel (PVE_CRITIC_IMPL=mma), 0 = CUDA cores (=ffma) */
+    uint16_t *tw_dev;            /* shared-memory image of the split weights (tcgen05 kernel) */
+    PvtVecs vecs;
+    int blocks_tc;
 };
 
 int32_t pve_critic_create(const float *weights_host, int32_t n_floats, int32_t device, pve_critic **out) {
@@ -1413,10 +1439,12 @@ int32_t pve_critic_create(const float *weights_host, int32_t n_floats, int32_t d
     c->device = device;
     int sms = 0, per_sm = 0;
     if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device) != cudaSuccess || sms <= 0) sms = 148;
-    c->use_mma = 1;
-    if (const char *impl = getenv("PVE_CRITIC_IMPL")) c->use_mma = strcmp(impl, "ffma") != 0;
+    c->use_mma = 2;
+    if (const char *impl = getenv("PVE_CRITIC_IMPL")) c->use_mma = strcmp(impl, "ffma") == 0 ? 0 : strcmp(impl, "mma") == 0 ? 1 : 2;
     bool ok = cudaFuncSetAttribute(pve_critic_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PVC_SMEM_BYTES) == cudaSuccess
-              && cudaFuncSetAttribute(pve_critic_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PVQ_SMEM_BYTES) == cudaSuccess;
+              && cudaFuncSetAttribute(pve_critic_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PVQ_SMEM_BYTES) == cudaSuccess
+              && cudaFuncSetAttribute(pve_critic_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PVT_CRITIC_SMEM) == cudaSuccess;
+    c->blocks_tc = sms;                      /* one persistent CTA per SM */
     if (ok && (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pve_critic_kernel, PVC_THREADS, PVC_SMEM_BYTES) != cudaSuccess || per_sm < 1)) per_sm = 1;
     c->blocks = per_sm * sms;
     if (ok && (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pve_critic_mma_kernel, PVQ_THREADS, PVQ_SMEM_BYTES) != cudaSuccess || per_sm < 1)) per_sm = 1;
@@ -1424,12 +1452,21 @@ int32_t pve_critic_create(const float *weights_host, int32_t n_floats, int32_t d
     uint32_t *packed = ok ? (uint32_t *)malloc(sizeof(uint32_t) * PVQ_WORDS) : nullptr;
     ok = ok && packed;
     if (ok) pvq_pack(weights_host, packed);
+    uint16_t *image = ok ? (uint16_t *)malloc(PVT_W_BYTES) : nullptr;
+    ok = ok && image;
+    if (ok) {
+        pvt_pack(weights_host + PVC_W1, weights_host + PVC_B1, weights_host + PVC_W2, weights_host + PVC_B2, 1, image);
+        pvt_vecs_critic(weights_host, &c->vecs);
+    }
+    ok = ok && cudaMalloc((void **)&c->tw_dev, PVT_W_BYTES) == cudaSuccess
+            && cudaMemcpy(c->tw_dev, image, PVT_W_BYTES, cudaMemcpyHostToDevice) == cudaSuccess;
+    free(image);
     ok = ok && cudaMalloc((void **)&c->w_dev, sizeof(float) * PVE_CRITIC_FLOATS) == cudaSuccess
             && cudaMalloc((void **)&c->pw_dev, sizeof(uint32_t) * PVQ_WORDS) == cudaSuccess
             && cudaMemcpy(c->w_dev, weights_host, sizeof(float) * PVE_CRITIC_FLOATS, cudaMemcpyHostToDevice) == cudaSuccess
             && cudaMemcpy(c->pw_dev, packed, sizeof(uint32_t) * PVQ_WORDS, cudaMemcpyHostToDevice) == cudaSuccess;
     free(packed);
-    if (!ok) { cudaFree(c->w_dev); cudaFree(c->pw_dev); free(c); cudaGetLastError(); return PVE_ECUDA; }
+    if (!ok) { fprintf(stderr, "pve_critic_create: %s\n", cudaGetErrorString(cudaPeekAtLastError())); cudaFree(c->w_dev); cudaFree(c->pw_dev); cudaFree(c->tw_dev); free(c); cudaGetLastError(); return PVE_ECUDA; }
     *out = c;
     return PVE_OK;
 #endif
@@ -1440,6 +1477,7 @@ void pve_critic_destroy(pve_critic *c) {
 #ifndef PVE_HOST_EMULATION
     cudaFree(c->w_dev);
     cudaFree(c->pw_dev);
+    cudaFree(c->tw_dev);
 #endif
     free(c);
 }
@@ -1453,7 +1491,12 @@ int32_t pve_critic_forward(pve_critic *c, const float *obs_dev, const float *act
 #else
     if (max_rows == 0) return PVE_OK;
     const long long tiles = (max_rows + PVC_TILE - 1) / PVC_TILE;              /* both kernels: 128 agents per tile */
-    if (c->use_mma) {
+    if (c->use_mma == 2) {
+        const long long ctas = (tiles + PVT_GROUPS - 1) / PVT_GROUPS;
+        const int blocks = (int)(ctas < c->blocks_tc ? ctas : c->blocks_tc);
+        pve_critic_tc_kernel<<<blocks, PVT_THREADS_CRITIC, PVT_CRITIC_SMEM, (pve_stream_t)stream_>>>(c->vecs, c->tw_dev, obs_dev, act7_dev, q_dev,
+                                                                                                  (long long)max_rows, n_rows_dev);
+    } else if (c->use_mma) {
         const int blocks = (int)(tiles < c->blocks_mma ? tiles : c->blocks_mma);
         pve_critic_mma_kernel<<<blocks, PVQ_THREADS, PVQ_SMEM_BYTES, (pve_stream_t)stream_>>>(c->pw_dev, obs_dev, act7_dev, q_dev,
                                                                                              (long long)max_rows, n_rows_dev);

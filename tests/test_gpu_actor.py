@@ -34,9 +34,10 @@ def check_actions(got, rows32, w, what):
     assert np.all(np.abs(got) <= 3.0)
 
 
-@pytest.fixture(params=["mma", "ffma"])
+@pytest.fixture(params=["tc5", "mma", "ffma"])
 def impl(request, monkeypatch):
-    """Both device implementations of the actor: tensor cores (bf16 x 3 split products, default) and fp32 FFMA."""
+    """The three device implementations of the actor: tcgen05 + tensor memory (bf16 x 3 split products, default), the same
+    products on mma.sync, and fp32 FFMA."""
     monkeypatch.setenv("PVE_ACTOR_IMPL", request.param)
     return request.param
 

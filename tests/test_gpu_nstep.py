@@ -40,9 +40,10 @@ def realistic_obs(rng, n):
     return obs
 
 
-@pytest.fixture(params=["mma", "ffma"])
+@pytest.fixture(params=["tc5", "mma", "ffma"])
 def critic_impl(request, monkeypatch):
-    """Both device implementations of the critic: tensor cores (bf16 x 3 split products, default) and fp32 FFMA."""
+    """The three device implementations of the critic: tcgen05 + tensor memory (bf16 x 3 split products, default), the
+    same products on mma.sync, and fp32 FFMA."""
     monkeypatch.setenv("PVE_CRITIC_IMPL", request.param)
     return request.param
 
@@ -242,7 +243,7 @@ def test_new_episode_keeps_the_memory_and_drops_the_buffers():
     assert n_prev > 1000 and folder.counters()["slot_conflicts"] == 0
 
 
-@pytest.mark.parametrize("impl", ["mma", "ffma"])
+@pytest.mark.parametrize("impl", ["tc5", "mma", "ffma"])
 def test_distinct_row_bootstrap_equals_the_seven_row_bootstrap(impl, monkeypatch):
     monkeypatch.setenv("PVE_ACTOR_IMPL", impl)             # both device implementations of the two networks
     monkeypatch.setenv("PVE_CRITIC_IMPL", impl)
