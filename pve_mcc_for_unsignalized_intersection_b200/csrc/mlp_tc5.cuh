@@ -52,7 +52,8 @@ struct PvtVecs {
 #define PVT_TILE 128
 #define PVT_TMEM_COLS 256
 #define PVT_RING 2048
-#define PVT_BATCH 2                                        /* intersections per ticket */
+#define PVT_BATCH 3                                        /* intersections per ticket */
+#define PVT_PCHUNKS 12                                     /* 32-slot chunks a producer loads at once */
 #define PVT_PRODUCERS 4                                    /* the register file is handed out four warps at a time: 13 warps cost 16 */
 #define PVT_THREADS_ACTOR (PVT_GROUPS * 128 + PVT_PRODUCERS * 32)
 #define PVT_THREADS_CRITIC (PVT_GROUPS * 128)
@@ -117,13 +118,26 @@ __device__ __forceinline__ uint64_t pvt_desc(uint32_t saddr, uint32_t kchunk) {
 }
 /* D (fp32, TMEM) (+)= A (bf16, smem) x B (bf16, smem); M = 128, N = 64 */
 #define PVT_IDESC ((1u << 4) | (1u << 7) | (1u << 10) | ((64u >> 3) << 17) | ((128u >> 4) << 24))
+/* The issuing warp runs converged with warp-uniform operands and elects one lane per instruction (the same lane every
+ * time), so that the descriptors live in uniform registers: issued from a single diverged thread, every tcgen05.mma
+ * cost ~16 instructions and ~100 cycles (a broadcast loop over the active lanes), 2 us of a 7.5 us round. */
+__device__ __forceinline__ bool pvt_elect() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}\n" : "=r"(pred));
+    return pred != 0;
+}
 __device__ __forceinline__ void pvt_mma(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t accumulate) {
-    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-                 "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n"
-                 :: "r"(tmem_d), "l"(da), "l"(db), "r"(PVT_IDESC), "r"(accumulate) : "memory");
+#ifdef PVT_X_NOMMA                      /* experiment: the kernel without its tensor-core work (results are garbage) */
+    return;
+#endif
+    if (pvt_elect())
+        asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                     "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n"
+                     :: "r"(tmem_d), "l"(da), "l"(db), "r"(PVT_IDESC), "r"(accumulate) : "memory");
 }
 __device__ __forceinline__ void pvt_commit(uint32_t bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(bar) : "memory");
+    if (pvt_elect())
+        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(bar) : "memory");
 }
 __device__ __forceinline__ void pvt_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void pvt_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -133,12 +147,11 @@ __device__ __forceinline__ void pvt_gsync(int id) { asm volatile("bar.sync %0, 1
 #define PVT_TIMEOUT(t0) do { if (clock64() - (t0) > 4000000000LL) __trap(); } while (0)
 __device__ __forceinline__ void pvt_wait(uint32_t bar, uint32_t parity) {
     uint32_t done;
-    const long long t0 = clock64();
-    for (;;) {
+    for (int spins = 0;; ++spins) {
         asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
                      : "=r"(done) : "r"(bar), "r"(parity) : "memory");
         if (done) break;
-        PVT_TIMEOUT(t0);
+        if (spins > (1 << 24)) __trap();
     }
 }
 #define PVT_LD16(r, o, taddr)                                                                                          \
@@ -175,17 +188,20 @@ __device__ __forceinline__ void pvt_store_chunk(unsigned char *a, int a_split, i
     *reinterpret_cast<uint4 *>(p + 2 * a_split) = l;
 }
 
+#ifndef PVT_X_PRODUCTS
+#define PVT_X_PRODUCTS 6               /* experiment knob: fewer products (results lose accuracy) */
+#endif
 /* one thread: the six split products over KSTEPS K = 16 slices, small terms first (as pvm_kstep);
- * a / b = shared-memory byte addresses of split 0, chunk 0 */
+ * a / b = descriptors of split 0, chunk 0 */
 template <int KSTEPS>
-__device__ __forceinline__ void pvt_issue(uint32_t tmem, uint32_t a, uint32_t a_split, uint32_t b, uint32_t b_split, bool fresh) {
+__device__ __forceinline__ void pvt_issue(uint32_t tmem, uint64_t a, uint32_t a_split, uint64_t b, uint32_t b_split, bool fresh) {
 #pragma unroll
-    for (int p = 0; p < 6; ++p) {
+    for (int p = 0; p < PVT_X_PRODUCTS; ++p) {
         const int sa = p == 0 ? 2 : (p == 1 || p == 3) ? 1 : 0;      /* al bh, am bm, ah bl, am bh, ah bm, ah bh */
         const int sb = (p == 0 || p == 3 || p == 5) ? 0 : (p == 1 || p == 4) ? 1 : 2;
 #pragma unroll
         for (int kk = 0; kk < KSTEPS; ++kk)
-            pvt_mma(tmem, pvt_desc(a + sa * a_split + kk * 4096, 2048), pvt_desc(b + sb * b_split + kk * 2048, 1024),
+            pvt_mma(tmem, a + ((sa * a_split + kk * 4096) >> 4), b + ((sb * b_split + kk * 2048) >> 4),      /* start-address field */
                     (!fresh || (p | kk) != 0) ? 1u : 0u);
     }
 }
@@ -208,14 +224,21 @@ __device__ __forceinline__ void pvt_ln_relu(float (&v)[64], const float *gamma, 
     for (int j = 0; j < 64; ++j) v[j] = fmaxf(fmaf(v[j], rs * gamma[j], beta[j]), 0.f);
 }
 
+#ifdef PVT_X_TRACE                     /* experiment: clock64 stamps of the first rounds of the first CTAs (tools/actor_trace.py) */
+__device__ long long pvt_trace_buf[8 * 3 * 16 * 12];
+#define PVT_STAMP(G, ev) do { if ((G).tr && (G).gt == 0) (G).tr[ev] = clock64(); } while (0)
+#else
+#define PVT_STAMP(G, ev) do { } while (0)
+#endif
 /* what a group needs for its rounds */
 struct PvtGroup {
     unsigned char *a;                  /* the group's operand buffer: [3 splits][chunks][128 rows][16 B] */
-    uint32_t a_addr, w_addr, ones_addr;/* shared-memory byte addresses: operand buffer, weight image, ones block */
+    uint64_t da, dw1, dw2, dwb, dones; /* descriptors (split 0, chunk 0): operand buffer, W1, W2, bias slice, ones block */
     uint32_t taddr;                    /* tensor memory: the group's 64 columns, this warp's 32 lanes */
     uint32_t bar, wbar, parity;
     int id, gt;                        /* named barrier of the group, thread in group */
-    bool w_ready;
+    bool w_ready, lead;                /* lead: this warp issues the group's products (warp-uniform by construction) */
+    long long *tr;                     /* PVT_X_TRACE: this round's stamps */
 };
 
 /* One round: row `src` (28 floats, or nullptr for a padding row) of every thread of the group through the network.
@@ -252,42 +275,48 @@ __device__ __forceinline__ float pvt_round(const PvtVecs &V, PvtGroup &G, const 
             pvt_store_chunk(G.a, A_SPLIT, 9, G.gt, y + 8);
         }
     }
+    PVT_STAMP(G, 2);
     pvt_fence_async_smem();            /* generic-proxy stores -> visible to the tensor core's async proxy */
     pvt_fence_before();                /* last round's tcgen05.ld of these TMEM columns is ordered before the barrier */
     pvt_gsync(G.id);
     const uint32_t tmem = G.taddr & 0x0000FFFFu;                       /* lane 0 of the group's columns */
-    if (G.gt == 0) {
+    if (G.lead) {                      /* the group's first warp, converged */
         pvt_fence_after();
         if (!G.w_ready) { pvt_wait(G.wbar, 0); G.w_ready = true; }
-        pvt_issue<2>(tmem, G.a_addr, A_SPLIT, G.w_addr, PVT_W1_SPLIT, true);
+        PVT_STAMP(G, 3);
+        pvt_issue<2>(tmem, G.da, A_SPLIT, G.dw1, PVT_W1_SPLIT, true);
         pvt_commit(G.bar);
+        PVT_STAMP(G, 4);
     }
     pvt_wait(G.bar, G.parity); G.parity ^= 1u;
+    PVT_STAMP(G, 5);
     __syncwarp();
     pvt_fence_after();
     float v[64];
     pvt_load_row(v, G.taddr);
+    PVT_STAMP(G, 6);
     pvt_ln_relu(v, V.ln1_g, V.ln1_b);                          /* NET:28-32 / 60-64 */
 #pragma unroll
     for (int c = 0; c < 8; ++c) pvt_store_chunk(G.a, A_SPLIT, c, G.gt, v + 8 * c);
+    PVT_STAMP(G, 7);
     pvt_fence_async_smem();
     pvt_fence_before();
     pvt_gsync(G.id);
-    if (G.gt == 0) {
+    if (G.lead) {
         pvt_fence_after();
-        const uint32_t w2 = G.w_addr + 3 * PVT_W1_SPLIT;
+        PVT_STAMP(G, 8);
         if (CRITIC) {
-            pvt_issue<5>(tmem, G.a_addr, A_SPLIT, w2, W2_SPLIT, true);
+            pvt_issue<5>(tmem, G.da, A_SPLIT, G.dw2, W2_SPLIT, true);
         } else {                       /* the second bias: ones block x (low, middle, high) of the bias slice */
-            const uint32_t wb = w2 + 3 * W2_SPLIT;
-            pvt_mma(tmem, pvt_desc(G.ones_addr, 2048), pvt_desc(wb + 2 * 2048, 1024), 0u);
-            pvt_mma(tmem, pvt_desc(G.ones_addr, 2048), pvt_desc(wb + 2048, 1024), 1u);
-            pvt_issue<4>(tmem, G.a_addr, A_SPLIT, w2, W2_SPLIT, false);
-            pvt_mma(tmem, pvt_desc(G.ones_addr, 2048), pvt_desc(wb, 1024), 1u);
+            pvt_mma(tmem, G.dones, G.dwb + ((2 * 2048) >> 4), 0u);
+            pvt_mma(tmem, G.dones, G.dwb + (2048 >> 4), 1u);
+            pvt_issue<4>(tmem, G.da, A_SPLIT, G.dw2, W2_SPLIT, false);
+            pvt_mma(tmem, G.dones, G.dwb, 1u);
         }
         pvt_commit(G.bar);
     }
     pvt_wait(G.bar, G.parity); G.parity ^= 1u;
+    PVT_STAMP(G, 9);
     __syncwarp();
     pvt_fence_after();
     pvt_load_row(v, G.taddr);
@@ -305,7 +334,7 @@ __device__ __forceinline__ float pvt_round(const PvtVecs &V, PvtGroup &G, const 
  * Ends with a CTA-wide barrier; G is filled for threads of the groups (warp < 4 PVT_GROUPS). */
 template <bool CRITIC>
 __device__ __forceinline__ void pvt_setup(unsigned char *smem, const uint16_t *__restrict__ PW, PvtCtrl *C, PvtGroup &G, uint32_t &tmem) {
-    const int tid = threadIdx.x, warp = tid >> 5;
+    const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, tid >> 5, 0);           /* provably warp-uniform */
     unsigned char *const abuf = smem + PVT_W_BYTES + (CRITIC ? 0 : PVT_ONES_BYTES);
     if (tid == 0) {
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(pvt_saddr(&C->wbar)) : "memory");
@@ -316,7 +345,7 @@ __device__ __forceinline__ void pvt_setup(unsigned char *smem, const uint16_t *_
         asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(pvt_saddr(&C->wbar)), "r"((uint32_t)PVT_W_BYTES) : "memory");
         asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                      :: "r"(pvt_saddr(smem)), "l"(PW), "r"((uint32_t)PVT_W_BYTES), "r"(pvt_saddr(&C->wbar)) : "memory");
-        C->q_tail = 0; C->q_head = 0; C->q_free = 0; C->q_done = 0; C->p_seq = 0; C->p_commit = 0; C->p_done = 0;
+        C->q_tail = 0; C->q_head = 0; C->q_free = 0; C->q_done = 0; C->p_seq = PVT_PRODUCERS; C->p_commit = 0; C->p_done = 0;
     }
     if (!CRITIC)                       /* ones block: [2 chunks][128 rows][8 bf16], element (row, 0) = 1 */
         for (int i = tid; i < PVT_ONES_BYTES / 16; i += blockDim.x)
@@ -333,10 +362,12 @@ __device__ __forceinline__ void pvt_setup(unsigned char *smem, const uint16_t *_
     const int g = warp >> 2;
     if (g < PVT_GROUPS) {
         G.a = abuf + g * 3 * PVT_A_SPLIT(CRITIC);
-        G.a_addr = pvt_saddr(G.a); G.w_addr = pvt_saddr(smem); G.ones_addr = pvt_saddr(smem + PVT_W_BYTES);
+        const uint32_t w = pvt_saddr(smem), w2 = w + 3 * PVT_W1_SPLIT;
+        G.da = pvt_desc(pvt_saddr(G.a), 2048); G.dw1 = pvt_desc(w, 1024); G.dw2 = pvt_desc(w2, 1024);
+        G.dwb = pvt_desc(w2 + 3 * 8192, 1024); G.dones = pvt_desc(w + PVT_W_BYTES, 2048);
         G.taddr = tmem + 64u * g + ((uint32_t)((warp & 3) * 32) << 16);
         G.bar = pvt_saddr(&C->mbar[g]); G.wbar = pvt_saddr(&C->wbar); G.parity = 0;
-        G.id = 1 + g; G.gt = tid & 127; G.w_ready = false;
+        G.id = 1 + g; G.gt = tid & 127; G.w_ready = false; G.lead = (warp & 3) == 0; G.tr = nullptr;
     }
 }
 __device__ __forceinline__ void pvt_teardown(uint32_t tmem) {
@@ -367,7 +398,11 @@ pve_actor_tc_kernel(const __grid_constant__ PvtVecs V, const uint16_t *__restric
     if (warp < 4 * PVT_GROUPS) {
         /* ---- a group: claim up to 128 queued slots, evaluate, store ---- */
         const int g = warp >> 2;
-        for (;;) {
+        for (int round = 0;; ++round) {
+#ifdef PVT_X_TRACE
+            G.tr = (blockIdx.x < 8 && round < 16) ? pvt_trace_buf + ((blockIdx.x * 3 + g) * 16 + round) * 12 : nullptr;
+#endif
+            PVT_STAMP(G, 0);
             if (G.gt == 0) {
                 int h, n;
                 const long long t0 = clock64();
@@ -393,45 +428,54 @@ pve_actor_tc_kernel(const __grid_constant__ PvtVecs V, const uint16_t *__restric
             const long long gs = valid ? (long long)ring[(head + G.gt) & (PVT_RING - 1)] : 0;
             pvt_gsync(G.id);                                         /* the ring entries and the claim have been read */
             if (G.gt == 0) atomicAdd(&C->q_free, n_valid);
+            PVT_STAMP(G, 1);
             const float o = pvt_round<false>(V, G, valid ? rows + gs * PVE_OBS_W : nullptr, nullptr);
             if (valid) {
                 float act = 3.f * tanhf(o);                                  /* NET:40-47 */
                 if (noise) act += noise_scale * noise[gs];                   /* main.py:44 */
                 actions[gs] = act;
             }
+            PVT_STAMP(G, 10);
         }
     } else {
         /* ---- a producer warp: controlled slots of PVT_BATCH intersections per ticket -> ring.  The four producers load
          * concurrently and append in the order in which they drew their tickets (p_seq / p_commit). ---- */
         const int cpe = (slots_per_env + 31) >> 5;                               /* 32-slot chunks per intersection */
         const unsigned lt = (1u << lane) - 1u;
-        int tk = 0, seq = 0;
-        if (lane == 0) { tk = atomicAdd(&ticket[0], PVT_BATCH); if (tk < n_env) seq = atomicAdd(&C->p_seq, 1); }
-        tk = __shfl_sync(0xffffffffu, tk, 0); seq = __shfl_sync(0xffffffffu, seq, 0);
-        while (tk < n_env) {
+        /* the first ticket of every producer is static (no round trip to the ticket counter before the first loads),
+         * the others are drawn from ticket[0] and start behind the static ones */
+        const int pw = warp - 4 * PVT_GROUPS, dyn0 = (int)gridDim.x * PVT_PRODUCERS * PVT_BATCH;
+        int tk = ((int)blockIdx.x * PVT_PRODUCERS + pw) * PVT_BATCH, seq = pw;
+        bool first = true;
+        while (first || tk < n_env) {
             const int envb = tk, my_seq = seq;
             int ntk = 0, nseq = 0;
-            if (lane == 0) { ntk = atomicAdd(&ticket[0], PVT_BATCH); if (ntk < n_env) nseq = atomicAdd(&C->p_seq, 1); }   /* travels meanwhile */
-            const int n_e = min(n_env, envb + PVT_BATCH) - envb;
+            if (lane == 0) {                                                     /* the next ticket travels meanwhile */
+                ntk = dyn0 + atomicAdd(&ticket[0], PVT_BATCH);
+                if (ntk < n_env) nseq = atomicAdd(&C->p_seq, 1);
+            }
+            const int n_e = max(0, min(n_env, envb + PVT_BATCH) - envb);
             const int nvl = (meta && lane < n_e) ? n_veh[envb + lane] : slots_per_env;
             const int n_chunks = n_e * cpe;
             int e = 0, c = 0;
-            for (int q0 = 0; q0 < n_chunks; q0 += 8) {
-                uint32_t pk[8]; bool pre[8]; int gi[8], sv[8], nvu[8];
+            bool turn = false;
+            for (int q0 = 0; q0 < n_chunks; q0 += PVT_PCHUNKS) {
+                uint32_t pk[PVT_PCHUNKS]; bool pre[PVT_PCHUNKS]; int gi[PVT_PCHUNKS], sv[PVT_PCHUNKS], nvu[PVT_PCHUNKS];
 #pragma unroll
-                for (int u = 0; u < 8; ++u) {                                    /* eight loads in flight */
+                for (int u = 0; u < PVT_PCHUNKS; ++u) {                          /* all loads in flight together */
                     const int s = 32 * c + lane;
                     const long long gs = (long long)(envb + e) * slots_per_env + s;
                     pre[u] = q0 + u < n_chunks && s < slots_per_env && gs < n_slots;
                     if (pre[u] && mask) pre[u] = mask[gs] != 0;                  /* only the marked rows */
                     pk[u] = (pre[u] && meta) ? meta[gs].packed : 0u;
-                    gi[u] = (int)gs; sv[u] = s; nvu[u] = __shfl_sync(0xffffffffu, nvl, e & 31);
+                    gi[u] = (int)gs; sv[u] = s; nvu[u] = e;                     /* the intersection; its vehicle count after the loads */
                     if (++c == cpe) { c = 0; ++e; }
                 }
-                unsigned bal[8]; int cnt = 0;
+                unsigned bal[PVT_PCHUNKS]; int cnt = 0;
 #pragma unroll
-                for (int u = 0; u < 8; ++u) {
+                for (int u = 0; u < PVT_PCHUNKS; ++u) {
                     bool want = pre[u];
+                    nvu[u] = __shfl_sync(0xffffffffu, nvl, nvu[u] & 31);
                     if (meta) {
                         want = pre[u] && sv[u] < nvu[u] && ((pk[u] >> 24) & PVE_F_CONTROL) != 0;
                         if (pre[u] && !want) actions[gi[u]] = 0.f;               /* main.py:401 */
@@ -441,15 +485,16 @@ pve_actor_tc_kernel(const __grid_constant__ PvtVecs V, const uint16_t *__restric
                 }
                 if (lane == 0) {
                     const long long t0 = clock64();
-                    if (q0 == 0)                                                 /* this ticket's turn to append */
+                    if (!turn)                                                   /* this ticket's turn to append */
                         while (*reinterpret_cast<volatile int *>(&C->p_commit) != my_seq) { __nanosleep(40); PVT_TIMEOUT(t0); }
                     const int tl = *reinterpret_cast<volatile int *>(&C->q_tail);
                     while (tl + cnt - *reinterpret_cast<volatile int *>(&C->q_free) > PVT_RING) { __nanosleep(100); PVT_TIMEOUT(t0); }
                 }
+                turn = true;
                 __syncwarp();
                 int tail = *reinterpret_cast<volatile int *>(&C->q_tail);
 #pragma unroll
-                for (int u = 0; u < 8; ++u) {
+                for (int u = 0; u < PVT_PCHUNKS; ++u) {
                     if ((bal[u] >> lane) & 1u) ring[(tail + __popc(bal[u] & lt)) & (PVT_RING - 1)] = gi[u] * slot_step;
                     tail += __popc(bal[u]);
                 }
@@ -457,8 +502,15 @@ pve_actor_tc_kernel(const __grid_constant__ PvtVecs V, const uint16_t *__restric
                 __syncwarp();
                 if (lane == 0) *reinterpret_cast<volatile int *>(&C->q_tail) = tail;
             }
-            __threadfence_block();
-            if (lane == 0) *reinterpret_cast<volatile int *>(&C->p_commit) = my_seq + 1;
+            if (lane == 0) {
+                if (!turn) {                                                     /* an empty static ticket still passes its turn on */
+                    const long long t0 = clock64();
+                    while (*reinterpret_cast<volatile int *>(&C->p_commit) != my_seq) { __nanosleep(40); PVT_TIMEOUT(t0); }
+                }
+                __threadfence_block();
+                *reinterpret_cast<volatile int *>(&C->p_commit) = my_seq + 1;
+            }
+            first = false;
             tk = __shfl_sync(0xffffffffu, ntk, 0); seq = __shfl_sync(0xffffffffu, nseq, 0);
         }
         __threadfence_block();

@@ -1368,6 +1368,12 @@ static cudaError_t launch_actor(pve_actor *a, const float *rows, const pve_veh_m
 }
 #endif
 
+#if defined(PVT_X_TRACE) && !defined(PVE_HOST_EMULATION)
+extern "C" int32_t pve_debug_trace(long long *out, int32_t n) {          /* experiment builds only */
+    return cudaMemcpyFromSymbol(out, pvt_trace_buf, sizeof(long long) * n) == cudaSuccess ? 0 : -1;
+}
+#endif
+
 int32_t pve_actor_forward(pve_actor *a, const float *rows_dev, int64_t n_rows, float *actions_dev, void *stream_) {
     if (!a || !rows_dev || !actions_dev || n_rows < 0) return PVE_EINVAL;
 #ifdef PVE_HOST_EMULATION
