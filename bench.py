@@ -653,18 +653,20 @@ def graft_arm(args, rank, world, local_rank, veh_cap, agent_cap):
         }
         if actor is not None:
             # 2 * (28*64 + 64*64 + 64) multiply-adds per agent; bytes: 112 B row in, 4 B action out, 8 B meta per slot
-            line["actor"] = {"kernel": "pve_actor_kernel", "kernel_ms_per_launch": float(sum(actor_ms)) / K,
+            line["actor"] = {"kernel": "pve_actor_tc_kernel" if os.environ.get("PVE_ACTOR_IMPL", "tc5") == "tc5" else "pve_actor_%s_kernel" % os.environ["PVE_ACTOR_IMPL"],
+                             "kernel_ms_per_launch": float(sum(actor_ms)) / K,
                              "gflop_per_launch": 2 * 5952 * kA / K / 1e9,
                              "tflops": 2 * 5952 * kA / (float(sum(actor_ms)) * 1e-3) / 1e12,
-                             "note": "tensor cores, bf16 x 3 split-precision products (fp32-equivalent: the reference's "
+                             "note": "tcgen05.mma + tensor memory (csrc/mlp_tc5.cuh), bf16 x 3 split-precision products "
+                                     "(fp32-equivalent: the reference's "
                                      "graph is fp32 and ill-conditioned at 1e-4); tflops counts the network's fp32 "
                                      "multiply-adds once; timed alone with a cold L2, inside the same ticks as roofline"}
         if folder is not None:
             fc = folder.counters()
             # per agent row: 784 B observation in + 784 B frame out; per record: 2 x 784 B frames in, 2 x 784 + 36 B out
             fold_bytes = (1568 * kA + 3172 * kA) / K
-            line["nstep"] = {"kernels": "pve_actor_mma_kernel x 2 (distinct rows: this tick's agents, last tick's referenced "
-                                        "rows) + pvn_mark/gather + pve_critic_kernel + pvn_plan/scan/fold",
+            line["nstep"] = {"kernels": "pve_actor_tc_kernel x 2 (distinct rows: this tick's agents, last tick's referenced "
+                                        "rows) + pvn_mark/gather + pve_critic_tc_kernel + pvn_plan/scan/fold",
                              "ms_per_push": float(sum(fold_ms)) / K, "seq_max_step": 12, "gamma": TRAIN_GAMMA,
                              "num_experiences": fc["num_experiences"], "records_last_push": fc["last_added"],
                              "slot_conflicts": fc["slot_conflicts"], "replay_capacity": folder.capacity,

@@ -52,8 +52,18 @@ struct PvtVecs {
 #define PVT_TILE 128
 #define PVT_TMEM_COLS 256
 #define PVT_RING 2048
+#ifndef PVT_BATCH
 #define PVT_BATCH 3                                        /* intersections per ticket */
+#endif
+#ifndef PVT_PCHUNKS
 #define PVT_PCHUNKS 12                                     /* 32-slot chunks a producer loads at once */
+#endif
+#ifndef PVT_BACKLOG
+#define PVT_BACKLOG PVT_RING                               /* queued-but-unclaimed entries beyond which a producer holds its commit */
+#endif
+#ifndef PVT_PREFETCH
+#define PVT_PREFETCH 1                                     /* draw the next ticket before this one's loads (1) or after its commit (0) */
+#endif
 #define PVT_PRODUCERS 4                                    /* the register file is handed out four warps at a time: 13 warps cost 16 */
 #define PVT_THREADS_ACTOR (PVT_GROUPS * 128 + PVT_PRODUCERS * 32)
 #define PVT_THREADS_CRITIC (PVT_GROUPS * 128)
@@ -450,7 +460,7 @@ pve_actor_tc_kernel(const __grid_constant__ PvtVecs V, const uint16_t *__restric
         while (first || tk < n_env) {
             const int envb = tk, my_seq = seq;
             int ntk = 0, nseq = 0;
-            if (lane == 0) {                                                     /* the next ticket travels meanwhile */
+            if (PVT_PREFETCH && lane == 0) {                                     /* the next ticket travels meanwhile */
                 ntk = dyn0 + atomicAdd(&ticket[0], PVT_BATCH);
                 if (ntk < n_env) nseq = atomicAdd(&C->p_seq, 1);
             }
@@ -488,7 +498,8 @@ pve_actor_tc_kernel(const __grid_constant__ PvtVecs V, const uint16_t *__restric
                     if (!turn)                                                   /* this ticket's turn to append */
                         while (*reinterpret_cast<volatile int *>(&C->p_commit) != my_seq) { __nanosleep(40); PVT_TIMEOUT(t0); }
                     const int tl = *reinterpret_cast<volatile int *>(&C->q_tail);
-                    while (tl + cnt - *reinterpret_cast<volatile int *>(&C->q_free) > PVT_RING) { __nanosleep(100); PVT_TIMEOUT(t0); }
+                    while (tl + cnt - *reinterpret_cast<volatile int *>(&C->q_free) > PVT_RING
+                           || (PVT_BACKLOG < PVT_RING && tl - *reinterpret_cast<volatile int *>(&C->q_head) > PVT_BACKLOG)) { __nanosleep(100); PVT_TIMEOUT(t0); }
                 }
                 turn = true;
                 __syncwarp();
@@ -511,6 +522,10 @@ pve_actor_tc_kernel(const __grid_constant__ PvtVecs V, const uint16_t *__restric
                 *reinterpret_cast<volatile int *>(&C->p_commit) = my_seq + 1;
             }
             first = false;
+            if (!PVT_PREFETCH && lane == 0) {
+                ntk = dyn0 + atomicAdd(&ticket[0], PVT_BATCH);
+                if (ntk < n_env) nseq = atomicAdd(&C->p_seq, 1);
+            }
             tk = __shfl_sync(0xffffffffu, ntk, 0); seq = __shfl_sync(0xffffffffu, nseq, 0);
         }
         __threadfence_block();

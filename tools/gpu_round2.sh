@@ -1,6 +1,6 @@
 #!/bin/bash
 # Round-2 evidence run on the GPU box: full bench, launch list, ncu --set full of the small step kernel, sanitizer.
-# Usage: tools/gpu_round2.sh [what...]   what = bench launches full stress rollout lanes train sanitizer
+# Usage: tools/gpu_round2.sh [what...]   what = bench launches full stress rollout lanes train actor tests sanitizer
 OUT=gpurun_out; mkdir -p $OUT
 WHAT=${*:-bench launches full}
 for w in $WHAT; do
@@ -24,6 +24,12 @@ lanes)
   done ;;
 train)
   timeout 900 python bench.py --workload train --steps 50 --warmup 5 --no-cpu-baseline --no-e2e > $OUT/r02_bench_train.json 2> $OUT/r02_bench_train.err; cut -c1-300 $OUT/r02_bench_train.json ;;
+actor)
+  for impl in tc5 mma; do echo "== actor timing $impl"; PVE_ACTOR_IMPL=$impl timeout 300 python tools/actor_timing.py 2>&1 | tail -5; done > $OUT/r02_actor_timing.txt; cat $OUT/r02_actor_timing.txt
+  timeout 900 ncu --set full --clock-control none --import-source on -k regex:pve_actor_tc_kernel -s 405 -c 1 -f -o $OUT/r02_actor_prof \
+      python tools/actor_timing.py > $OUT/r02_actor_run.log 2>&1; echo "ncu actor rc=$?"; ls -la $OUT/r02_actor_prof.ncu-rep ;;
+tests)
+  timeout 1700 python -m pytest tests -x -q -m gpu > $OUT/r02_gpu_tests.log 2>&1; echo "gpu tests rc=$?"; tail -3 $OUT/r02_gpu_tests.log ;;
 sanitizer)
   timeout 1500 compute-sanitizer --tool memcheck --error-exitcode 9 python -m pytest tests/test_gpu_parity_more.py tests/test_gpu_lane4.py -x -q -k "pipelined or two_handles or out_cap or dual or lane8_matches or rollout8_direct" > $OUT/r02_sanitizer_memcheck.log 2>&1; echo "memcheck rc=$?"; tail -5 $OUT/r02_sanitizer_memcheck.log
   timeout 1500 compute-sanitizer --tool racecheck --error-exitcode 9 python -m pytest tests/test_gpu_parity.py -x -q -k "teacher_forced_every_tick" > $OUT/r02_sanitizer_racecheck.log 2>&1; echo "racecheck rc=$?"; tail -8 $OUT/r02_sanitizer_racecheck.log ;;

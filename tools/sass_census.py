@@ -7,7 +7,7 @@ import sys
 
 lib = sys.argv[1] if len(sys.argv) > 1 else "pve_mcc_for_unsignalized_intersection_b200/csrc/libpve_mcc.so"
 sass = subprocess.run(["cuobjdump", "-sass", lib], stdout=subprocess.PIPE, text=True).stdout.split("\n")
-FAM = [("HMMA", r"HMMA"), ("UTC*MMA", r"UTC[A-Z]*MMA"), ("LDTM/STTM", r"LDTM|STTM"), ("UTMALDG/UTMASTG/UBLKCP", r"UTMALDG|UTMASTG|UBLKCP"),
+FAM = [("HMMA", r"(?<!UTC)HMMA"), ("UTC*MMA", r"UTC[A-Z]*MMA"), ("LDTM/STTM", r"LDTM|STTM"), ("UTMALDG/UTMASTG/UBLKCP", r"UTMALDG|UTMASTG|UBLKCP"),
        ("LDGSTS", r"LDGSTS"), ("DFMA/DADD/DMUL", r" D(FMA|ADD|MUL)"), ("BAR", r" BAR\."), ("ATOMS", r"ATOMS"), ("REDG/ATOMG", r"REDG|ATOMG"),
        ("SHFL", r"SHFL"), ("MUFU", r"MUFU")]
 rows, cur = [], None
@@ -37,6 +37,7 @@ print("\n%d kernels in the library (the step kernel's other instantiations -- ca
       "and are not listed).  Library totals: %s.\n" % (len(rows), ", ".join("%s %d" % (f, tot[f]) for f, _ in FAM)))
 print("Reading: the environment step (`pve_step_kernel`, `pve_step_big_kernel`) is scalar float64 + integer work with shared-memory staging -- no "
       "tensor instructions by design (north_star: no dense contraction on this path; the per-row `cp.async.bulk` stores tried in round 1 were "
-      "slower).  The policy / critic kernels (rows N1 / N2) still run on the legacy `HMMA.16816` path: there is no `UTC*MMA`, `LDTM`/`STTM` or "
-      "`UTMALDG` instruction in this build -- a tcgen05 + TMEM version was not written in round 2 (the round went into the step kernel's roofline "
-      "fraction, the measurement and the host path, as VERDICT r01 ordered them).")
+      "slower).  The policy / critic kernels of rows N1 / N2 exist three times: `pve_actor_tc_kernel` / `pve_critic_tc_kernel` (csrc/mlp_tc5.cuh, the "
+      "default) issue `UTCHMMA` (tcgen05.mma, accumulators in tensor memory read back with `LDTM`) and fetch their weights with one `UBLKCP` bulk "
+      "copy; `pve_actor_mma_kernel` / `pve_critic_mma_kernel` are the round-1 `HMMA.16816` (mma.sync) versions kept for A/B "
+      "(PVE_ACTOR_IMPL / PVE_CRITIC_IMPL = mma), `pve_actor_kernel` / `pve_critic_kernel` the fp32 FFMA ones (= ffma).")
