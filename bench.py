@@ -452,7 +452,7 @@ def graft_arm(args, rank, world, local_rank, veh_cap, agent_cap):
                                                  if k.startswith("actor__")}), device=dev)
             t_critic = BatchedCritic(CriticWeights({k[len("critic__"):].replace("__", "/"): z[k] for k in z.files
                                                     if k.startswith("critic__")}), device=dev)
-        folder = NStepFolder(scene, t_actor, t_critic, seq_max_step=12, buffer_size=500000)      # main.py:91, 212
+        folder = NStepFolder(scene, t_actor, t_critic, seq_max_step=12, buffer_size=max(500000, scene.out_cap + 1))   # main.py:91, 212 (a tick must fit)
     gen = torch.Generator(device=dev)
     gen.manual_seed(99 + rank)
     if stress:
@@ -469,6 +469,8 @@ def graft_arm(args, rank, world, local_rank, veh_cap, agent_cap):
 
     def tick(a):
         """One tick of the workload: the environment step and, for `train`, main.py:243-266 on its outputs."""
+        if folder is not None:
+            folder.bind_outputs()              # the step writes its observations straight into the folder's frame log
         out = scene.step(a)
         if folder is not None:
             folder.push(out, TRAIN_GAMMA)
@@ -524,6 +526,8 @@ def graft_arm(args, rank, world, local_rank, veh_cap, agent_cap):
             aev[0].record()
             a = actions(K + t)
             aev[1].record()
+            if folder is not None:
+                folder.bind_outputs()
             out = scene.step(a)
             if folder is not None:             # the folding of this tick, timed on its own
                 fev[0].record()

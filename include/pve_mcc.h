@@ -317,6 +317,11 @@ int32_t pve_nstep_push_scene(pve_nstep *f, pve_scene *s, const pve_outputs *out_
                              pve_actor *target_actor, pve_critic *target_critic, void *stream);
 /* a new episode (main.py:230 builds a new TrafficInteraction every epoch): every vehicle's buffered transitions are
  * dropped, the replay memory and num_experiences are kept (agent1_memory_seq lives across epochs, main.py:212) */
+/* Where the NEXT push expects its observations: a block of the folder's frame log ([out_cap][7][28] floats, device).
+ * Hand it to the step as pve_outputs.obs and the push finds the frames in place; any other pve_outputs.obs is copied
+ * into the log by the push (one out_cap x 784 B device copy).  The log holds the last seq_max_step + 2 pushes: the
+ * per-vehicle buffers of main.py:243-246 keep references into it instead of private copies of veh["state"]. */
+int32_t pve_nstep_obs_slot(const pve_nstep *f, float **obs_dev);
 int32_t pve_nstep_reset(pve_nstep *f, void *stream);
 int32_t pve_nstep_replay(const pve_nstep *f, pve_replay_view *view);
 /* out_host[0] = num_experiences (replay_buffer.py:47), [1] = records added by the last push, [2] = history slots

@@ -106,6 +106,7 @@ def load_library(path=None):
     lib.pve_nstep_push.argtypes = [vp, C.POINTER(PveOutputs), C.c_double, vp, vp, vp]
     lib.pve_nstep_push_scene.argtypes = [vp, vp, C.POINTER(PveOutputs), C.c_double, vp, vp, vp]
     lib.pve_nstep_reset.argtypes = [vp, vp]
+    lib.pve_nstep_obs_slot.argtypes = [vp, C.POINTER(vp)]
     lib.pve_nstep_replay.argtypes = [vp, C.POINTER(PveReplayView)]
     lib.pve_nstep_counters.argtypes = [vp, C.POINTER(i64), vp]
     lib.pve_nstep_q_dev.argtypes = [vp]

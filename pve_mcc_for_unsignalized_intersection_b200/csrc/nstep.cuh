@@ -17,9 +17,15 @@
  *     key    u64   uid << 32 | stamp of the last push that saw it (all ones = free)
  *     fill   u8x2  n = transitions buffered, head = ring index of the oldest state
  *     rew    f32[M]        reward of the transition whose state_next sits at the same ring index
- *     frames f32[M][7][28] ring of observations, M = seq_max_step + 2: transition i of the buffer is
- *                          (frames[head + i], frames[head + i + 1]) because state_now of a tick is state_next
- *                          of the tick before (TIS:288, main.py:235) or zeros for a new vehicle (TIS:380)
+ *     fidx   i32[M]        ring of FRAME REFERENCES, M = seq_max_step + 2: transition i of the buffer is
+ *                          (frame[head + i], frame[head + i + 1]) because state_now of a tick is state_next
+ *                          of the tick before (TIS:288, main.py:235) or zeros for a new vehicle (TIS:380, reference -1)
+ * The frames themselves live once, in a FRAME LOG of the last M pushes' observation blocks ([M][out_cap][7][28]; a
+ * reference is a row of the log).  A vehicle is an agent on consecutive ticks, so its M frames were pushed by the last M
+ * pushes and the slot that the current push overwrites (push - M) is referenced by nobody.  The step kernel can write a
+ * tick's observations straight into the log (pve_nstep_obs_slot: no copy); any other observation buffer is copied in.
+ * Round 1 kept a private 14-frame ring per table slot: 11.5 GB per 4 096 intersections and one more 784-byte copy per
+ * agent-tick; now the table is 122 bytes per slot (128 MB) and the log 784 B x out_cap x M.
  * A vehicle is an agent on consecutive ticks from its arrival until Done (TIS:419, 336, 353), so "stamp ==
  * previous push" identifies a live history; anything else in the slot is stale and is overwritten.  A slot
  * whose other owner is still live is counted in counters[2] (sticky; size the table with more slots).
@@ -30,8 +36,8 @@
  *     pvn_scan_kernel  one CTA: prefix over the blocks, advances num_experiences
  *     pvn_fold_kernel  one warp per agent row: ring update, return folding in float64, record written at
  *                      its deque position (order of the reference: intersection, lane, j ascending)
- * HBM-bound: per agent 784 B observation in, 784 B frame out, and per record 2 x 784 B frames in,
- * 2 x 784 + 36 B out = 4.7 KB per agent-tick in steady state.
+ * HBM-bound: per record 2 x 784 B frames in, 2 x 784 + 36 B out = 3.2 KB per agent-tick in steady state (round 1, with
+ * the per-slot frame rings: 4.7 KB).
  *
  * The critic (model_agent_maddpg.py:52-76: LN(28) -> Dense 64 -> LN -> ReLU -> concat 7 actions -> Dense 64 ->
  * LN -> ReLU -> Dense 1) reuses the register-tiled fp32 GEMM chain of actor.cuh; fp32 FFMA for the same
@@ -63,7 +69,9 @@ struct PvnTable {
     unsigned long long *key;         /* [B][U] */
     uint8_t *fill;                   /* [B][U][2] */
     float *rew;                      /* [B][U][M] */
-    float *frames;                   /* [B][U][M][196] */
+    int32_t *fidx;                   /* [B][U][M] rows of the frame log, -1 = the all-zero frame */
+    float *log;                      /* [M][out_cap][196] observation blocks of the last M pushes */
+    long long out_cap;
     int U, M, S, B;
 };
 
@@ -302,7 +310,7 @@ __device__ __forceinline__ void pvn_zero_frame(float *__restrict__ dst, const in
 
 __global__ void __launch_bounds__(256)
 pvn_fold_kernel(const PvnTable T, const PvnReplay R, const int32_t *__restrict__ ids, const uint8_t *__restrict__ status,
-                const float *__restrict__ obs, const float *__restrict__ reward, const float *__restrict__ q,
+                const float *__restrict__ reward, const float *__restrict__ q,
                 const int32_t *__restrict__ agent_offset, const long long out_cap, const unsigned stamp, const double gamma,
                 const uint32_t *__restrict__ plan, const long long *__restrict__ blk_base) {
     const long long n_rows = min((long long)agent_offset[T.B], out_cap);
@@ -318,16 +326,16 @@ pvn_fold_kernel(const PvnTable T, const PvnReplay R, const int32_t *__restrict__
         const int M = T.M;
         int n = 0, head = 0;
         if (!is_new) { n = T.fill[slot * 2]; head = T.fill[slot * 2 + 1]; }
-        float *const frames = T.frames + slot * (size_t)M * PVN_OBS;
+        int32_t *const fidx = T.fidx + slot * (size_t)M;
         float *const rew = T.rew + slot * (size_t)M;
-        const float *const obs_r = obs + r * PVN_OBS;
+        const long long my_row = (long long)(stamp % (unsigned)M) * T.out_cap + r;   /* this tick's observation in the log */
+        const float *const obs_r = T.log + my_row * PVN_OBS;
         const float rew_now = reward[r];
         /* append: state_next and reward of this tick (main.py:244-246) */
         int at = head + n + 1; at -= at >= M ? M : 0;
-        if (is_new) pvn_zero_frame(frames + (size_t)head * PVN_OBS, lane);           /* TIS:380 */
-        if (!(emit && done)) {                                                       /* a Done vehicle never comes back */
-            pvn_copy_frame(frames + (size_t)at * PVN_OBS, obs_r, lane);
-            if (lane == 0) rew[at] = rew_now;
+        if (lane == 0) {
+            if (is_new) fidx[head] = -1;                                             /* TIS:380 */
+            if (!(emit && done)) { fidx[at] = (int32_t)my_row; rew[at] = rew_now; }  /* a Done vehicle never comes back */
         }
         n += 1;
         if (emit) {
@@ -340,9 +348,11 @@ pvn_fold_kernel(const PvnTable T, const PvnReplay R, const int32_t *__restrict__
                 tgt = (double)__shfl_sync(0xffffffffu, mine, i) + gamma * tgt;
             const long long pos = (blk_base[r / PVN_PLAN_THREADS] + (long long)(pl >> 2)) % R.cap;   /* RB:47-53 */
             int nx = head + 1; nx -= nx >= M ? M : 0;
-            const float *const src_next = n == 1 ? obs_r : frames + (size_t)nx * PVN_OBS;
-            if (is_new) pvn_zero_frame(R.state + pos * PVN_OBS, lane);
-            else pvn_copy_frame(R.state + pos * PVN_OBS, frames + (size_t)head * PVN_OBS, lane);
+            /* both references were stored by earlier pushes (n == 1: the next state is this tick's own row) */
+            const int f_state = is_new ? -1 : fidx[head];
+            const float *const src_next = n == 1 ? obs_r : T.log + (size_t)fidx[nx] * PVN_OBS;
+            if (f_state < 0) pvn_zero_frame(R.state + pos * PVN_OBS, lane);
+            else pvn_copy_frame(R.state + pos * PVN_OBS, T.log + (size_t)f_state * PVN_OBS, lane);
             pvn_copy_frame(R.next_state + pos * PVN_OBS, src_next, lane);
             if (lane < PVE_OBS_H) R.action[pos * PVE_OBS_H + lane] = src_next[lane * PVE_OBS_W + 2];   /* TIS:290 */
             if (lane == 0) { R.reward[pos] = (float)tgt; R.done[pos] = 0; }          /* main.py:263-264 */

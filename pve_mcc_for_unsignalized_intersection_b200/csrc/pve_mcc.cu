@@ -1534,7 +1534,7 @@ struct pve_nstep {
 void pve_nstep_destroy(pve_nstep *f) {
     if (!f) return;
 #ifndef PVE_HOST_EMULATION
-    cudaFree(f->T.key); cudaFree(f->T.fill); cudaFree(f->T.rew); cudaFree(f->T.frames);
+    cudaFree(f->T.key); cudaFree(f->T.fill); cudaFree(f->T.rew); cudaFree(f->T.fidx); cudaFree(f->T.log);
     cudaFree(f->R.state); cudaFree(f->R.action); cudaFree(f->R.reward); cudaFree(f->R.next_state); cudaFree(f->R.done);
     cudaFree(f->need); cudaFree(f->mu_prev);
     cudaFree(f->act7); cudaFree(f->q); cudaFree(f->plan); cudaFree(f->blk_count); cudaFree(f->blk_base); cudaFree(f->counters);
@@ -1556,7 +1556,8 @@ int32_t pve_nstep_create(int32_t n_envs, int32_t uid_slots, int32_t seq_max_step
     if (!f) return PVE_ENOMEM;
     f->device = device;
     f->out_cap = out_cap;
-    f->T.B = n_envs; f->T.U = uid_slots; f->T.S = seq_max_step; f->T.M = seq_max_step + 2;
+    f->T.B = n_envs; f->T.U = uid_slots; f->T.S = seq_max_step; f->T.M = seq_max_step + 2; f->T.out_cap = out_cap;
+    if ((long long)f->T.M * out_cap > 0x7fffffffLL) { free(f); return PVE_EINVAL; }   /* frame references are 32-bit log rows */
     f->R.cap = buffer_size - 1;
     f->n_blk = (int)((out_cap + PVN_PLAN_THREADS - 1) / PVN_PLAN_THREADS);
     int sms = 0;
@@ -1566,7 +1567,8 @@ int32_t pve_nstep_create(int32_t n_envs, int32_t uid_slots, int32_t seq_max_step
     bool ok = cudaMalloc((void **)&f->T.key, slots * 8) == cudaSuccess
               && cudaMalloc((void **)&f->T.fill, slots * 2) == cudaSuccess
               && cudaMalloc((void **)&f->T.rew, slots * f->T.M * sizeof(float)) == cudaSuccess
-              && cudaMalloc((void **)&f->T.frames, slots * f->T.M * PVN_OBS * sizeof(float)) == cudaSuccess
+              && cudaMalloc((void **)&f->T.fidx, slots * f->T.M * sizeof(int32_t)) == cudaSuccess
+              && cudaMalloc((void **)&f->T.log, (size_t)f->T.M * oc * PVN_OBS * sizeof(float)) == cudaSuccess
               && cudaMalloc((void **)&f->R.state, cap * PVN_OBS * sizeof(float)) == cudaSuccess
               && cudaMalloc((void **)&f->R.next_state, cap * PVN_OBS * sizeof(float)) == cudaSuccess
               && cudaMalloc((void **)&f->R.action, cap * PVE_OBS_H * sizeof(float)) == cudaSuccess
@@ -1617,10 +1619,16 @@ static int32_t nstep_fold(pve_nstep *f, const pve_outputs *O, double gamma, pve_
     int32_t rc = pve_critic_forward(target_critic, O->obs, f->act7, f->out_cap, n_rows_dev, f->q, stream_);
     if (rc != PVE_OK) return rc;
     const unsigned stamp = (unsigned)(++f->pushes);
+    /* this tick's observations belong in slot stamp % M of the frame log: already there if the step wrote them to
+     * pve_nstep_obs_slot(), copied otherwise (the whole block: the row count lives on the device) */
+    float *const slot = f->T.log + (size_t)(stamp % (unsigned)f->T.M) * (size_t)f->out_cap * PVN_OBS;
+    if (O->obs != slot
+        && cudaMemcpyAsync(slot, O->obs, (size_t)f->out_cap * PVN_OBS * sizeof(float), cudaMemcpyDeviceToDevice, stream) != cudaSuccess)
+        return PVE_ECUDA;
     pvn_plan_kernel<<<f->n_blk, PVN_PLAN_THREADS, 0, stream>>>(f->T, O->ids, O->status, O->agent_offset, f->out_cap, stamp,
                                                               f->plan, f->blk_count, f->counters);
     pvn_scan_kernel<<<1, 1024, 0, stream>>>(f->blk_count, f->blk_base, f->n_blk, f->counters);
-    pvn_fold_kernel<<<f->fold_blocks, 256, 0, stream>>>(f->T, f->R, O->ids, O->status, O->obs, O->reward, f->q, O->agent_offset,
+    pvn_fold_kernel<<<f->fold_blocks, 256, 0, stream>>>(f->T, f->R, O->ids, O->status, O->reward, f->q, O->agent_offset,
                                                         f->out_cap, stamp, gamma, f->plan, f->blk_base);
     return cudaGetLastError() == cudaSuccess ? PVE_OK : PVE_ECUDA;
 }
@@ -1672,6 +1680,12 @@ int32_t pve_nstep_push_scene(pve_nstep *f, pve_scene *s, const pve_outputs *O, d
     if (cudaGetLastError() != cudaSuccess) return PVE_ECUDA;
     return nstep_fold(f, O, gamma, target_critic, stream_);
 #endif
+}
+
+int32_t pve_nstep_obs_slot(const pve_nstep *f, float **obs_dev) {
+    if (!f || !obs_dev) return PVE_EINVAL;
+    *obs_dev = f->T.log ? f->T.log + (size_t)((unsigned)(f->pushes + 1) % (unsigned)f->T.M) * (size_t)f->out_cap * PVN_OBS : nullptr;
+    return f->T.log ? PVE_OK : PVE_ESTATE;
 }
 
 int32_t pve_nstep_reset(pve_nstep *f, void *stream_) {

@@ -188,6 +188,21 @@ class NStepFolder:
         if rc != 0:
             raise N.NativeError("pve_nstep_push failed with %d" % rc)
 
+    def bind_outputs(self, outputs=None):
+        """Zero-copy: make the next ``scene.step`` write its observations straight into the folder's frame log.  Call it
+        before every step whose outputs will be pushed (``outputs`` defaults to ``scene.out``; its ``obs`` tensor is
+        replaced by a view of the log block the next push expects, so read ``outputs.obs`` before the next call).
+        Without it ``push`` copies the observation block into the log (same results, one more device copy per tick)."""
+        outputs = self.scene.out if outputs is None else outputs
+        ptr = C.c_void_p()
+        rc = self.lib.pve_nstep_obs_slot(self._h, C.byref(ptr))
+        if rc != 0:
+            raise N.NativeError("pve_nstep_obs_slot failed with %d" % rc)
+        outputs.obs = self._wrap(ptr.value, (self.scene.out_cap, OBS_H, OBS_W), torch.float32)
+        if outputs is self.scene.out:
+            self.scene._out_native.obs = ptr.value            # the struct the scene hands to pve_step
+        return outputs
+
     def reset(self):
         """A new episode (main.py:230: a new ``TrafficInteraction`` per epoch): the vehicles' buffered transitions are
         dropped; the replay memory stays (``agent1_memory_seq`` is created once, main.py:212)."""

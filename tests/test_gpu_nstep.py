@@ -274,3 +274,34 @@ def _distinct_row_bootstrap():
     n = c0["num_experiences"]
     for k in ("state", "action", "reward", "next_state"):
         assert torch.equal(plain.arrays()[k][:n], fast.arrays()[k][:n]), k
+
+
+def test_frame_log_in_place_equals_the_copied_observations():
+    """pve_nstep_obs_slot: a step that writes its observations straight into the folder's frame log (bind_outputs) and
+    a push that copies them in must leave the same replay memory, bit for bit; the log wraps many times."""
+    aw, cw = nets()
+    B, S = 256, 5
+    scenes, folders = [], []
+    for _ in range(2):
+        scene = P.make_scene("cuda", B, vm=6, neighbour_sources=True)
+        scene.reset(synthetic_arrivals(B, 1000, 40.0, seed=11), warmup=False)
+        scenes.append(scene)
+        folders.append(NStepFolder(scene, BatchedActor(aw), BatchedCritic(cw), S, buffer_size=1_000_000))
+    gen = torch.Generator(device="cuda").manual_seed(5)
+    for t in range(150):
+        acts = ((torch.rand(B, scenes[0].veh_cap, device="cuda", generator=gen) * 6 - 3) * scenes[0].control_mask()).contiguous()
+        if t == 70:
+            for f in folders:
+                f.reset()                                            # a new episode: buffers dropped, memory kept
+        folders[0].bind_outputs()
+        out0 = scenes[0].step(acts)
+        out1 = scenes[1].step(acts)
+        n = out0.n_agents
+        assert n == out1.n_agents and torch.equal(out0.obs[:n], out1.obs[:n])
+        folders[0].push(out0, 0.9)
+        folders[1].push(out1, 0.9)
+    c0, c1 = folders[0].counters(), folders[1].counters()
+    assert c0["num_experiences"] == c1["num_experiences"] > 100_000 and c0["slot_conflicts"] == 0
+    n = c0["num_experiences"]
+    for k in ("state", "action", "reward", "next_state"):
+        assert torch.equal(folders[0].arrays()[k][:n], folders[1].arrays()[k][:n]), k
