@@ -1,6 +1,6 @@
 #!/bin/bash
 # Round-2 evidence run on the GPU box: full bench, launch list, ncu --set full of the small step kernel, sanitizer.
-# Usage: tools/gpu_round2.sh [what...]   what = bench launches full stress rollout lanes train actor tests sanitizer
+# Usage: tools/gpu_round2.sh [what...]   what = bench launches full stress rollout lanes train actor tests smoke sanitizer sanitizer2
 OUT=gpurun_out; mkdir -p $OUT
 WHAT=${*:-bench launches full}
 for w in $WHAT; do
@@ -30,6 +30,10 @@ actor)
       python tools/actor_timing.py > $OUT/r02_actor_run.log 2>&1; echo "ncu actor rc=$?"; ls -la $OUT/r02_actor_prof.ncu-rep ;;
 tests)
   timeout 1700 python -m pytest tests -x -q -m gpu > $OUT/r02_gpu_tests.log 2>&1; echo "gpu tests rc=$?"; tail -3 $OUT/r02_gpu_tests.log ;;
+sanitizer2)   # the round's new kernels: tcgen05 actor / critic, frame-log fold
+  timeout 900 compute-sanitizer --tool memcheck --error-exitcode 9 python -m pytest tests/test_gpu_actor.py tests/test_gpu_nstep.py -x -q -k "(tc5 and (shapes or critic_kernel or recorded_rows)) or frame_log" > $OUT/r02_sanitizer_memcheck_tc5.log 2>&1; echo "memcheck tc5 rc=$?"; tail -5 $OUT/r02_sanitizer_memcheck_tc5.log ;;
+smoke)
+  timeout 600 python -c "import __graft_entry__ as g; g.smoke(); print('smoke ok')" 2>&1 | tail -3 ;;
 sanitizer)
   timeout 1500 compute-sanitizer --tool memcheck --error-exitcode 9 python -m pytest tests/test_gpu_parity_more.py tests/test_gpu_lane4.py -x -q -k "pipelined or two_handles or out_cap or dual or lane8_matches or rollout8_direct" > $OUT/r02_sanitizer_memcheck.log 2>&1; echo "memcheck rc=$?"; tail -5 $OUT/r02_sanitizer_memcheck.log
   timeout 1500 compute-sanitizer --tool racecheck --error-exitcode 9 python -m pytest tests/test_gpu_parity.py -x -q -k "teacher_forced_every_tick" > $OUT/r02_sanitizer_racecheck.log 2>&1; echo "racecheck rc=$?"; tail -8 $OUT/r02_sanitizer_racecheck.log ;;
