@@ -729,6 +729,8 @@ def main():
     classes = [(96, 48), (96, 64), (128, 80), (128, 96), (192, 128), (384, 320), (576, 416)]
     want = (384, 320) if args.workload == "stress" else (args.veh_cap, args.agent_cap)
     todo = [c for c in classes if c[0] >= want[0] and c[1] >= want[1]]
+    if lanes_of(args) != 12:                   # the 4- / 8-lane path has two classes: 64/64 and 128/96
+        todo = [(64, 64), (128, 96)] if args.workload == "lane4" and args.veh_cap == VEH_CAP else [(128, 96)]
     for vc, ac in todo:
         if graft_arm(args, rank, world, local_rank, vc, ac):
             break

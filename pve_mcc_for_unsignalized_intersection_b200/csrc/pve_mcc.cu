@@ -211,14 +211,14 @@ __global__ void pve_classify_kernel(PveState S, int B) {
 
 /* ---- lane_num = 4 / 8 (scene_step4.cuh): one warp per intersection, PVE4_WARPS intersections per CTA -------------- */
 #define PVE4_WARPS 4
-template <int NLN>
+template <int NLN, int LC>
 __global__ void __launch_bounds__(32 * PVE4_WARPS)
 pve4_step_kernel(const Pve4Params P, const PveState S, const pve_outputs O, const int32_t *spawn_tick, const uint8_t *draws,
                  const float *actions, const int64_t *off4) {
     extern __shared__ __align__(16) unsigned char pve_smem[];
     const int b = (int)blockIdx.x * PVE4_WARPS + (int)(threadIdx.x >> 5);
     if (b >= P.B) return;
-    Pve4Smem &M = ((Pve4Smem *)pve_smem)[threadIdx.x >> 5];
+    Pve4SmemT<LC> &M = ((Pve4SmemT<LC> *)pve_smem)[threadIdx.x >> 5];
     pve4_step_block<NLN>(P, S, O, spawn_tick, draws, actions, b, M, off4[b]);
 }
 
@@ -518,19 +518,28 @@ static int32_t launch_step4(pve_scene *s, const float *actions, const pve_output
     const int B = s->cfg.n_envs;
 #ifndef PVE_HOST_EMULATION
     static bool attr_set[16] = {false};
-    const size_t smem = sizeof(Pve4Smem) * PVE4_WARPS;
+    /* capacity class 64 (lists and vehicle slots of <= 64 entries): half the shared memory, twice the resident warps */
+    const bool small = s->prm.VC <= 64;
+    const size_t smem = (small ? sizeof(Pve4SmemT<64>) : sizeof(Pve4SmemT<128>)) * PVE4_WARPS;
     if (!attr_set[s->device & 15]) {
-        RT_CHECK(s, cudaFuncSetAttribute(pve4_step_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        RT_CHECK(s, cudaFuncSetAttribute(pve4_step_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        RT_CHECK(s, cudaFuncSetAttribute(pve4_step_kernel<4, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(Pve4SmemT<128>) * PVE4_WARPS)));
+        RT_CHECK(s, cudaFuncSetAttribute(pve4_step_kernel<8, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(Pve4SmemT<128>) * PVE4_WARPS)));
+        RT_CHECK(s, cudaFuncSetAttribute(pve4_step_kernel<4, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(Pve4SmemT<64>) * PVE4_WARPS)));
+        RT_CHECK(s, cudaFuncSetAttribute(pve4_step_kernel<8, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(Pve4SmemT<64>) * PVE4_WARPS)));
         attr_set[s->device & 15] = true;
     }
     if (s->profiling) RT_CHECK(s, cudaEventRecord(s->ev[0], stream));
     pve4_offsets_kernel<<<1, 1024, 0, stream>>>(s->st.n_ctrl, s->off4, B);
     RT_CHECK(s, cudaGetLastError());
-    if (s->lane_num == 4)
-        pve4_step_kernel<4><<<(B + PVE4_WARPS - 1) / PVE4_WARPS, 32 * PVE4_WARPS, smem, stream>>>(s->prm4, s->st, O, s->spawn_tick, nullptr, actions, s->off4);
+    const int grid = (B + PVE4_WARPS - 1) / PVE4_WARPS;
+    if (s->lane_num == 4 && small)
+        pve4_step_kernel<4, 64><<<grid, 32 * PVE4_WARPS, smem, stream>>>(s->prm4, s->st, O, s->spawn_tick, nullptr, actions, s->off4);
+    else if (s->lane_num == 4)
+        pve4_step_kernel<4, 128><<<grid, 32 * PVE4_WARPS, smem, stream>>>(s->prm4, s->st, O, s->spawn_tick, nullptr, actions, s->off4);
+    else if (small)
+        pve4_step_kernel<8, 64><<<grid, 32 * PVE4_WARPS, smem, stream>>>(s->prm4, s->st, O, s->spawn_tick, s->draws, actions, s->off4);
     else
-        pve4_step_kernel<8><<<(B + PVE4_WARPS - 1) / PVE4_WARPS, 32 * PVE4_WARPS, smem, stream>>>(s->prm4, s->st, O, s->spawn_tick, s->draws, actions, s->off4);
+        pve4_step_kernel<8, 128><<<grid, 32 * PVE4_WARPS, smem, stream>>>(s->prm4, s->st, O, s->spawn_tick, s->draws, actions, s->off4);
     RT_CHECK(s, cudaGetLastError());
     if (s->profiling) RT_CHECK(s, cudaEventRecord(s->ev[1], stream));
     const int G = s->n_groups;
@@ -720,7 +729,9 @@ int32_t pve_create(const pve_config *cfg, int32_t device, pve_scene **out) {
             snprintf(s->err, sizeof s->err, "lane_num = %d holds at most %d vehicles per intersection", s->lane_num, PVE4_LC);
             return PVE_EINVAL;
         }
-        VC = 128; AC = AC < 96 ? 96 : AC; s->smem_bytes = sizeof(Pve4Smem);
+        /* two capacity classes on this path: 64/64 and 128/>=96 */
+        if (cfg->veh_cap <= 64) { VC = 64; AC = 64; s->smem_bytes = sizeof(Pve4SmemT<64>); }
+        else { VC = 128; AC = AC < 96 ? 96 : AC; s->smem_bytes = sizeof(Pve4Smem); }
     }
     s->cfg.veh_cap = VC;          /* rounded up to the capacity class; see pve_veh_cap() */
     s->cfg.agent_cap = AC;

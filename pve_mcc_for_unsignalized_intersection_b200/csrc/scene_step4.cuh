@@ -63,23 +63,26 @@ struct Pve4Params {
 };
 
 /* shared memory of one intersection (one warp) */
-struct alignas(16) Pve4Smem {
+template <int LC_>      /* list capacity == vehicle slots staged per intersection: 64 (16 KB of shared memory less per CTA) or 128 */
+struct alignas(16) Pve4SmemT {
+    static constexpr int LC = LC_;
     pve_env_header h;                              /* first: copied with 16-byte accesses */
-    double p[PVE4_LC], v[PVE4_LC], a[PVE4_LC], jerk[PVE4_LC], js[PVE4_LC], virdis[PVE4_LC];
-    double lpos[PVE4_LC], tpos[PVE4_LC];          /* the current route's list (sorted); candidate positions */
-    float rew[PVE4_LC];                            /* reward of output row g (overrides included) */
-    int32_t uid[PVE4_LC], coll[PVE4_LC];
-    uint32_t step[PVE4_LC];
-    int16_t hdr[PVE4_LC];                          /* vir_header as a vehicle slot, or -1 */
-    uint16_t lslot[PVE4_LC], agent[PVE4_LC], newpos[PVE4_LC], outrow[PVE4_LC], rowveh[PVE4_LC];
-    uint8_t lane_of[PVE4_LC], intent[PVE4_LC], ctl[PVE4_LC], ctl_step[PVE4_LC], fin[PVE4_LC], del[PVE4_LC], lock[PVE4_LC],
-        done_row[PVE4_LC], fin_now[PVE4_LC], ltag[PVE4_LC], tmem[PVE4_LC], ttag[PVE4_LC];
-    int8_t lock_a[PVE4_LC];
+    double p[LC_], v[LC_], a[LC_], jerk[LC_], js[LC_], virdis[LC_];
+    double lpos[LC_], tpos[LC_];          /* the current route's list (sorted); candidate positions */
+    float rew[LC_];                            /* reward of output row g (overrides included) */
+    int32_t uid[LC_], coll[LC_];
+    uint32_t step[LC_];
+    int16_t hdr[LC_];                          /* vir_header as a vehicle slot, or -1 */
+    uint16_t lslot[LC_], agent[LC_], newpos[LC_], outrow[LC_], rowveh[LC_];
+    uint8_t lane_of[LC_], intent[LC_], ctl[LC_], ctl_step[LC_], fin[LC_], del[LC_], lock[LC_],
+        done_row[LC_], fin_now[LC_], ltag[LC_], tmem[LC_], ttag[LC_];
+    int8_t lock_a[LC_];
     int32_t misc[16];                              /* see P4M_* */
     int32_t spawn[PVE4_MAXNL], spawn_int[PVE4_MAXNL], spawn_uid[PVE4_MAXNL];
     int16_t nbr[8];
     int32_t lane_off[PVE4_MAXNL + 1];
 };
+typedef Pve4SmemT<PVE4_LC> Pve4Smem;
 enum { P4M_NA = 0, P4M_N, P4M_IDX, P4M_GOUT, P4M_COLL, P4M_LOCK, P4M_NREM, P4M_PASSED, P4M_PSTEP, P4M_Q5U, P4M_COLLAG, P4M_NSPAWN,
        P4M_NCTRL, P4M_SURV };
 
@@ -201,10 +204,10 @@ PVE_DEV void pve8_world_xy(const Pve4Params &P, double p, int i, int m, double *
 
 /* one tick of intersection b.  rows_cur: the stored rows (indexed by the vehicle slots of the tick's start, rewritten at
  * the end for the next tick); rows_new: scratch for the rows computed this tick (same indexing). */
-template <int NLN>      /* lane_num: 4 or 8 */
+template <int NLN, class SMEM>      /* lane_num: 4 or 8; SMEM: Pve4SmemT<64> or <128> */
 PVE_DEV void pve4_step_block(const Pve4Params &P, const PveState &S, const pve_outputs &O,
                              const int32_t *PVE_RESTRICT spawn_tick, const uint8_t *PVE_RESTRICT draws,
-                             const float *PVE_RESTRICT actions, const int b, Pve4Smem &M, const int64_t obase) {
+                             const float *PVE_RESTRICT actions, const int b, SMEM &M, const int64_t obase) {
     constexpr int PVE4_NLX = NLN;
     const size_t vbase = (size_t)b * (size_t)P.VC;
     float *const rows_cur = S.row0[0] + vbase * PVE_OBS_W;
@@ -458,7 +461,7 @@ PVE_DEV void pve4_step_block(const Pve4Params &P, const PveState &S, const pve_o
             for (; k < M.lane_off[i + 1]; ++k) if (!M.del[k]) { M.newpos[k] = (uint16_t)pos++; ++cnt; }
             M.spawn[i] = 0;
             if (tick >= M.h.next_spawn[i] && cnt < 255) {                                         /* TIS:379 */
-                if (surv + granted < P.VC && surv + granted < PVE4_LC) {
+                if (surv + granted < P.VC && surv + granted < SMEM::LC) {
                     M.spawn[i] = 1 + pos;                         /* slot + 1 */
                     if (NLN == 4) {
                         M.spawn_int[i] = M.h.pad_[0] % 3;         /* TIS:387: intention_re % 3 */

@@ -18,6 +18,20 @@ def test_golden_rollout4_direct(name):
     assert scene.backend == "cuda-sm_100a" and scene.launch_info["dual"] is False
 
 
+@pytest.mark.parametrize("name", E.ROLLOUTS4)
+def test_golden_rollout4_direct_in_the_64_class(name, monkeypatch):
+    """The small capacity class of this path (64 vehicle slots, lists of 64 entries: half the shared memory per warp)
+    against the same rollouts of the reference."""
+    monkeypatch.setattr(E, "CAPS4", (64, 64))
+    scene = E.run_golden("cuda", name)
+    assert scene.veh_cap == 64 and scene.backend == "cuda-sm_100a"
+
+
+def test_free_running_lane4_matches_oracle_in_the_64_class(monkeypatch):
+    monkeypatch.setattr(E, "CAPS4", (64, 64))
+    assert E.free_run4("cuda", 6, 1400, 300, seed=5) > 9000
+
+
 def test_free_running_lane4_matches_oracle():
     assert E.free_run4("cuda", 6, 1400, 300, seed=5) > 9000
     assert E.free_run4("cuda", 4, 600, 300, seed=8, vm=6) > 1500

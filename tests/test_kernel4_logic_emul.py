@@ -16,12 +16,16 @@ from test_oracle4_golden import ROLLOUTS4, ROLLOUTS8, load4
 BACKEND = "emul"
 
 
+CAPS4 = None            # (veh_cap, agent_cap) of the scenes built here; None = the library's default class (128 / 96)
+
+
 def make_scene4(backend, B, vm=5, collision_thr=2, lanes=4):
     cfg = SceneConfig(vm=vm, collision_thr=collision_thr, lane_num=lanes)
+    caps = {} if CAPS4 is None else {"veh_cap": CAPS4[0], "agent_cap": CAPS4[1]}
     if backend == "cuda":
-        return BatchedScene(B, cfg, device="cuda:0")
+        return BatchedScene(B, cfg, device="cuda:0", **caps)
     from emul.build_emul import build_emul
-    return BatchedScene(B, cfg, device="cpu", _library=build_emul())
+    return BatchedScene(B, cfg, device="cpu", _library=build_emul(), **caps)
 
 
 def check_state(st, snap, b, what):
