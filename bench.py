@@ -657,7 +657,8 @@ def graft_arm(args, rank, world, local_rank, veh_cap, agent_cap):
         }
         if actor is not None:
             # 2 * (28*64 + 64*64 + 64) multiply-adds per agent; bytes: 112 B row in, 4 B action out, 8 B meta per slot
-            line["actor"] = {"kernel": "pve_actor_tc_kernel" if os.environ.get("PVE_ACTOR_IMPL", "tc5") == "tc5" else "pve_actor_%s_kernel" % os.environ["PVE_ACTOR_IMPL"],
+            line["actor"] = {"kernel": {"tc5": "pve_actor_tc_kernel", "mma": "pve_actor_mma_kernel", "ffma": "pve_actor_kernel"}.get(
+                                 os.environ.get("PVE_ACTOR_IMPL", ""), "pve_actor_tc_kernel" if B * veh_cap >= 16384 else "pve_actor_mma_kernel"),
                              "kernel_ms_per_launch": float(sum(actor_ms)) / K,
                              "gflop_per_launch": 2 * 5952 * kA / K / 1e9,
                              "tflops": 2 * 5952 * kA / (float(sum(actor_ms)) * 1e-3) / 1e12,

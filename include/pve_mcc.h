@@ -262,6 +262,12 @@ int32_t pve_actor_forward(pve_actor *a, const float *rows_dev, int64_t n_rows, f
  * `+ noise_scale * noise_dev[b][k]` (main.py:44; noise_dev may be null) */
 int32_t pve_act(pve_scene *s, pve_actor *a, const float *noise_dev, float noise_scale, float *actions_dev,
                 void *stream);
+/* n_ticks x { pve_act; pve_step }: the test drivers' loop main.py:394-441 / 553-575 (policy on every controlled vehicle,
+ * step(), scene_update(), delete_vehicle()) enqueued from C, so that a small scene's evaluation is not bound by the
+ * caller's per-tick overhead.  `out` receives every tick's outputs in turn (the last tick's remain); the running
+ * tallies are those of pve_stats / the per-intersection statistics.  Asynchronous like its two halves. */
+int32_t pve_rollout(pve_scene *s, pve_actor *a, int32_t n_ticks, const float *noise_dev, float noise_scale,
+                    float *actions_dev, const pve_outputs *out, void *stream);
 
 /* device-side row count: like pve_actor_forward for the first min(max_rows, n_rows_dev[0] * mult) rows of a dense
  * matrix; nothing is read back (used on the 7 rows of every agent's observation: mult = 7, n_rows_dev =

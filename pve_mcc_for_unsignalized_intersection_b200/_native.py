@@ -95,6 +95,7 @@ def load_library(path=None):
     lib.pve_actor_destroy.restype = None
     lib.pve_actor_forward.argtypes = [vp, vp, i64, vp, vp]
     lib.pve_act.argtypes = [vp, vp, vp, C.c_float, vp, vp]
+    lib.pve_rollout.argtypes = [vp, vp, i32, vp, C.c_float, vp, C.POINTER(PveOutputs), vp]
     lib.pve_actor_forward_n.argtypes = [vp, vp, i64, vp, i32, vp, vp]
     lib.pve_critic_create.argtypes = [vp, i32, i32, C.POINTER(vp)]
     lib.pve_critic_destroy.argtypes = [vp]

@@ -141,3 +141,14 @@ class BatchedActor:
                               C.c_float(float(noise_scale)), out.data_ptr(), self._stream())
         scene._check(rc)
         return out
+
+    def rollout(self, scene, n_ticks, out=None, noise=None, noise_scale=0.0):
+        """``n_ticks`` x (``act``; ``scene.step``) enqueued by the library (``pve_rollout``): the test drivers' loop
+        main.py:553-575 without a Python round trip per tick.  Returns ``scene.out`` (the last tick's outputs)."""
+        if out is None:
+            out = torch.empty(scene.B, scene.veh_cap, dtype=torch.float32, device=self.device)
+        scene.out._n = None
+        rc = self.lib.pve_rollout(scene._h, self._h, int(n_ticks), noise.data_ptr() if noise is not None else None,
+                                  C.c_float(float(noise_scale)), out.data_ptr(), C.byref(scene._out_native), self._stream())
+        scene._check(rc)
+        return scene.out

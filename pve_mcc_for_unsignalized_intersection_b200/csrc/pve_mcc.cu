@@ -1268,13 +1268,15 @@ struct pve_actor {
     int *ticket;                 /* [2] work counter + exit counter of the kernel, zero between launches */
     int device;
     int blocks_ffma, blocks_mma; /* one resident wave of CTAs each */
-    int use_mma;                 /* 2 = tcgen05 kernel (default), 1 = mma.sync kernel (PVE_ACTOR_IMPL=mma), 0 = CUDA cores (=ffma) */
+    int use_mma;                 /* 3 = by size (default: tcgen05 from PVE_TC_MIN_ROWS candidate rows on, mma.sync below: its fixed cost is
+                                  * ~4 us lower), 2 = tcgen05 kernel (PVE_ACTOR_IMPL=tc5), 1 = mma.sync kernel (=mma), 0 = CUDA cores (=ffma) */
     uint16_t *tw_dev;            /* shared-memory image of the split weights (tcgen05 kernel) */
     PvtVecs vecs;                /* bias / LayerNorm / last-layer vectors: a kernel parameter of the tcgen05 kernel */
     int blocks_tc;
     float *zero_dev;             /* [28] zeros + [1] the action of an all-zero row (a missing neighbour, TIS:1334) */
 };
 
+#define PVE_TC_MIN_ROWS 16384     /* candidate rows (vehicle slots / matrix rows) from which the tcgen05 kernels are the faster ones */
 #ifndef PVE_HOST_EMULATION
 static cudaError_t launch_actor(pve_actor *a, const float *rows, const pve_veh_meta *meta, const int32_t *n_veh,
                                 const float *noise, float noise_scale, float *actions, int slots_per_env, int n_env,
@@ -1292,8 +1294,8 @@ int32_t pve_actor_create(const float *weights_host, int32_t n_floats, int32_t de
     pve_actor *a = (pve_actor *)calloc(1, sizeof(pve_actor));
     if (!a) return PVE_ENOMEM;
     a->device = device;
-    a->use_mma = 2;
-    if (const char *impl = getenv("PVE_ACTOR_IMPL")) a->use_mma = strcmp(impl, "ffma") == 0 ? 0 : strcmp(impl, "mma") == 0 ? 1 : 2;
+    a->use_mma = 3;
+    if (const char *impl = getenv("PVE_ACTOR_IMPL")) a->use_mma = strcmp(impl, "ffma") == 0 ? 0 : strcmp(impl, "mma") == 0 ? 1 : strcmp(impl, "tc5") == 0 ? 2 : 3;
     int sms = 0, per_sm = 0;
     if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device) != cudaSuccess || sms <= 0) sms = 148;
     bool ok = cudaFuncSetAttribute(pve_actor_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PVA_SMEM_BYTES) == cudaSuccess
@@ -1360,11 +1362,12 @@ static cudaError_t launch_actor(pve_actor *a, const float *rows, const pve_veh_m
                                 const float *noise, float noise_scale, float *actions, int slots_per_env, int n_env,
                                 long long n_slots, pve_stream_t stream, const int32_t *limit_dev, int limit_mult,
                                 const uint8_t *mask, int slot_step) {
-    if (a->use_mma == 2) {
+    const int impl = a->use_mma == 3 ? (n_slots >= PVE_TC_MIN_ROWS ? 2 : 1) : a->use_mma;
+    if (impl == 2) {
         const int blocks = n_env < a->blocks_tc ? n_env : a->blocks_tc;
         pve_actor_tc_kernel<<<blocks, PVT_THREADS_ACTOR, PVT_ACTOR_SMEM, stream>>>(a->vecs, a->tw_dev, rows, meta, n_veh, noise, noise_scale,
                                                                                 actions, slots_per_env, n_env, n_slots, a->ticket, limit_dev, limit_mult, mask, slot_step);
-    } else if (a->use_mma) {
+    } else if (impl) {
         const int blocks = n_env < a->blocks_mma ? n_env : a->blocks_mma;
         pve_actor_mma_kernel<<<blocks, PVM_THREADS, PVM_SMEM_BYTES, stream>>>(a->pw_dev, rows, meta, n_veh, noise, noise_scale,
                                                                            actions, slots_per_env, n_env, n_slots, a->ticket, limit_dev, limit_mult, mask, slot_step);
@@ -1418,6 +1421,18 @@ int32_t pve_act(pve_scene *s, pve_actor *a, const float *noise_dev, float noise_
 #endif
 }
 
+int32_t pve_rollout(pve_scene *s, pve_actor *a, int32_t n_ticks, const float *noise_dev, float noise_scale,
+                    float *actions_dev, const pve_outputs *out, void *stream) {
+    if (!s || !a || !actions_dev || !out || n_ticks < 0) return PVE_EINVAL;
+    for (int32_t t = 0; t < n_ticks; ++t) {
+        int32_t rc = pve_act(s, a, noise_dev, noise_scale, actions_dev, stream);
+        if (rc != PVE_OK) return rc;
+        rc = pve_step(s, actions_dev, out, stream);
+        if (rc != PVE_OK) return rc;
+    }
+    return PVE_OK;
+}
+
 int32_t pve_actor_forward_n(pve_actor *a, const float *rows_dev, int64_t max_rows, const int32_t *n_rows_dev,
                             int32_t mult, float *actions_dev, void *stream_) {
     if (!a || !rows_dev || !actions_dev || !n_rows_dev || max_rows < 0 || mult < 1) return PVE_EINVAL;
@@ -1438,7 +1453,7 @@ struct pve_critic {
     float *w_dev;                /* flat fp32 parameters (FFMA kernel) */
     uint32_t *pw_dev;            /* split bf16 fragments + vectors (tensor-core kernel) */
     int device, blocks, blocks_mma;
-    int use_mma;                 /* 2 = tcgen05 kernel (default), 1 = mma.sync kernel (PVE_CRITIC_IMPL=mma), 0 = CUDA cores (=ffma) */
+    int use_mma;                 /* 3 = by size (default), 2 = tcgen05 kernel (PVE_CRITIC_IMPL=tc5), 1 = mma.sync kernel (=mma), 0 = CUDA cores (=ffma) */
     uint16_t *tw_dev;            /* shared-memory image of the split weights (tcgen05 kernel) */
     PvtVecs vecs;
     int blocks_tc;
@@ -1456,8 +1471,8 @@ int32_t pve_critic_create(const float *weights_host, int32_t n_floats, int32_t d
     c->device = device;
     int sms = 0, per_sm = 0;
     if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device) != cudaSuccess || sms <= 0) sms = 148;
-    c->use_mma = 2;
-    if (const char *impl = getenv("PVE_CRITIC_IMPL")) c->use_mma = strcmp(impl, "ffma") == 0 ? 0 : strcmp(impl, "mma") == 0 ? 1 : 2;
+    c->use_mma = 3;
+    if (const char *impl = getenv("PVE_CRITIC_IMPL")) c->use_mma = strcmp(impl, "ffma") == 0 ? 0 : strcmp(impl, "mma") == 0 ? 1 : strcmp(impl, "tc5") == 0 ? 2 : 3;
     bool ok = cudaFuncSetAttribute(pve_critic_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PVC_SMEM_BYTES) == cudaSuccess
               && cudaFuncSetAttribute(pve_critic_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PVQ_SMEM_BYTES) == cudaSuccess
               && cudaFuncSetAttribute(pve_critic_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PVT_CRITIC_SMEM) == cudaSuccess;
@@ -1508,12 +1523,13 @@ int32_t pve_critic_forward(pve_critic *c, const float *obs_dev, const float *act
 #else
     if (max_rows == 0) return PVE_OK;
     const long long tiles = (max_rows + PVC_TILE - 1) / PVC_TILE;              /* both kernels: 128 agents per tile */
-    if (c->use_mma == 2) {
+    const int impl = c->use_mma == 3 ? (max_rows >= PVE_TC_MIN_ROWS ? 2 : 1) : c->use_mma;
+    if (impl == 2) {
         const long long ctas = (tiles + PVT_GROUPS - 1) / PVT_GROUPS;
         const int blocks = (int)(ctas < c->blocks_tc ? ctas : c->blocks_tc);
         pve_critic_tc_kernel<<<blocks, PVT_THREADS_CRITIC, PVT_CRITIC_SMEM, (pve_stream_t)stream_>>>(c->vecs, c->tw_dev, obs_dev, act7_dev, q_dev,
                                                                                                   (long long)max_rows, n_rows_dev);
-    } else if (c->use_mma) {
+    } else if (impl) {
         const int blocks = (int)(tiles < c->blocks_mma ? tiles : c->blocks_mma);
         pve_critic_mma_kernel<<<blocks, PVQ_THREADS, PVQ_SMEM_BYTES, (pve_stream_t)stream_>>>(c->pw_dev, obs_dev, act7_dev, q_dev,
                                                                                              (long long)max_rows, n_rows_dev);

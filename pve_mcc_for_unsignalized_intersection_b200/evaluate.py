@@ -60,16 +60,18 @@ def evaluate_tables(tables, weights, ticks=36000, vm=5, collision_thr=2, device=
     dev = scene.device
     acts = torch.empty(B, scene.veh_cap, dtype=torch.float32, device=dev)
     # the tallies of main.py:567-571 (jerks of finished vehicles, lock events, agents with collision > 0) are kept per
-    # intersection by the step kernel itself (pve_env_stats_dev): the loop is two launches per tick and never
-    # synchronises; the sticky overflow counter is looked at every 2000 ticks so that a run that left the capacity class
+    # intersection by the step kernel itself (pve_env_stats_dev): the loop is enqueued by the library (pve_rollout, 1000
+    # ticks per call) and never synchronises; the sticky overflow counter is looked at every 2000 ticks so that a run that left the capacity class
     # stops early
-    for i in range(ticks):
-        actor.act(scene, out=acts)                                   # main.py:557-565
-        scene.step(acts)                                             # main.py:566 (+ delete_vehicle, 575)
-        if i % 2000 == 1999 and scene.stats()["overflow"] != 0:
+    done = 0
+    while done < ticks:
+        n = min(1000, ticks - done)
+        actor.rollout(scene, n, out=acts)                            # main.py:557-566 (+ delete_vehicle, 575), n ticks
+        done += n
+        if done % 2000 == 0 and scene.stats()["overflow"] != 0:
             break
-        if progress and i % 1000 == 0:
-            progress(i, scene)
+        if progress:
+            progress(done - 1, scene)
     es = scene.env_stats().cpu().numpy()
     names = list(scene.ENV_STAT_NAMES)
     coll = es[:, names.index("collided_agent_steps")]

@@ -104,6 +104,30 @@ def test_act_on_scene_matches_forward_and_masks(impl):
     assert torch.all(noisy[~mask] == 0)
 
 
+def test_rollout_entry_point_equals_the_python_loop():
+    """pve_rollout (n ticks of act + step enqueued by the library) against the same ticks driven from Python: state,
+    counters and the last tick's outputs bit for bit."""
+    from pve_mcc_for_unsignalized_intersection_b200.arrivals import synthetic_arrivals
+    w = ActorWeights.from_npz(os.path.join(GOLD, "actor_agent1.npz"))
+    B, T = 48, 333
+    scenes = [P.make_scene("cuda", B, vm=5) for _ in range(2)]
+    actor = BatchedActor(w)
+    for sc in scenes:
+        sc.reset(synthetic_arrivals(B, 1000, 60.0, seed=21), warmup=True)
+    acts = torch.empty(B, scenes[0].veh_cap, device="cuda")
+    for _ in range(T):
+        scenes[0].step(actor.act(scenes[0], out=acts))
+    out1 = actor.rollout(scenes[1], T - 100)
+    out1 = actor.rollout(scenes[1], 100)
+    st0, st1 = scenes[0].get_state(), scenes[1].get_state()
+    for k in st0:
+        assert np.array_equal(np.asarray(st0[k]), np.asarray(st1[k])), k
+    n = scenes[0].out.n_agents
+    assert n == out1.n_agents and n > 0
+    assert torch.equal(scenes[0].out.obs[:n], out1.obs[:n]) and torch.equal(scenes[0].out.reward[:n], out1.reward[:n])
+    assert scenes[0].stats() == scenes[1].stats()
+
+
 def test_closed_loop_reproduces_config1_of_the_reference():
     """BASELINE.json config 1: pretrained actor, arvTimeNewVeh_new_1000_12.mat, 1000 ticks -- here with the
     CUDA actor and the CUDA scene in a loop, against the trace recorded from the unmodified reference scene
