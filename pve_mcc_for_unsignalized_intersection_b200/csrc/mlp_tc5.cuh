@@ -8,9 +8,9 @@
  *
  * Shape of the work.  One persistent CTA per SM: THREE GROUPS of 128 threads, each group evaluating 128 rows per round
  * with its own operand buffer, its own 64 columns of tensor memory and its own mbarrier, so that one group's tensor-core
- * phases and global-memory latencies hide behind the other groups' epilogues; in the actor a 13th warp is the PRODUCER
- * (tickets of intersections, meta loads eight deep, ballot compaction of the controlled slots into a ring in shared
- * memory) and runs ahead of the groups.  THREAD r OF A GROUP OWNS ROW r end to end:
+ * phases and global-memory latencies hide behind the other groups' epilogues; in the actor four more warps are PRODUCERS
+ * (tickets of intersections, meta loads twelve deep, ballot compaction of the controlled slots into a ring in shared
+ * memory; ring positions are reserved with an atomic and every entry validates itself) and run ahead of the groups.  THREAD r OF A GROUP OWNS ROW r end to end:
  *   - it loads its 28 inputs, applies the first LayerNorm in registers, splits the result and stores the three bf16
  *     operands straight into the K-major, un-swizzled core-matrix layout of a tcgen05 shared-memory descriptor
  *     (core matrix = 8 rows x 16 bytes; a thread's 16 bytes of one K-chunk sit at  chunk * 2048 + r * 16, so a warp's
@@ -51,15 +51,13 @@ struct PvtVecs {
 #define PVT_GROUPS 3
 #define PVT_TILE 128
 #define PVT_TMEM_COLS 256
-#define PVT_RING 2048
+#define PVT_RING 4096
+#define PVT_MARGIN 1536                                    /* ring slots never handed out: three other producers may reserve at the same time, and the groups free their tiles out of order */
 #ifndef PVT_BATCH
 #define PVT_BATCH 3                                        /* intersections per ticket */
 #endif
 #ifndef PVT_PCHUNKS
 #define PVT_PCHUNKS 12                                     /* 32-slot chunks a producer loads at once */
-#endif
-#ifndef PVT_BACKLOG
-#define PVT_BACKLOG PVT_RING                               /* queued-but-unclaimed entries beyond which a producer holds its commit */
 #endif
 #ifndef PVT_PREFETCH
 #define PVT_PREFETCH 1                                     /* draw the next ticket before this one's loads (1) or after its commit (0) */
@@ -109,8 +107,8 @@ struct PvtCtrl {                       /* in dynamic shared memory, after the bu
     uint64_t wbar;                     /* the weights have landed */
     uint64_t mbar[PVT_GROUPS];         /* a group's products are complete */
     uint32_t tmem_slot;
-    int q_tail, q_head, q_free, q_done;
-    int p_seq, p_commit, p_done;       /* producers: next sequence number, whose turn it is to append, how many have finished */
+    int q_res, q_head, q_free, q_done; /* ring positions reserved by the producers / claimed by the groups / read and cleared; all producers done */
+    int p_done;                        /* producers that have finished */
     int grp_head[PVT_GROUPS], grp_n[PVT_GROUPS];
 };
 #define PVT_A_SPLIT(CRITIC) ((CRITIC) ? 20480 : 16384)
@@ -355,7 +353,7 @@ __device__ __forceinline__ void pvt_setup(unsigned char *smem, const uint16_t *_
         asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(pvt_saddr(&C->wbar)), "r"((uint32_t)PVT_W_BYTES) : "memory");
         asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                      :: "r"(pvt_saddr(smem)), "l"(PW), "r"((uint32_t)PVT_W_BYTES), "r"(pvt_saddr(&C->wbar)) : "memory");
-        C->q_tail = 0; C->q_head = 0; C->q_free = 0; C->q_done = 0; C->p_seq = PVT_PRODUCERS; C->p_commit = 0; C->p_done = 0;
+        C->q_res = 0; C->q_head = 0; C->q_free = 0; C->q_done = 0; C->p_done = 0;
     }
     if (!CRITIC)                       /* ones block: [2 chunks][128 rows][8 bf16], element (row, 0) = 1 */
         for (int i = tid; i < PVT_ONES_BYTES / 16; i += blockDim.x)
@@ -403,6 +401,7 @@ pve_actor_tc_kernel(const __grid_constant__ PvtVecs V, const uint16_t *__restric
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     uint32_t tmem;
     PvtGroup G;
+    for (int i = tid; i < PVT_RING; i += PVT_THREADS_ACTOR) ring[i] = -1;       /* empty; ordered by the barrier inside pvt_setup */
     pvt_setup<false>(pvt_smem, PW, C, G, tmem);
 
     if (warp < 4 * PVT_GROUPS) {
@@ -417,9 +416,9 @@ pve_actor_tc_kernel(const __grid_constant__ PvtVecs V, const uint16_t *__restric
                 int h, n;
                 const long long t0 = clock64();
                 for (;;) {
-                    const int done = *reinterpret_cast<volatile int *>(&C->q_done);      /* before the tail: a set flag means the tail is final */
+                    const int done = *reinterpret_cast<volatile int *>(&C->q_done);      /* before the count: a set flag means it is final */
                     __threadfence_block();
-                    const int t = *reinterpret_cast<volatile int *>(&C->q_tail);
+                    const int t = *reinterpret_cast<volatile int *>(&C->q_res);
                     h = *reinterpret_cast<volatile int *>(&C->q_head);
                     const int avail = t - h;
                     n = avail >= PVT_TILE ? PVT_TILE : (done ? avail : -1);
@@ -435,7 +434,17 @@ pve_actor_tc_kernel(const __grid_constant__ PvtVecs V, const uint16_t *__restric
             const int n_valid = *reinterpret_cast<volatile int *>(&C->grp_n[g]), head = *reinterpret_cast<volatile int *>(&C->grp_head[g]);
             if (n_valid == 0) break;
             const bool valid = G.gt < n_valid;
-            const long long gs = valid ? (long long)ring[(head + G.gt) & (PVT_RING - 1)] : 0;
+            long long gs = 0;
+            if (valid) {                                             /* the position is reserved; its entry may still be on its way */
+                volatile int *const e = ring + ((head + G.gt) & (PVT_RING - 1));
+                int v = *e;
+                if (v < 0) {
+                    const long long t0 = clock64();
+                    while ((v = *e) < 0) { __nanosleep(20); PVT_TIMEOUT(t0); }
+                }
+                *e = -1;
+                gs = v;
+            }
             pvt_gsync(G.id);                                         /* the ring entries and the claim have been read */
             if (G.gt == 0) atomicAdd(&C->q_free, n_valid);
             PVT_STAMP(G, 1);
@@ -448,27 +457,25 @@ pve_actor_tc_kernel(const __grid_constant__ PvtVecs V, const uint16_t *__restric
             PVT_STAMP(G, 10);
         }
     } else {
-        /* ---- a producer warp: controlled slots of PVT_BATCH intersections per ticket -> ring.  The four producers load
-         * concurrently and append in the order in which they drew their tickets (p_seq / p_commit). ---- */
+        /* ---- a producer warp: controlled slots of PVT_BATCH intersections per ticket -> ring.  The four producers work
+         * independently: a producer reserves ring positions with one atomic and fills them; an entry validates itself (>= 0),
+         * so nobody waits for a turn (appending in ticket order cost ~0.6 us per producer at the start, one after the other,
+         * while two of the three groups had nothing to claim). ---- */
         const int cpe = (slots_per_env + 31) >> 5;                               /* 32-slot chunks per intersection */
         const unsigned lt = (1u << lane) - 1u;
         /* the first ticket of every producer is static (no round trip to the ticket counter before the first loads),
          * the others are drawn from ticket[0] and start behind the static ones */
         const int pw = warp - 4 * PVT_GROUPS, dyn0 = (int)gridDim.x * PVT_PRODUCERS * PVT_BATCH;
-        int tk = ((int)blockIdx.x * PVT_PRODUCERS + pw) * PVT_BATCH, seq = pw;
+        int tk = ((int)blockIdx.x * PVT_PRODUCERS + pw) * PVT_BATCH;
         bool first = true;
         while (first || tk < n_env) {
-            const int envb = tk, my_seq = seq;
-            int ntk = 0, nseq = 0;
-            if (PVT_PREFETCH && lane == 0) {                                     /* the next ticket travels meanwhile */
-                ntk = dyn0 + atomicAdd(&ticket[0], PVT_BATCH);
-                if (ntk < n_env) nseq = atomicAdd(&C->p_seq, 1);
-            }
+            const int envb = tk;
+            int ntk = 0;
+            if (PVT_PREFETCH && lane == 0) ntk = dyn0 + atomicAdd(&ticket[0], PVT_BATCH);    /* the next ticket travels meanwhile */
             const int n_e = max(0, min(n_env, envb + PVT_BATCH) - envb);
             const int nvl = (meta && lane < n_e) ? n_veh[envb + lane] : slots_per_env;
             const int n_chunks = n_e * cpe;
             int e = 0, c = 0;
-            bool turn = false;
             for (int q0 = 0; q0 < n_chunks; q0 += PVT_PCHUNKS) {
                 uint32_t pk[PVT_PCHUNKS]; bool pre[PVT_PCHUNKS]; int gi[PVT_PCHUNKS], sv[PVT_PCHUNKS], nvu[PVT_PCHUNKS];
 #pragma unroll
@@ -493,44 +500,32 @@ pve_actor_tc_kernel(const __grid_constant__ PvtVecs V, const uint16_t *__restric
                     bal[u] = __ballot_sync(0xffffffffu, want);
                     cnt += __popc(bal[u]);
                 }
+                int base = 0;
                 if (lane == 0) {
                     const long long t0 = clock64();
-                    if (!turn)                                                   /* this ticket's turn to append */
-                        while (*reinterpret_cast<volatile int *>(&C->p_commit) != my_seq) { __nanosleep(40); PVT_TIMEOUT(t0); }
-                    const int tl = *reinterpret_cast<volatile int *>(&C->q_tail);
-                    while (tl + cnt - *reinterpret_cast<volatile int *>(&C->q_free) > PVT_RING
-                           || (PVT_BACKLOG < PVT_RING && tl - *reinterpret_cast<volatile int *>(&C->q_head) > PVT_BACKLOG)) { __nanosleep(100); PVT_TIMEOUT(t0); }
+                    while (*reinterpret_cast<volatile int *>(&C->q_res) + cnt + PVT_MARGIN - *reinterpret_cast<volatile int *>(&C->q_free) > PVT_RING) {
+                        __nanosleep(100); PVT_TIMEOUT(t0);
+                    }
+                    base = atomicAdd(&C->q_res, cnt);
                 }
-                turn = true;
-                __syncwarp();
-                int tail = *reinterpret_cast<volatile int *>(&C->q_tail);
+                base = __shfl_sync(0xffffffffu, base, 0);
 #pragma unroll
                 for (int u = 0; u < PVT_PCHUNKS; ++u) {
-                    if ((bal[u] >> lane) & 1u) ring[(tail + __popc(bal[u] & lt)) & (PVT_RING - 1)] = gi[u] * slot_step;
-                    tail += __popc(bal[u]);
+                    if ((bal[u] >> lane) & 1u)
+                        *reinterpret_cast<volatile int *>(&ring[(base + __popc(bal[u] & lt)) & (PVT_RING - 1)]) = gi[u] * slot_step;
+                    base += __popc(bal[u]);
                 }
-                __threadfence_block();
-                __syncwarp();
-                if (lane == 0) *reinterpret_cast<volatile int *>(&C->q_tail) = tail;
-            }
-            if (lane == 0) {
-                if (!turn) {                                                     /* an empty static ticket still passes its turn on */
-                    const long long t0 = clock64();
-                    while (*reinterpret_cast<volatile int *>(&C->p_commit) != my_seq) { __nanosleep(40); PVT_TIMEOUT(t0); }
-                }
-                __threadfence_block();
-                *reinterpret_cast<volatile int *>(&C->p_commit) = my_seq + 1;
             }
             first = false;
-            if (!PVT_PREFETCH && lane == 0) {
-                ntk = dyn0 + atomicAdd(&ticket[0], PVT_BATCH);
-                if (ntk < n_env) nseq = atomicAdd(&C->p_seq, 1);
-            }
-            tk = __shfl_sync(0xffffffffu, ntk, 0); seq = __shfl_sync(0xffffffffu, nseq, 0);
+            if (!PVT_PREFETCH && lane == 0) ntk = dyn0 + atomicAdd(&ticket[0], PVT_BATCH);
+            tk = __shfl_sync(0xffffffffu, ntk, 0);
         }
         __threadfence_block();
         __syncwarp();
-        if (lane == 0 && atomicAdd(&C->p_done, 1) == PVT_PRODUCERS - 1) *reinterpret_cast<volatile int *>(&C->q_done) = 1;
+        if (lane == 0 && atomicAdd(&C->p_done, 1) == PVT_PRODUCERS - 1) {
+            __threadfence_block();
+            *reinterpret_cast<volatile int *>(&C->q_done) = 1;
+        }
     }
     pvt_teardown(tmem);
     if (tid == 0 && atomicAdd(&ticket[1], 1) == (int)gridDim.x - 1) { ticket[0] = 0; ticket[1] = 0; }
