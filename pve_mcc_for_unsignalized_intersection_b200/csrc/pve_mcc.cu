@@ -584,7 +584,8 @@ static int32_t launch_step(pve_scene *s, const float *actions, const pve_outputs
     bool done = false;
     if (s->dual) {
         done = true;
-        if (ACc == 96) RT_CHECK(s, (O.nbr_src ? launch_dual<128, 96, true>(s, actions, O, stream) : launch_dual<128, 96, false>(s, actions, O, stream)));
+        if (VCc == 192) RT_CHECK(s, (O.nbr_src ? launch_dual<192, 128, true>(s, actions, O, stream) : launch_dual<192, 128, false>(s, actions, O, stream)));
+        else if (ACc == 96) RT_CHECK(s, (O.nbr_src ? launch_dual<128, 96, true>(s, actions, O, stream) : launch_dual<128, 96, false>(s, actions, O, stream)));
         else RT_CHECK(s, (O.nbr_src ? launch_dual<128, 80, true>(s, actions, O, stream) : launch_dual<128, 80, false>(s, actions, O, stream)));
     }
 #define X(vc, ac)                                                                              \
@@ -740,8 +741,8 @@ int32_t pve_create(const pve_config *cfg, int32_t device, pve_scene **out) {
      * tick of 4 096 stress intersections: 128 threads 0.766 ms, 256: 0.586, 512: 0.487) */
     s->threads = cfg->threads == 0 ? (VC >= 384 ? 512 : 128) : cfg->threads;
 #ifndef PVE_HOST_EMULATION
-    /* dual mode for the default class with the default CTA size (env PVE_DUAL=0 turns it off) */
-    s->dual = (cfg->threads == 0 && VC == 128 && s->lane_num == 12) ? 1 : 0;
+    /* dual mode for the classes 128/80, 128/96 and 192/128 with the default CTA size (env PVE_DUAL=0 turns it off) */
+    s->dual = (cfg->threads == 0 && (VC == 128 || VC == 192) && s->lane_num == 12) ? 1 : 0;
     if (const char *d = getenv("PVE_DUAL")) s->dual = s->dual && atoi(d) != 0;
     s->dual_pdl = 0;      /* experiment knob: 1 = one stream, the small kernel as the big kernel's programmatic dependent */
     if (const char *d = getenv("PVE_DUAL_PDL")) s->dual_pdl = atoi(d) != 0;

@@ -120,15 +120,18 @@ def test_teacher_forced_stress_in_the_large_classes(veh_cap, agent_cap, headway,
     assert len(o_ref["reward"]) > 2 * 0.6 * agent_cap and o_ref["overflow"] == 0
 
 
-def test_dual_kernel_mode_equals_single_kernel_mode(monkeypatch):
+@pytest.mark.parametrize("caps", [(128, 96), (192, 128)])
+def test_dual_kernel_mode_equals_single_kernel_mode(caps, monkeypatch):
     """The default launch (two concurrent kernels: small-class CTAs + the intersections that do not fit) and the
-    single-kernel launch (PVE_DUAL=0) give identical bytes, at a density where both kernels have work every tick."""
+    single-kernel launch (PVE_DUAL=0) give identical bytes, at a density where both kernels have work every tick;
+    for both capacity classes that run in dual mode."""
     B = 192
     tabs = synthetic_arrivals(B, 1200, 45.0, seed=31, rows=48)
     monkeypatch.setenv("PVE_DUAL", "1")
-    dual = P.make_scene("cuda", B, vm=5)
+    dual = P.make_scene("cuda", B, vm=5, veh_cap=caps[0], agent_cap=caps[1])
     monkeypatch.setenv("PVE_DUAL", "0")
-    single = P.make_scene("cuda", B, vm=5)
+    single = P.make_scene("cuda", B, vm=5, veh_cap=caps[0], agent_cap=caps[1])
+    assert dual.launch_info["dual"] is True and single.launch_info["dual"] is False and dual.veh_cap == caps[0]
     dual.reset(tabs, warmup=True)
     single.reset(tabs, warmup=True)
     gen = torch.Generator(device="cuda")
