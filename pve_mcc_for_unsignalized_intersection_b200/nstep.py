@@ -224,6 +224,12 @@ class NStepFolder:
             raise N.NativeError("n-step history table too small: %d slot conflicts (uid_slots must exceed the number of "
                                 "vehicles an intersection spawns during one agent's lifetime); create the folder with a "
                                 "larger uid_slots" % int(out[2]))
+        if self.scene.stats()["overflow"] != 0:
+            # an intersection outgrew its capacity class or the outputs did not fit out_cap: that tick's rows of the
+            # intersection were not emitted, so transitions folded from them are not the reference's
+            raise N.NativeError("the scene's sticky overflow counter is set (capacity class %d/%d or out_cap %d too small): "
+                                "the replay memory may hold transitions of ticks whose rows were not emitted"
+                                % (self.scene.veh_cap, self.scene.agent_cap, self.scene.out_cap))
         return {"num_experiences": int(out[0]), "last_added": int(out[1]), "slot_conflicts": int(out[2]), "pushes": int(out[3])}
 
     def __len__(self):
