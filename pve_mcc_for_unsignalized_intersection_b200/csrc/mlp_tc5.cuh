@@ -10,12 +10,14 @@
  * with its own operand buffer, its own 64 columns of tensor memory and its own mbarrier, so that one group's tensor-core
  * phases and global-memory latencies hide behind the other groups' epilogues; in the actor four more warps are PRODUCERS
  * (tickets of intersections, meta loads twelve deep, ballot compaction of the controlled slots into a ring in shared
- * memory; ring positions are reserved with an atomic and every entry validates itself) and run ahead of the groups.  THREAD r OF A GROUP OWNS ROW r end to end:
+ * memory; ring positions are reserved with an atomic and every entry validates itself) and run ahead of the groups.
+ * THREAD r OF A GROUP OWNS ROW r end to end:
  *   - it loads its 28 inputs, applies the first LayerNorm in registers, splits the result and stores the three bf16
  *     operands straight into the K-major, un-swizzled core-matrix layout of a tcgen05 shared-memory descriptor
  *     (core matrix = 8 rows x 16 bytes; a thread's 16 bytes of one K-chunk sit at  chunk * 2048 + r * 16, so a warp's
  *     128-bit stores are contiguous: no bank conflicts, no swizzle needed);
- *   - the group's first thread issues the split products as  tcgen05.mma.cta_group::1.kind::f16  (M = 128, N = 64,
+ *   - the group's first warp, converged, issues the split products (an elected lane per instruction) as
+ *     tcgen05.mma.cta_group::1.kind::f16  (M = 128, N = 64,
  *     K = 16 per instruction; 12 for the first layer, 27 / 30 for the second) into a 128-lane x 64-column fp32
  *     accumulator in tensor memory and commits them to the group's mbarrier.  The biases ride in the products: input
  *     column 28 (71 in the critic) is the constant 1 and the matching weight row holds the bias; the actor's second
