@@ -23,6 +23,10 @@ ref = json.load(open(os.path.join(G, "batch_test_reference.json")))
 tabs = np.load(os.path.join(G, "batch_test_tables.npz"))
 w = ActorWeights.from_npz(os.path.join(G, "actor_agent1.npz"))
 dens = list(evaluate.DENSITIES)
+torch.zeros(1, device="cuda").item()          # the CUDA context exists before the clock starts
+from pve_mcc_for_unsignalized_intersection_b200.actor import BatchedActor  # noqa: E402
+BatchedActor(w).close()                        # ... and the library is loaded
+torch.cuda.synchronize()
 t0 = time.perf_counter()
 res = evaluate.evaluate_tables([tabs["d%d" % d] for d in dens], w, ticks=36000, veh_cap=192, agent_cap=128)
 torch.cuda.synchronize()
